@@ -1,0 +1,484 @@
+/*
+ * TEST INFRASTRUCTURE -- CPU oracle for the LIRA query phase and ground-truth path.
+ *
+ * This is a plain-C restatement of what the reference computes on the hot path. It is the
+ * CHECKER for the CUDA library, never the product: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it. Nothing under
+ * lira-ann-search_b200/ links, imports or calls it.
+ *
+ * Pinning status: the reference ships no golden vectors or unit tests.
+ *   - The C++ twin of the query phase (search.cpp) IS compiled unmodified into
+ *     oracle/_ref/search_ref and tests/test_oracle_vs_ref.py checks this file against its
+ *     per-threshold recall / nprobe / cmp output, and tests/golden/ holds outputs produced
+ *     by importing the reference's own Python (utils.py, LIRA_smallscale.py,
+ *     model_probing.py) -- see oracle/make_golden.py.
+ *   - The per-list arithmetic itself lives in Faiss 1.9.0 (requirements.txt:6), a
+ *     third-party dependency that is NOT in /root/reference and not installable here.
+ *     IndexFlat::search is restated below from its published algorithm; that part of the
+ *     parity is "unpinned by Faiss itself" and anchored on the reference's call sites
+ *     (LIRA_smallscale.py:168-171, utils.py:293-310, compute_knn.cpp:233-259).
+ *
+ * Each function cites the reference lines it follows.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------ */
+/* helpers                                                                              */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    double key; /* smaller is better */
+    int64_t id; /* tie-break: smaller id first */
+} cand_t;
+
+static inline int cand_less(const cand_t* a, const cand_t* b) {
+    if (a->key < b->key) return 1;
+    if (a->key > b->key) return 0;
+    return a->id < b->id;
+}
+
+/* Keep the k best of a stream in a sorted array (ascending by (key,id)). This reproduces
+ * Faiss' heap result handler for k < 100 as seen from outside: a candidate enters only if
+ * strictly better than the current worst, equal keys are reported in ascending id
+ * (faiss/utils/Heap.h heap_reorder).  Because candidates arrive in
+ * ascending id inside one list, "strictly better than the worst" and "(key,id) lexicographic"
+ * select the same set. */
+static inline void topk_push(cand_t* best, int* n, int k, double key, int64_t id) {
+    cand_t c = {key, id};
+    if (*n == k) {
+        if (!cand_less(&c, &best[k - 1])) return;
+    } else {
+        (*n)++;
+    }
+    int i = *n - 1;
+    while (i > 0 && cand_less(&c, &best[i - 1])) {
+        best[i] = best[i - 1];
+        --i;
+    }
+    best[i] = c;
+}
+
+static inline int cmp_cand(const void* a, const void* b) {
+    const cand_t* x = (const cand_t*)a;
+    const cand_t* y = (const cand_t*)b;
+    if (cand_less(x, y)) return -1;
+    if (cand_less(y, x)) return 1;
+    return 0;
+}
+
+/* direct-difference squared L2, sequential fp32 accumulation: search.cpp:253-260 (l2_sq) */
+static inline float l2sq_f32(const float* a, const float* b, long d) {
+    float s = 0.0f;
+    for (long j = 0; j < d; ++j) {
+        float diff = a[j] - b[j];
+        s += diff * diff;
+    }
+    return s;
+}
+/* inner product, sequential fp32: search.cpp:263-269 (ip) */
+static inline float ip_f32(const float* a, const float* b, long d) {
+    float s = 0.0f;
+    for (long j = 0; j < d; ++j) s += a[j] * b[j];
+    return s;
+}
+static inline double l2sq_f64(const float* a, const float* b, long d) {
+    double s = 0.0;
+    for (long j = 0; j < d; ++j) {
+        double diff = (double)a[j] - (double)b[j];
+        s += diff * diff;
+    }
+    return s;
+}
+static inline double ip_f64(const float* a, const float* b, long d) {
+    double s = 0.0;
+    for (long j = 0; j < d; ++j) s += (double)a[j] * (double)b[j];
+    return s;
+}
+
+/* metric: 0 = L2 (squared, no sqrt), 1 = inner product (bigger is better).
+ * prec:   0 = fp32 sequential (reference C++ arithmetic), 1 = fp64 (arbiter).
+ * returns the "smaller is better" key (L2sq or -IP) */
+static inline double pair_key(const float* q, const float* v, long d, int metric, int prec) {
+    if (metric == 0) return prec ? l2sq_f64(q, v, d) : (double)l2sq_f32(q, v, d);
+    return prec ? -ip_f64(q, v, d) : -(double)ip_f32(q, v, d);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a1/a2: centroid-distance features                                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* C++ twin: search.cpp:220-235 (compute_l2_to_centroids: fp32 loop + sqrtf) followed by
+ * search.cpp:238-250 (standardize_distances: (d-mean)/scale, scale==0 -> 1). */
+ORACLE_API void oracle_features_cpp(const float* q, long Q, const float* cent, long B, long d,
+                                    const float* mean, const float* scale, float* out) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < Q; ++i) {
+        for (long c = 0; c < B; ++c) {
+            float dist = sqrtf(l2sq_f32(q + i * d, cent + c * d, d));
+            if (mean) {
+                float s = scale[c];
+                if (s == 0.0f) s = 1.0f;
+                dist = (dist - mean[c]) / s;
+            }
+            out[i * B + c] = dist;
+        }
+    }
+}
+
+/* Python twin: utils.py:98-118 get_dist_cid -- scipy cdist(..., 'euclidean') evaluates
+ * sqrt(sum((a-b)^2)) in fp64 and the result is cast to fp32 (utils.py:115). With
+ * mean64/scale64 non-NULL it then applies sklearn StandardScaler.transform on the fp32
+ * matrix (utils.py:142-143, 162, 167): in-place X -= mean_ ; X /= scale_ with fp64
+ * operands, i.e. each step is computed in fp64 and rounded back to fp32. */
+ORACLE_API void oracle_features_py(const float* x, long n, const float* cent, long B, long d,
+                                   const double* mean64, const double* scale64, float* out) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        for (long c = 0; c < B; ++c) {
+            float dist = (float)sqrt(l2sq_f64(x + i * d, cent + c * d, d));
+            if (mean64) {
+                dist = (float)((double)dist - mean64[c]);
+                dist = (float)((double)dist / scale64[c]);
+            }
+            out[i * B + c] = dist;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a3: probing model forward (model_probing.py:5-39)                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* y = W x + b with W[out,in] row-major (torch nn.Linear layout), fp64 accumulation. */
+static void linear_f64(const double* x, long in, const float* W, const float* b, long out,
+                       double* y, int relu) {
+    for (long o = 0; o < out; ++o) {
+        double s = b ? (double)b[o] : 0.0;
+        const float* w = W + o * in;
+        for (long j = 0; j < in; ++j) s += (double)w[j] * x[j];
+        y[o] = (relu && s < 0.0) ? 0.0 : s;
+    }
+}
+
+/* weights: W1[128,B] b1[128] W2[64,128] b2[64]   (distance_net, model_probing.py:12-17)
+ *          W3[128,d] b3[128] W4[64,128] b4[64]   (vector_net,   model_probing.py:19-24)
+ *          W5[128,128] b5[128] W6[Bout,128] b6[Bout] (fc,        model_probing.py:26-31)
+ * forward: model_probing.py:33-39 (cat(out_dist, out_vec) -> fc -> sigmoid).
+ * Evaluated in fp64 from fp32 inputs/weights: the arbiter, not a bit-twin of cuBLAS/MKL.
+ * logits_out / probs_out: [n, Bout] fp64; h_out (optional): last hidden activation [n,128]. */
+ORACLE_API void oracle_mlp_forward(const float* x_dist, const float* x_vec, long n, long B, long d,
+                                   long Bout, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, const float* W3, const float* b3,
+                                   const float* W4, const float* b4, const float* W5,
+                                   const float* b5, const float* W6, const float* b6,
+                                   double* logits_out, double* probs_out, double* h_out) {
+#pragma omp parallel
+    {
+        double* xin = (double*)malloc(sizeof(double) * (size_t)(B > d ? B : d));
+        double h1[128], h2[128], cat[128], h5[128];
+        double* lg = (double*)malloc(sizeof(double) * (size_t)Bout);
+#pragma omp for schedule(static)
+        for (long i = 0; i < n; ++i) {
+            for (long j = 0; j < B; ++j) xin[j] = (double)x_dist[i * B + j];
+            linear_f64(xin, B, W1, b1, 128, h1, 1);
+            linear_f64(h1, 128, W2, b2, 64, cat, 1);
+            for (long j = 0; j < d; ++j) xin[j] = (double)x_vec[i * d + j];
+            linear_f64(xin, d, W3, b3, 128, h2, 1);
+            linear_f64(h2, 128, W4, b4, 64, cat + 64, 1);
+            linear_f64(cat, 128, W5, b5, 128, h5, 1);
+            linear_f64(h5, 128, W6, b6, Bout, lg, 0);
+            for (long o = 0; o < Bout; ++o) {
+                if (logits_out) logits_out[i * Bout + o] = lg[o];
+                if (probs_out) probs_out[i * Bout + o] = 1.0 / (1.0 + exp(-lg[o]));
+            }
+            if (h_out)
+                for (long j = 0; j < 128; ++j) h_out[i * 128 + j] = h5[j];
+        }
+        free(xin);
+        free(lg);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a5: partition selection                                                              */
+/* ------------------------------------------------------------------------------------ */
+
+/* mode 0: Python   -- scores[q,b] >  thr            (LIRA_smallscale.py:206, LIRA_largescale.py:163)
+ * mode 1: C++      -- scores[q,b] >= thr, and if none: argmax (first max) (search.cpp:448-466)
+ * mode 2: top-n    -- the nprobe = (int)value best scores, ties to the lower partition id
+ *                     (utils.py:512 all_outputs[q].topk(probeM)); ids emitted best-first.
+ * scores are fp32 (model output). thr is passed as double: Python compares the fp32 score
+ * with a float64 np.arange value; for mode 1 pass (double)(float)thr.
+ * probe_offsets[Q+1], probe_ids[capacity Q*B] are written; returns total count. */
+ORACLE_API long oracle_select(const float* scores, long Q, long B, int mode, double value,
+                              long* probe_offsets, int* probe_ids) {
+    long total = 0;
+    probe_offsets[0] = 0;
+    for (long q = 0; q < Q; ++q) {
+        const float* s = scores + q * B;
+        if (mode == 0 || mode == 1) {
+            long before = total;
+            for (long b = 0; b < B; ++b) {
+                int hit = (mode == 0) ? ((double)s[b] > value) : ((double)s[b] >= value);
+                if (hit) probe_ids[total++] = (int)b;
+            }
+            if (mode == 1 && total == before) {
+                long best = 0;
+                for (long b = 1; b < B; ++b)
+                    if (s[b] > s[best]) best = b;
+                probe_ids[total++] = (int)best;
+            }
+        } else {
+            long np_ = (long)value;
+            if (np_ > B) np_ = B;
+            cand_t* best = (cand_t*)malloc(sizeof(cand_t) * (size_t)(np_ > 0 ? np_ : 1));
+            int nb = 0;
+            for (long b = 0; b < B; ++b) topk_push(best, &nb, (int)np_, -(double)s[b], b);
+            for (int i = 0; i < nb; ++i) probe_ids[total++] = (int)best[i].id;
+            free(best);
+        }
+        probe_offsets[q + 1] = total;
+    }
+    return total;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a6/a7: per-list flat index search (Faiss IndexFlat semantics, restated)              */
+/* ------------------------------------------------------------------------------------ */
+
+/* One "IndexFlatL2/IP.search(q[nq,d], k)" on a list of n_b vectors stored contiguously
+ * (utils.py:407-422 builds it with x_d[ids]; LIRA_smallscale.py:168 calls it with nq=1).
+ * Published Faiss behaviour restated: exact squared L2 (no sqrt)
+ * or inner product; results best-first; labels are LOCAL positions in the list; when the
+ * list holds fewer than k vectors the tail is label -1 with distance +inf (L2) / -inf (IP);
+ * at equal distance the lower position wins.
+ * D: [nq,k] fp32 (the metric value: L2sq or IP, NOT the negated key), I: [nq,k] int64. */
+ORACLE_API void oracle_list_search(const float* list_vecs, long n_b, long d, const float* q,
+                                   long nq, int k, int metric, int prec, float* D, int64_t* I) {
+#pragma omp parallel
+    {
+        cand_t* best = (cand_t*)malloc(sizeof(cand_t) * (size_t)k);
+#pragma omp for schedule(static)
+        for (long qi = 0; qi < nq; ++qi) {
+            int nb = 0;
+            for (long i = 0; i < n_b; ++i)
+                topk_push(best, &nb, k, pair_key(q + qi * d, list_vecs + i * d, d, metric, prec), i);
+            for (int j = 0; j < k; ++j) {
+                if (j < nb) {
+                    D[qi * k + j] = (float)(metric == 0 ? best[j].key : -best[j].key);
+                    I[qi * k + j] = best[j].id;
+                } else {
+                    D[qi * k + j] = metric == 0 ? INFINITY : -INFINITY;
+                    I[qi * k + j] = -1;
+                }
+            }
+        }
+        free(best);
+    }
+}
+
+/* get_cmp_recall (LIRA_smallscale.py:145-174 / LIRA_largescale.py:120-149): for EVERY
+ * (query, list) pair the top-k inside the list, mapped to global ids through
+ * list_ids (== np.array(cluster_ids[b])). CSR index: list_offsets[B+1], list_ids[E],
+ * list_vecs[E,d]. found[Q,B,k] int64 is pre-filled with -1 by the caller semantics
+ * (np.full(...,-1), :154); cmp[Q,B] = list size (:171); empty lists are skipped (:161).
+ * Reference quirk reproduced: for a non-empty list shorter than k
+ * Faiss returns label -1, and xd_id_bid[-1] (:169) maps it to the LAST id of the list. */
+ORACLE_API void oracle_scan_all_pairs(const long* list_offsets, const int* list_ids,
+                                      const float* list_vecs, long B, long d, const float* q,
+                                      long Q, int k, int metric, int prec, int64_t* found,
+                                      int64_t* cmp) {
+#pragma omp parallel
+    {
+        cand_t* best = (cand_t*)malloc(sizeof(cand_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 8) collapse(1)
+        for (long qi = 0; qi < Q; ++qi) {
+            for (long b = 0; b < B; ++b) {
+                long lo = list_offsets[b], hi = list_offsets[b + 1];
+                int64_t* out = found + (qi * B + b) * k;
+                if (hi == lo) {
+                    for (int j = 0; j < k; ++j) out[j] = -1;
+                    cmp[qi * B + b] = 0;
+                    continue;
+                }
+                int nb = 0;
+                for (long i = lo; i < hi; ++i)
+                    topk_push(best, &nb, k, pair_key(q + qi * d, list_vecs + i * d, d, metric, prec),
+                              i - lo);
+                for (int j = 0; j < k; ++j)
+                    out[j] = (j < nb) ? list_ids[lo + best[j].id] : list_ids[hi - 1];
+                cmp[qi * B + b] = hi - lo;
+            }
+        }
+        free(best);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a10: the online query path (search.cpp:468-514)                                      */
+/* ------------------------------------------------------------------------------------ */
+
+/* For each query: scan its probed lists, score = L2sq or -IP (search.cpp:480-492), global
+ * top-k of (score, gid).
+ * dedup = 1 (north-star / Python recall semantics, LIRA_smallscale.py:210-214): an id that
+ *           sits in several probed lists (learned redundancy) counts once, BEFORE selection.
+ * dedup = 0 (search.cpp:499-513 as shipped): select k pairs first, then collapse equal ids,
+ *           so duplicates can occupy slots; the result may hold fewer than k distinct ids.
+ * Order among equal scores: (score, gid) ascending (std::nth_element leaves this
+ * unspecified; a deterministic rule is needed for a checker).
+ * out_ids[Q,k] int64 (-1 padded), out_dist[Q,k] fp32 metric value (+/-inf padded),
+ * out_cmp[Q] = sum of probed list sizes (search.cpp:477). */
+ORACLE_API void oracle_search(const long* list_offsets, const int* list_ids, const float* list_vecs,
+                              long B, long d, const float* q, long Q, const long* probe_offsets,
+                              const int* probe_ids, int k, int metric, int prec, int dedup,
+                              int64_t* out_ids, float* out_dist, int64_t* out_cmp) {
+    (void)B;
+#pragma omp parallel
+    {
+        cand_t* cand = NULL;
+        size_t cap = 0;
+#pragma omp for schedule(dynamic, 4)
+        for (long qi = 0; qi < Q; ++qi) {
+            size_t n = 0;
+            for (long p = probe_offsets[qi]; p < probe_offsets[qi + 1]; ++p) {
+                int b = probe_ids[p];
+                n += (size_t)(list_offsets[b + 1] - list_offsets[b]);
+            }
+            if (n > cap) {
+                free(cand);
+                cap = n + n / 2 + 16;
+                cand = (cand_t*)malloc(sizeof(cand_t) * cap);
+            }
+            size_t m = 0;
+            for (long p = probe_offsets[qi]; p < probe_offsets[qi + 1]; ++p) {
+                int b = probe_ids[p];
+                for (long i = list_offsets[b]; i < list_offsets[b + 1]; ++i) {
+                    cand[m].key = pair_key(q + qi * d, list_vecs + i * d, d, metric, prec);
+                    cand[m].id = list_ids[i];
+                    ++m;
+                }
+            }
+            if (out_cmp) out_cmp[qi] = (int64_t)n;
+            qsort(cand, m, sizeof(cand_t), cmp_cand);
+            int w = 0;
+            if (dedup) {
+                for (size_t i = 0; i < m && w < k; ++i) {
+                    int dup = 0;
+                    for (int j = 0; j < w; ++j)
+                        if (out_ids[qi * k + j] == cand[i].id) { dup = 1; break; }
+                    if (dup) continue;
+                    out_ids[qi * k + w] = cand[i].id;
+                    out_dist[qi * k + w] = (float)(metric == 0 ? cand[i].key : -cand[i].key);
+                    ++w;
+                }
+            } else {
+                size_t top = m < (size_t)k ? m : (size_t)k;
+                for (size_t i = 0; i < top; ++i) {
+                    int dup = 0;
+                    for (int j = 0; j < w; ++j)
+                        if (out_ids[qi * k + j] == cand[i].id) { dup = 1; break; }
+                    if (dup) continue;
+                    out_ids[qi * k + w] = cand[i].id;
+                    out_dist[qi * k + w] = (float)(metric == 0 ? cand[i].key : -cand[i].key);
+                    ++w;
+                }
+            }
+            for (; w < k; ++w) {
+                out_ids[qi * k + w] = -1;
+                out_dist[qi * k + w] = metric == 0 ? INFINITY : -INFINITY;
+            }
+        }
+        free(cand);
+    }
+}
+
+/* recall@k as search.cpp:520-528: |gt[q,:k] n result[q]| / k, mean over queries. */
+ORACLE_API double oracle_recall(const int64_t* ids, long Q, int k, const int* gt, long gt_dim) {
+    double sum = 0.0;
+    for (long qi = 0; qi < Q; ++qi) {
+        int hit = 0;
+        for (int j = 0; j < k; ++j) {
+            int g = gt[qi * gt_dim + j];
+            for (int t = 0; t < k; ++t)
+                if (ids[qi * k + t] == g) { hit++; break; }
+        }
+        sum += (double)hit / (double)k;
+    }
+    return Q ? sum / (double)Q : 0.0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a11: exact kNN (compute_knn.cpp:208-259, utils.py:293-310, LIRA_largescale.py:221-231) */
+/* ------------------------------------------------------------------------------------ */
+
+/* Exact top-k of every query row against all base rows.
+ * form 0: direct difference, precision per `prec`.
+ * form 1: Faiss BLAS form for nx >= 20: |x|^2 + |y|^2 - 2 x.y in fp32,
+ *         negatives clamped to 0 (metric L2 only).
+ * Result best-first, ties to the lower base id (heap path, k < 100; the k >= 100 reservoir
+ * path of Faiss has unspecified tie order, the checker uses the same rule and tests compare
+ * modulo ties). The caller drops column 0 for self-kNN as compute_knn.cpp:254-259 does. */
+ORACLE_API void oracle_knn(const float* base, long N, const float* query, long Q, long d, int k,
+                           int metric, int prec, int form, float* D, int64_t* I) {
+    float* bn = NULL;
+    if (form == 1) {
+        bn = (float*)malloc(sizeof(float) * (size_t)N);
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < N; ++i) bn[i] = ip_f32(base + i * d, base + i * d, d);
+    }
+#pragma omp parallel
+    {
+        cand_t* best = (cand_t*)malloc(sizeof(cand_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 4)
+        for (long qi = 0; qi < Q; ++qi) {
+            const float* qv = query + qi * d;
+            int nb = 0;
+            float qn = form == 1 ? ip_f32(qv, qv, d) : 0.0f;
+            for (long i = 0; i < N; ++i) {
+                double key;
+                if (form == 1 && metric == 0) {
+                    float v = qn + bn[i] - 2.0f * ip_f32(qv, base + i * d, d);
+                    key = v < 0.0f ? 0.0 : (double)v;
+                } else {
+                    key = pair_key(qv, base + i * d, d, metric, prec);
+                }
+                topk_push(best, &nb, k, key, i);
+            }
+            for (int j = 0; j < k; ++j) {
+                if (j < nb) {
+                    D[qi * k + j] = (float)(metric == 0 ? best[j].key : -best[j].key);
+                    I[qi * k + j] = best[j].id;
+                } else {
+                    D[qi * k + j] = metric == 0 ? INFINITY : -INFINITY;
+                    I[qi * k + j] = -1;
+                }
+            }
+        }
+        free(best);
+    }
+    free(bn);
+}
+
+ORACLE_API int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+ORACLE_API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
