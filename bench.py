@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of the LIRA query phase at recall@10 >= 0.95 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU search.cpp
+
+Workload (config.workload = "sift1m-shape"): BASELINE.json configs[0] -- 1M x 128 fp32 integer-valued
+Gaussian-mixture base ("SIFT1M-shape", synthetic: no datasets on the box), 10k queries, B = 1024 K-Means
+partitions, LIRA probing model trained here with the reference loop shape (BCELoss + Adam), 3 % learned
+redundancy (n_mul = 2), k = 10, L2. One step = the whole query phase for the 10k-query batch:
+centroid features -> MLP -> threshold select -> grouped list scan -> dedup merge.
+
+N > 1: the inverted lists are striped across the ranks (entry j of every list -> rank j mod N), every
+rank answers all queries on its stripe, per-rank top-k lists are all-gathered over NCCL and merged
+with id de-duplication (strong scaling of the same workload).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CACHE = os.environ.get("LIRA_BENCH_CACHE", "/tmp/lira_bench_cache")
+SEED = 43
+
+
+# ---------------------------------------------------------------------------------------------
+# workload construction (untimed; torch on the GPU is build-side plumbing here)
+# ---------------------------------------------------------------------------------------------
+def make_workload(N=1_000_000, d=128, Q=10_000, B=1024, k=10, redundancy_ratio=0.03, dev="cuda:0", log=print):
+    import torch
+    tag = f"sift1m_N{N}_d{d}_Q{Q}_B{B}_k{k}_r{redundancy_ratio}_s{SEED}_v3"
+    path = os.path.join(CACHE, tag)
+    names = ["x_d", "x_q", "gt", "centroids", "scaler_mean", "scaler_scale", "data_2_bkt"] + [f"mlp_{i}" for i in range(12)]
+    if all(os.path.exists(os.path.join(path, n + ".npy")) for n in names):
+        log(f"[bench] workload cache hit: {path}")
+        return {n: np.load(os.path.join(path, n + ".npy")) for n in names}, path
+    t0 = time.time()
+    g = torch.Generator(device=dev).manual_seed(SEED * 1_000_003)
+    ncomp = 4096
+    centres = torch.randn(ncomp, d, generator=g, device=dev)
+    w = torch.exp(0.5 * torch.randn(ncomp, generator=g, device=dev))
+
+    def draw(m):
+        c = torch.multinomial(w, m, replacement=True, generator=g)
+        x = centres[c] + 0.8 * torch.randn(m, d, generator=g, device=dev)
+        return torch.clamp(torch.round(16 * x + 100), 0, 255)
+
+    x_d = draw(N)
+    x_q = draw(Q)
+
+    def knn_torch(qs, kk, exclude_self_from=None):
+        out = torch.empty(qs.shape[0], kk, dtype=torch.int64, device=dev)
+        bn = (x_d * x_d).sum(1)
+        for a in range(0, qs.shape[0], 2048):
+            qb = qs[a:a + 2048]
+            dist = bn[None, :] - 2.0 * qb @ x_d.T  # + |q|^2, constant per row (integer data: exact in fp32)
+            out[a:a + 2048] = dist.topk(kk, largest=False).indices
+        return out
+
+    gt = knn_torch(x_q, 100)
+    log(f"[bench] data + ground truth: {time.time() - t0:.1f}s")
+
+    # K-Means (build side; utils.build_kmeans_index shape)
+    from lira_ann_search_b200.utils import Kmeans
+    km = Kmeans(d, B, niter=20, device=dev).train(x_d.cpu().numpy())
+    cent = torch.as_tensor(km.centroids, device=dev)
+    assign = Kmeans.assign(x_d, cent)
+    log(f"[bench] kmeans: {time.time() - t0:.1f}s")
+
+    # training set: a 10 % sample of base points with their exact 10-NN (labels: partitions holding a kNN)
+    n_tr = min(N, 100_000)
+    tr_idx = torch.randperm(N, generator=torch.Generator().manual_seed(SEED))[:n_tr].to(dev)
+    knn_tr = knn_torch(x_d[tr_idx], k + 1)[:, 1:]
+    labels = torch.zeros(n_tr, B, device=dev)
+    labels.scatter_(1, assign[knn_tr], 1.0)
+
+    def feats_of(x):
+        return torch.cdist(x, cent)
+
+    f_all_mean = torch.zeros(B, dtype=torch.float64, device=dev)
+    f_all_sq = torch.zeros(B, dtype=torch.float64, device=dev)
+    for a in range(0, N, 65536):
+        f = feats_of(x_d[a:a + 65536]).double()
+        f_all_mean += f.sum(0)
+        f_all_sq += (f * f).sum(0)
+    mean = f_all_mean / N
+    scale = torch.sqrt(torch.clamp(f_all_sq / N - mean * mean, min=0))
+    scale[scale == 0] = 1.0
+    mean32, scale32 = mean.float(), scale.float()
+
+    from lira_ann_search_b200.model_probing import MLP_2_Input
+    torch.manual_seed(SEED)
+    model = MLP_2_Input(B, d, B).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.BCELoss()
+    xf = (feats_of(x_d[tr_idx]) - mean32) / scale32
+    xv = x_d[tr_idx]
+    for epoch in range(8):
+        perm = torch.randperm(n_tr, device=dev)
+        for a in range(0, n_tr, 512):
+            idx = perm[a:a + 512]
+            opt.zero_grad()
+            loss = crit(model(xf[idx], xv[idx]), labels[idx])
+            loss.backward()
+            opt.step()
+    log(f"[bench] probing model trained (last loss {loss.item():.4f}): {time.time() - t0:.1f}s")
+
+    # learned redundancy, n_mul = 2 (LIRA_smallscale.py:77-97, 331-354): the redundancy_ratio fraction of
+    # points with the largest predicted nprobe get a second partition chosen by the model
+    model.eval()
+    npred = torch.empty(N, device=dev)
+    top2 = torch.empty(N, 2, dtype=torch.int64, device=dev)
+    neff = torch.empty(N, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        for a in range(0, N, 65536):
+            xb = x_d[a:a + 65536]
+            s = model((feats_of(xb) - mean32) / scale32, xb)
+            neff[a:a + 65536] = (s > 0.5).sum(1)
+            top2[a:a + 65536] = s.topk(2).indices
+    order = torch.argsort(neff, descending=True, stable=True)[:int(N * redundancy_ratio)]
+    d2b = torch.full((N, 2), -1, dtype=torch.int64, device=dev)
+    d2b[:, 0] = assign
+    cur = assign[order]
+    t1, t2 = top2[order, 0], top2[order, 1]
+    second = torch.where(cur != t1, t1, torch.where(neff[order] > 1, t2, torch.full_like(t1, -1)))
+    second = torch.where(neff[order] > 0, second, torch.full_like(second, -1))
+    d2b[order, 1] = second
+    log(f"[bench] redundancy: {int((second >= 0).sum())} second copies: {time.time() - t0:.1f}s")
+
+    sd = model.state_dict()
+    out = {"x_d": x_d.cpu().numpy().astype(np.float32), "x_q": x_q.cpu().numpy().astype(np.float32),
+           "gt": gt.cpu().numpy().astype(np.int32), "centroids": km.centroids.astype(np.float32),
+           "scaler_mean": mean32.cpu().numpy(), "scaler_scale": scale32.cpu().numpy(),
+           "data_2_bkt": d2b.cpu().numpy().astype(np.int32)}
+    keys = ("distance_net.0", "distance_net.2", "vector_net.0", "vector_net.2", "fc.0", "fc.2")
+    i = 0
+    for kk in keys:
+        out[f"mlp_{i}"] = sd[kk + ".weight"].float().cpu().numpy(); i += 1
+        out[f"mlp_{i}"] = sd[kk + ".bias"].float().cpu().numpy(); i += 1
+    os.makedirs(path, exist_ok=True)
+    for n, v in out.items():
+        np.save(os.path.join(path, n + ".npy"), v)
+    del x_d, model
+    torch.cuda.empty_cache()
+    return out, path
+
+
+def recall_at(ids, gt, k):
+    hit = (gt[:, :k, None] == ids[:, None, :k]).any(-1)
+    return float(hit.sum(1).mean() / k)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU search.cpp (oracle/_ref/search_ref), else the oracle port
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, wl, wl_path, thr, log):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    n_sample = int(os.environ.get("LIRA_REF_SAMPLE", "1000"))
+    k = args.k
+    exe = os.path.join(ROOT, "oracle", "_ref", "search_ref")
+    cores = os.cpu_count() or 1
+    passes = args.warmup + args.steps
+    if os.path.exists(exe):
+        from lira_ann_search_b200.model_probing import MLP_2_Input
+        from lira_ann_search_b200.utils import write_xvecs
+        with tempfile.TemporaryDirectory() as td:
+            pfx = os.path.join(td, "bench")
+            np.save(pfx + "_centroids.npy", wl["centroids"])
+            np.save(pfx + "_data_2_bkt.npy", wl["data_2_bkt"])
+            np.save(pfx + "_x_d.npy", wl["x_d"])
+            np.save(pfx + "_scaler_mean.npy", wl["scaler_mean"])
+            np.save(pfx + "_scaler_scale.npy", wl["scaler_scale"])
+            B, d = wl["centroids"].shape
+            model = MLP_2_Input(B, d, B)
+            keys = ("distance_net.0", "distance_net.2", "vector_net.0", "vector_net.2", "fc.0", "fc.2")
+            sd = {}
+            for i, kk in enumerate(keys):
+                sd[kk + ".weight"] = torch.as_tensor(wl[f"mlp_{2 * i}"])
+                sd[kk + ".bias"] = torch.as_tensor(wl[f"mlp_{2 * i + 1}"])
+            model.load_state_dict(sd)
+            torch.jit.save(torch.jit.script(model.eval()), pfx + "_mlp_2_input.pt")
+            ds = os.path.join(td, "data", "bench")
+            os.makedirs(ds)
+            write_xvecs(os.path.join(ds, "bench_query.fvecs"), wl["x_q"][:n_sample])
+            write_xvecs(os.path.join(ds, "bench_groundtruth.ivecs"), wl["gt"][:n_sample])
+            # one process, `passes` thresholds 1e-7 apart: the artifacts load once, every pass is one step
+            step = 1e-7
+            cmd = [exe, "--dataset", "bench", "--data_path", os.path.join(td, "data"), "--artifacts_dir", td,
+                   "--prefix", "bench", "--k", str(k), "--metric", "L2", "--num_threads", str(cores),
+                   "--t_min", repr(thr), "--t_max", repr(thr + step * (passes - 1) + step / 4), "--t_step", repr(step)]
+            t0 = time.time()
+            txt = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+            log(f"[bench] reference search.cpp ran in {time.time() - t0:.1f}s")
+        import re
+        qps = [float(x) for x in re.findall(r"QPS\s*:\s*([-+0-9.eE]+)", txt)]
+        rec = [float(x) for x in re.findall(r"avg_recall\s*:\s*([-+0-9.eE]+)", txt)]
+        qps, rec = qps[args.warmup:], rec[args.warmup:]
+        value = float(np.mean(qps))
+        kind, used = "reference", 1  # search.cpp has no OpenMP pragma: one thread per query by construction
+        sample = f"first {n_sample} of {len(wl['x_q'])} queries, threshold {thr:g}, recall@{k} {np.mean(rec):.4f}"
+    else:
+        import oracle as O
+        off, ids, vecs = O.build_lists_from_data_2_bkt(wl["x_d"], wl["data_2_bkt"], wl["centroids"].shape[0])
+        w = [wl[f"mlp_{i}"] for i in range(12)]
+        q = wl["x_q"][:n_sample]
+        times = []
+        for _ in range(passes):
+            t0 = time.perf_counter()
+            f = O.features_cpp(q, wl["centroids"], wl["scaler_mean"], wl["scaler_scale"])
+            _, probs, _ = O.mlp_forward(f, q, w)
+            poff, pids = O.select(probs.astype(np.float32), O.SELECT_GE_ARGMAX, thr)
+            out_ids, _, _ = O.search(off, ids, vecs, q, poff, pids, k, O.L2, O.F32, 1)
+            times.append(time.perf_counter() - t0)
+        value = n_sample / float(np.mean(times[args.warmup:]))
+        kind, used = "port", O.num_threads()
+        sample = f"first {n_sample} queries, threshold {thr:g}, recall@{k} {recall_at(out_ids, wl['gt'][:n_sample], k):.4f}"
+    line = {"metric": "qps_at_recall10_ge_0.95", "value": value, "unit": "queries/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / value,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "sift1m-shape", "N": int(wl["x_d"].shape[0]), "d": int(wl["x_d"].shape[1]),
+                       "Q": int(len(wl["x_q"])), "B": int(wl["centroids"].shape[0]), "k": k, "threshold": thr},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": used, "kind": kind, "sample": sample,
+                             "host_cores": cores},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--N", type=int, default=1_000_000)
+    ap.add_argument("--Q", type=int, default=10_000)
+    ap.add_argument("--B", type=int, default=1024)
+    ap.add_argument("--recall", type=float, default=0.95)
+    ap.add_argument("--cpu-sample", type=int, default=2000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
+    if args.impl == "reference" and rank != 0:
+        return
+
+    import torch
+    import lira_ann_search_b200 as L
+    L._cabi.require_gpu()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1 and args.impl == "b200":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    # rank 0 builds (or loads) the workload, the others wait and load the cache
+    if rank == 0:
+        wl, wl_path = make_workload(args.N, 128, args.Q, args.B, args.k, dev=dev, log=log)
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        wl, wl_path = make_workload(args.N, 128, args.Q, args.B, args.k, dev=dev, log=log)
+    N, d = wl["x_d"].shape
+    Q, B, k = len(wl["x_q"]), wl["centroids"].shape[0], args.k
+    weights = [wl[f"mlp_{i}"] for i in range(12)]
+
+    # ---- index (striped across ranks when world > 1) and model --------------------------------
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    d2b = wl["data_2_bkt"]
+    if world > 1:
+        from lira_ann_search_b200.parallel import stripe_assignment
+        d2b = stripe_assignment(d2b, B, rank, world)
+    index = L.LiraIndex.from_data_2_bkt(wl["x_d"], d2b, B, "L2", device=local)
+    model = L.LiraModel.from_arrays(wl["centroids"], wl["scaler_mean"], wl["scaler_scale"], weights, device=local)
+    d_q = torch.as_tensor(wl["x_q"], device=dev)
+    gt = wl["gt"]
+
+    def gather_merge(D, I):
+        if dist is None:
+            return D, I
+        from lira_ann_search_b200.parallel import allgather_merge
+        return allgather_merge(D, I, k, "L2", dedup=True, device=local)
+
+    # ---- operating point: the largest threshold (fewest probes) with recall@10 >= target -------
+    scores = torch.empty((Q, (B + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    h_scores = model.scores(wl["x_q"])
+    scores[:, :B] = torch.as_tensor(h_scores, device=dev)
+    best = None
+    sweep = []
+    for thr in [round(0.02 * i, 2) for i in range(40, 0, -1)]:
+        D, I, npb, cmp_ = index.select_search_dev(scores, d_q, L.SELECT_GT, thr, k, True)
+        D, I = gather_merge(D, I)
+        torch.cuda.synchronize()
+        rec = recall_at(I.cpu().numpy(), gt, k)
+        sweep.append((thr, rec, float(npb.float().mean())))
+        if rec >= args.recall:
+            best = (thr, rec, float(npb.float().mean()), float(cmp_.float().mean()))
+            break
+    if best is None:
+        best = (0.02, sweep[-1][1], sweep[-1][2], 0.0)
+        log(f"[bench] WARNING: recall target {args.recall} not reached by threshold 0.02 (recall {best[1]:.4f})")
+    thr = best[0]
+    log(f"[bench] operating point: threshold {thr} recall@{k} {best[1]:.4f} nprobe {best[2]:.2f}")
+
+    if args.impl == "reference":
+        run_reference(args, wl, wl_path, thr, log)
+        return
+
+    # ---- timed region ------------------------------------------------------------------------
+    out = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    index.set_timing(True)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        nonlocal out
+        out = index.probe_search_dev(model, d_q, L.SELECT_GT, thr, k, True, out=out)
+        return gather_merge(out[0], out[1])
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    launches0 = L.launch_count()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    scan_ms, scan_bytes, scan_pairs = [], [], []
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+        ev[i][0].record(stream)
+        D, I = step()
+        ev[i][1].record(stream)
+        ev[i][1].synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t_wall
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    launches = L.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    rec = recall_at(I.cpu().numpy(), gt, k)
+
+    # ---- scan kernel roofline: CUDA events around the scan launch on the library's stream ------
+    for _ in range(5):
+        flush.zero_()
+        torch.cuda.synchronize()
+        Dh, Ih, nph, cmph = index.probe_search(model, wl["x_q"], L.SELECT_GT, thr, k, True)
+        tm = index.last_timing()
+        scan_ms.append(tm["scan_ms"]); scan_bytes.append(tm["scan_bytes"]); scan_pairs.append(tm["scan_pairs"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    s_ms = float(np.mean(scan_ms))
+    achieved = float(np.mean(scan_bytes)) / (s_ms * 1e-3) / 1e9
+    flops = 2.0 * d * float(np.mean(scan_pairs))
+
+    # ---- e2e: host buffers through the C ABI (H2D of the queries and D2H of the results inside) ----
+    pin_q = torch.empty((Q, d), dtype=torch.float32).pin_memory()
+    pin_q.copy_(torch.as_tensor(wl["x_q"]))
+    q_host = pin_q.numpy()
+    e2e_t = []
+    for i in range(3 + min(args.steps, 10)):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        Dh, Ih, nph, cmph = index.probe_search(model, q_host, L.SELECT_GT, thr, k, True)
+        if dist is not None:
+            Dg, Ig = gather_merge(torch.as_tensor(Dh, device=dev), torch.as_tensor(Ih, device=dev))
+            Ih = Ig.cpu().numpy()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t[3:]))
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (the oracle port, bounded sample, same probe sets) -----------------------
+    import oracle as O
+    ns = min(args.cpu_sample, Q)
+    off, ids, vecs = O.build_lists_from_data_2_bkt(wl["x_d"], wl["data_2_bkt"], B)
+    t0 = time.perf_counter()
+    f = O.features_cpp(wl["x_q"][:ns], wl["centroids"], wl["scaler_mean"], wl["scaler_scale"])
+    _, probs, _ = O.mlp_forward(f, wl["x_q"][:ns], weights)
+    poff, pids = O.select(probs.astype(np.float32), O.SELECT_GT, thr)
+    cids, _, _ = O.search(off, ids, vecs, wl["x_q"][:ns], poff, pids, k, O.L2, O.F32, 1)
+    cpu_s = time.perf_counter() - t0
+    same = float(np.mean((Ih[:ns] == cids).all(1))) if world == 1 else None
+
+    line = {
+        "metric": "qps_at_recall10_ge_0.95", "value": Q * args.steps / (total_ms * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "sift1m-shape", "N": int(N), "d": int(d), "Q": int(Q), "B": int(B), "k": k,
+                   "n_mul": 2, "redundancy_ratio": 0.03, "select": "score > threshold", "threshold": thr,
+                   "recall_at_10": rec, "avg_nprobe": best[2], "avg_cmp": best[3],
+                   "l2_between_steps": "flushed (256 MiB write); probed lists per step also exceed the 126 MB L2",
+                   "parallelism": "single GPU" if world == 1 else f"lists striped over {world} ranks + NCCL all-gather + merge"},
+        "recall_at_10": rec,
+        "e2e": {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(Q * d * 4),
+                "d2h_bytes_per_step": int(Q * k * 12 + Q * 12)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "kernel": "scan_lists_kernel", "kernel_ms": s_ms,
+                     "algorithmic_bytes": float(np.mean(scan_bytes)), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "fp32_companion": {"flops": flops, "achieved_tflops": flops / (s_ms * 1e-3) / 1e12,
+                                        "peak_tflops_at_max_clock": 74.4}},
+        "cpu_baseline": {"value": ns / cpu_s, "unit": "queries/s", "cores": O.num_threads(), "kind": "port",
+                         "sample": f"first {ns} of {Q} queries, same threshold; ids identical to GPU on {same} of rows"},
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/*
+ * liblira_b200 -- C ABI of the B200-native LIRA query phase and ground-truth path.
+ *
+ * The reference (qfshen23/LIRA-ANN-search) has no plugin / FFI layer: its hot path is reached
+ * through Python call shapes (LIRA_smallscale.py, LIRA_largescale.py, utils.py, model_probing.py)
+ * that bottom out in faiss-cpu, and through two C++ programs (search.cpp, compute_knn.cpp).
+ * Every entry point below names the reference interface it stands in for (file:line into the
+ * reference tree). INTEGRATION.md shows the ctypes / C++ stubs a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer it passes;
+ *   - functions return 0 on success, non-zero on failure, and lira_last_error() then holds a
+ *     message (the reference throws std::runtime_error -> "[Error] ..." + exit 1, search.cpp:552-555);
+ *   - vectors are fp32 row-major; ids are int32 inside the index (index.py:166-167, search.cpp:274)
+ *     and int64 in results (faiss idx_t; numpy default int, LIRA_smallscale.py:154);
+ *   - metric: LIRA_METRIC_L2 = squared L2, no sqrt (faiss IndexFlatL2; search.cpp:253-260),
+ *             LIRA_METRIC_IP = inner product, larger is better (IndexFlatIP; search.cpp:263-269);
+ *   - one caller thread per handle; each handle owns one CUDA stream on its device;
+ *   - names ending in _dev take DEVICE pointers (and a cudaStream_t passed as void*; NULL = the
+ *     handle's own stream) and do not synchronise; all other functions take HOST pointers, copy
+ *     in/out inside the call and return after the results have landed.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef LIRA_B200_H_
+#define LIRA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIRA_METRIC_L2 0
+#define LIRA_METRIC_IP 1
+
+/* partition-selection modes (a5) */
+#define LIRA_SELECT_GT 0        /* score >  value          LIRA_smallscale.py:206, LIRA_largescale.py:163 */
+#define LIRA_SELECT_GE_ARGMAX 1 /* score >= value, argmax if none   search.cpp:448-466                    */
+#define LIRA_SELECT_TOPN 2      /* the (int)value best scores       utils.py:512 (all_outputs[q].topk)    */
+
+typedef struct lira_index lira_index_t; /* inverted lists resident in HBM       */
+typedef struct lira_model lira_model_t; /* probing model + centroids + scaler   */
+
+/* ---- library -------------------------------------------------------------------------- */
+const char* lira_last_error(void);
+int lira_version(void);
+int lira_device_count(void); /* 0 when no CUDA device / driver is present */
+
+/* ---- a6: inverted lists ------------------------------------------------------------------
+ * utils.create_flat_indexes / create_inner_indexes (utils.py:407-429): list b holds
+ * x_d[cluster_ids[b]] in that order, i.e. local index i of list b <-> list_ids[list_offsets[b]+i].
+ * base[N,d] host; list_offsets[B+1] (int64), list_ids[E] (int32, values in [0,N)). The vectors are
+ * gathered into list order on the device; `base` is not referenced after the call. */
+int lira_index_create(const float* base, int64_t N, int d, const int64_t* list_offsets,
+                      const int32_t* list_ids, int B, int metric, int device, lira_index_t** out);
+/* search.cpp:368-403: build the lists from data_2_bkt[N,n_mul] (int32, -1 = empty slot); ids of a
+ * bucket are sorted and unique. Errors with "bucket id out of range." like search.cpp:375-377. */
+int lira_index_create_from_assign(const float* base, int64_t N, int d, const int32_t* data_2_bkt,
+                                  int n_mul, int B, int metric, int device, lira_index_t** out);
+/* adopt lists already laid out on the device: vecs[E, ld] fp32 (ld % 4 == 0, 16-byte aligned),
+ * ids[E] int32, offsets host int64[B+1]. The index does NOT own or copy vecs/ids. */
+int lira_index_create_dev(const float* d_vecs, int64_t ld, int d, const int64_t* list_offsets,
+                          const int32_t* d_ids, int B, int metric, int device, lira_index_t** out);
+int lira_index_free(lira_index_t* h);
+int64_t lira_index_ntotal(const lira_index_t* h, int list); /* faiss Index.ntotal of list b (LIRA_smallscale.py:171); list < 0: all entries */
+int lira_index_nlist(const lira_index_t* h);
+int lira_index_dim(const lira_index_t* h);
+
+/* ---- a7: per-list flat search (the faiss IndexFlat surface) ------------------------------
+ * inner_indexes[b].search(q[nq,d], k) -> (D[nq,k] fp32, I[nq,k] int64 LOCAL positions), best
+ * first, -1 / +-inf padded when the list holds fewer than k vectors (LIRA_smallscale.py:168). */
+int lira_index_list_search(lira_index_t* h, int list, const float* q, int64_t nq, int k, float* D,
+                           int64_t* I);
+/* get_cmp_recall (LIRA_smallscale.py:145-174, LIRA_largescale.py:120-149) in one call: for EVERY
+ * (query, list) pair the top-k inside the list mapped to global ids.
+ * found[Q,B,k] int64 (shorter non-empty lists repeat their last id, empty lists stay -1, exactly as
+ * the reference's xd_id_bid[idx] indexing does); cmp[Q,B] int64 = list size. */
+int lira_scan_all_pairs(lira_index_t* h, const float* q, int64_t Q, int k, int64_t* found,
+                        int64_t* cmp);
+
+/* ---- a10: online search with explicit probe sets (search.cpp:468-514) --------------------
+ * probe_offsets[Q+1] / probe_ids[P]: CSR of the probed lists per query.
+ * dedup = 1: an id stored in several probed lists counts once before selection (Python recall
+ *            semantics, LIRA_smallscale.py:210-214); dedup = 0: search.cpp:499-513 as shipped.
+ * D[Q,k] metric value, I[Q,k] global ids (-1 padded), cmp[Q] (may be NULL) = sum of probed sizes. */
+int lira_search(lira_index_t* h, const float* q, int64_t Q, const int64_t* probe_offsets,
+                const int32_t* probe_ids, int k, int dedup, float* D, int64_t* I, int64_t* cmp);
+int lira_search_dev(lira_index_t* h, const float* d_q, int64_t ldq, int64_t Q,
+                    const int64_t* d_probe_offsets, const int32_t* d_probe_ids, int64_t P, int k,
+                    int dedup, float* d_D, int64_t* d_I, int64_t* d_cmp, void* stream);
+
+/* ---- a1-a5: probing model --------------------------------------------------------------
+ * centroids[B,d]; scaler mean/scale[B] (utils.py:171-175 -> search.cpp:322-329; scale==0 acts as 1);
+ * weights: the 12 tensors of MLP_2_Input in state_dict order (model_probing.py:12-31):
+ *   distance_net.0 W[128,B] b[128], distance_net.2 W[64,128] b[64], vector_net.0 W[128,d] b[128],
+ *   vector_net.2 W[64,128] b[64], fc.0 W[128,128] b[128], fc.2 W[Bout,128] b[Bout]; Bout == B. */
+int lira_model_create(const float* centroids, const float* scaler_mean, const float* scaler_scale,
+                      int B, int d, const float* const weights[12], int device, lira_model_t** out);
+int lira_model_free(lira_model_t* m);
+/* get_dist_cid + StandardScaler.transform (utils.py:98-118, 142-167) == compute_l2_to_centroids +
+ * standardize_distances (search.cpp:220-250): out[Q,B] fp32. mean/scale NULL -> raw distances.
+ * Always Euclidean, also for inner-product datasets (utils.py:115). */
+int lira_centroid_features(const float* q, int64_t Q, const float* centroids, int B, int d,
+                           const float* mean, const float* scale, int device, float* out);
+/* model(x_dist, x_vec) for a batch of raw queries: all_outputs[Q,B] of model_evaluate /
+ * model_infer (model_probing.py:86-156); feats (may be NULL) receives the scaled distances. */
+int lira_model_scores(lira_model_t* m, const float* q, int64_t Q, float* scores, float* feats);
+
+/* ---- the whole query phase (search.cpp:421-517 per batch) --------------------------------
+ * features -> MLP -> select(mode,value) -> grouped scan -> merge.
+ * nprobe[Q] / cmp[Q] may be NULL. */
+int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t Q, int mode,
+                      double value, int k, int dedup, float* D, int64_t* I, int32_t* nprobe,
+                      int64_t* cmp);
+int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q,
+                          int mode, double value, int k, int dedup, float* d_D, int64_t* d_I,
+                          int32_t* d_nprobe, int64_t* d_cmp, void* stream);
+/* search with scores already on the device (threshold replay of query_tuning, LIRA_smallscale.py:199-220) */
+int lira_select_search_dev(lira_index_t* h, const float* d_scores, int64_t lds, const float* d_q,
+                           int64_t ldq, int64_t Q, int mode, double value, int k, int dedup, float* d_D,
+                           int64_t* d_I, int32_t* d_nprobe, int64_t* d_cmp, void* stream);
+
+/* ---- a11: exact k-nearest neighbours -----------------------------------------------------
+ * compute_knn.cpp:208-259 / utils.compute_data_knn fallback (utils.py:286-319) /
+ * LIRA_largescale.py:221-231: brute-force top-k of query[Q,d] against base[N,d]; ties to the lower
+ * base id. The caller drops column 0 for self-kNN as the reference does (compute_knn.cpp:254-259). */
+int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d, int k, int metric,
+             int device, float* D, int64_t* I);
+
+/* ---- multi-GPU merge (e): per-rank top-k lists -> global top-k with id de-duplication ----
+ * d_keys_in[R, Q, k]: rank-major gathered (score,id) lists as produced by lira_*_topk_keys_dev /
+ * lira_pack_keys_dev; output as lira_search. */
+int lira_pack_keys_dev(const float* d_D, const int64_t* d_I, int64_t n, int metric, uint64_t* d_keys,
+                       int device, void* stream);
+int lira_merge_ranks_dev(const uint64_t* d_keys_in, int R, int64_t Q, int k, int metric, int dedup,
+                         float* d_D, int64_t* d_I, int device, void* stream);
+
+/* ---- instrumentation -------------------------------------------------------------------
+ * kernels launched by this library since load (bench.py's gpu_launches), and the device time of
+ * the last scan kernel / last whole search in milliseconds (CUDA events on the handle's stream). */
+int64_t lira_launch_count(void);
+int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes,
+                           int64_t* scan_pairs);
+int lira_index_set_timing(lira_index_t* h, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIRA_B200_H_ */

@@ -1,0 +1,1009 @@
+// liblira_b200: host side of the C ABI declared in include/lira_b200.h.
+// Owns device memory behind the handles, builds the TMA tensor maps, sequences the kernels of
+// probe_kernels.cuh / scan_kernels.cuh on one stream per handle. No torch types, no CPU fallback.
+#include "../../include/lira_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "probe_kernels.cuh"
+
+namespace lira {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+static std::atomic<long long> g_launches{0};
+
+#define LIRA_LAUNCH_CHECK()                                                                    \
+    do {                                                                                       \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        LIRA_CUDA_OK(cudaGetLastError());                                                      \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int grid_for(long long n, int block, int cap = 148 * 8) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, cap));
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point resolved at run time: the .so has no link dependency on
+// libcuda, so it loads -- and its symbols can be checked -- on a machine without a GPU)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(PFN_encodeTiled* out) {
+    static PFN_encodeTiled fn = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LIRA_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        LIRA_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        fn = (PFN_encodeTiled)p;
+    }
+    *out = fn;
+    return 0;
+}
+
+// rows x cols fp32 matrix with row stride ld (floats); box = 128 rows x 32 floats, 128-byte swizzle.
+static int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols, long long ld) {
+    PFN_encodeTiled enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    LIRA_REQUIRE(((uintptr_t)base & 15) == 0 && (ld % 4) == 0, "tensor map: base must be 16-byte aligned, ld % 4 == 0");
+    cuuint64_t dims[2] = {(cuuint64_t)std::max(cols, 1), (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grow-only device buffers
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) LIRA_CUDA_OK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        LIRA_CUDA_OK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct Workspace {
+    DevBuf q, sel, nsel, cmp, list_count, cursor, group_offsets, probe_offsets, group_queries, probe_slot, items,
+        n_items, part_key, D, I, scores, probe_ids, nprobe;
+    void release() {
+        for (DevBuf* b : {&q, &sel, &nsel, &cmp, &list_count, &cursor, &group_offsets, &probe_offsets, &group_queries,
+                          &probe_slot, &items, &n_items, &part_key, &D, &I, &scores, &probe_ids, &nprobe})
+            b->release();
+    }
+};
+
+}  // namespace lira
+
+using namespace lira;
+
+struct lira_index {
+    int device = 0, B = 0, d = 0, ds = 0, metric = 0;
+    long long E = 0;
+    float* vecs = nullptr;
+    int* ids = nullptr;
+    bool owns = true;
+    long long* d_offsets = nullptr;
+    int* d_list_order = nullptr;
+    std::vector<long long> h_offsets;
+    CUtensorMap tmap;
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_scan_ms = 0.f, last_total_ms = 0.f;
+    long long last_scan_bytes = 0, last_scan_pairs = 0, last_Q = 0;
+    int last_k = 0;
+    int num_sms = 148;
+};
+
+struct lira_model {
+    int device = 0, B = 0, Bp = 0, d = 0, ds = 0;
+    float* centroids = nullptr;  // [B, ds]
+    float *mean = nullptr, *scale = nullptr;
+    float* W[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* bias[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int out_dim[6], in_dim[6], in_ld[6];
+    CUtensorMap tm_cent, tm_w[6];
+    cudaStream_t stream = nullptr;
+    DevBuf feats, h1, cat, h2, h5, scores, q;
+};
+
+namespace lira {
+
+// ---------------------------------------------------------------------------------------------
+// kernel attribute setup (once per process and device)
+// ---------------------------------------------------------------------------------------------
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    LIRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static int init_kernels(int device) {
+    static bool done_dev[64] = {false};
+    if (device < 64 && done_dev[device]) return 0;
+    int rc = 0;
+    rc |= set_smem(scan_lists_kernel<OP_L2, 1>, scan_smem_bytes<1>());
+    rc |= set_smem(scan_lists_kernel<OP_DOT, 1>, scan_smem_bytes<1>());
+    rc |= set_smem(scan_lists_kernel<OP_L2, 4>, scan_smem_bytes<4>());
+    rc |= set_smem(scan_lists_kernel<OP_DOT, 4>, scan_smem_bytes<4>());
+    rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
+    rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
+    rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
+    if (device < 64) done_dev[device] = (rc == 0);
+    return rc;
+}
+
+static int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: liblira_b200 has no CPU fallback");
+        return 3;
+    }
+    LIRA_REQUIRE(device >= 0 && device < n, "device ordinal out of range");
+    LIRA_CUDA_OK(cudaSetDevice(device));
+    return init_kernels(device);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense tile GEMM launcher
+// ---------------------------------------------------------------------------------------------
+template <int TM, int OP, int EPI>
+static int launch_dense(const CUtensorMap& tm, const DenseParams& p, cudaStream_t st) {
+    dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM);
+    if (p.M <= 0 || p.N <= 0) return 0;
+    dense_tile_kernel<TM, OP, EPI><<<grid, N_THREADS, DENSE_SMEM_BYTES, st>>>(tm, p);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+static int model_forward(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
+                         float* d_feats_out, cudaStream_t st) {
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
+    const size_t Qs = (size_t)Q;
+    if (int rc = m->feats.ensure(Qs * m->Bp * 4)) return rc;
+    if (int rc = m->h1.ensure(Qs * 128 * 4)) return rc;
+    if (int rc = m->cat.ensure(Qs * 128 * 4)) return rc;
+    if (int rc = m->h2.ensure(Qs * 128 * 4)) return rc;
+    if (int rc = m->h5.ensure(Qs * 128 * 4)) return rc;
+    float* feats = d_feats_out ? d_feats_out : m->feats.as<float>();
+    const long long ldf = d_feats_out ? m->B : m->Bp;
+    if (d_feats_out) LIRA_REQUIRE((m->B % 4) == 0, "feats output needs B % 4 == 0");
+    DenseParams p;
+    // K0: ||q - c_b||_2, standardised (utils.py:98-118,142-167; search.cpp:220-250)
+    p = DenseParams{d_q, ldq, (int)Q, m->ds, m->B, feats, ldf, 0, m->mean, m->scale};
+    if (int rc = launch_dense<64, OP_L2, EPI_FEATURE>(m->tm_cent, p, st)) return rc;
+    // distance_net (model_probing.py:12-17)
+    p = DenseParams{feats, ldf, (int)Q, m->in_ld[0], 128, m->h1.as<float>(), 128, 0, m->bias[0], nullptr};
+    if (int rc = launch_dense<32, OP_DOT, EPI_BIAS_RELU>(m->tm_w[0], p, st)) return rc;
+    p = DenseParams{m->h1.as<float>(), 128, (int)Q, 128, 64, m->cat.as<float>(), 128, 0, m->bias[1], nullptr};
+    if (int rc = launch_dense<32, OP_DOT, EPI_BIAS_RELU>(m->tm_w[1], p, st)) return rc;
+    // vector_net (model_probing.py:19-24)
+    p = DenseParams{d_q, ldq, (int)Q, m->ds, 128, m->h2.as<float>(), 128, 0, m->bias[2], nullptr};
+    if (int rc = launch_dense<32, OP_DOT, EPI_BIAS_RELU>(m->tm_w[2], p, st)) return rc;
+    p = DenseParams{m->h2.as<float>(), 128, (int)Q, 128, 64, m->cat.as<float>(), 128, 64, m->bias[3], nullptr};
+    if (int rc = launch_dense<32, OP_DOT, EPI_BIAS_RELU>(m->tm_w[3], p, st)) return rc;
+    // fc (model_probing.py:26-31): cat -> 128 -> B, sigmoid
+    p = DenseParams{m->cat.as<float>(), 128, (int)Q, 128, 128, m->h5.as<float>(), 128, 0, m->bias[4], nullptr};
+    if (int rc = launch_dense<32, OP_DOT, EPI_BIAS_RELU>(m->tm_w[4], p, st)) return rc;
+    p = DenseParams{m->h5.as<float>(), 128, (int)Q, 128, m->B, d_scores, lds, 0, m->bias[5], nullptr};
+    if (int rc = launch_dense<64, OP_DOT, EPI_BIAS_SIGMOID>(m->tm_w[5], p, st)) return rc;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the search core: probe sets (from scores, explicit CSR, or all pairs) -> groups -> scan -> merge
+// ---------------------------------------------------------------------------------------------
+struct ProbeSpec {
+    int kind;  // 0 = select from scores, 1 = explicit CSR (device), 2 = all pairs
+    const float* d_scores = nullptr;
+    long long lds = 0;
+    int mode = 0;
+    double value = 0;
+    const long long* d_probe_offsets = nullptr;
+    const int* d_probe_ids = nullptr;
+    long long P = 0;
+};
+
+__global__ void csr_hist_kernel(const long long* probe_offsets, const int* probe_ids, const long long* list_offsets,
+                                int Q, int B, int* list_count, long long* cmp, int* nsel, int* bad) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    long long c = 0;
+    const long long lo = probe_offsets[q], hi = probe_offsets[q + 1];
+    for (long long j = lo + lane; j < hi; j += 32) {
+        const int b = probe_ids[j];
+        if (b < 0 || b >= B) { *bad = 1; continue; }
+        atomicAdd(list_count + b, 1);
+        c += list_offsets[b + 1] - list_offsets[b];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) {
+        if (cmp) cmp[q] = c;
+        nsel[q] = (int)(hi - lo);
+    }
+}
+
+__global__ void scatter_csr_kernel(const long long* probe_offsets, const int* probe_ids, const long long* group_offsets,
+                                   int* cursor, int* group_queries, int* probe_slot, int Q, int B) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    for (long long j = probe_offsets[q] + lane; j < probe_offsets[q + 1]; j += 32) {
+        const int b = probe_ids[j];
+        if (b < 0 || b >= B) continue;
+        const int pos = (int)group_offsets[b] + atomicAdd(cursor + b, 1);
+        group_queries[pos] = q;
+        probe_slot[j] = pos;
+    }
+}
+
+__global__ void uniform_groups_kernel(long long* group_offsets, int B, long long Q) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= B; i += gridDim.x * blockDim.x) group_offsets[i] = i * Q;
+}
+
+__global__ void copy_nprobe_kernel(const int* nsel, int* out, int Q) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += gridDim.x * blockDim.x) out[i] = nsel[i];
+}
+
+static int launch_scan(lira_index* h, const ScanParams& sp, int k, cudaStream_t st) {
+    const int grid = h->num_sms;
+    const int S = k <= 32 ? 1 : 4;
+    if (h->metric == LIRA_METRIC_L2) {
+        if (S == 1) scan_lists_kernel<OP_L2, 1><<<grid, N_THREADS, scan_smem_bytes<1>(), st>>>(h->tmap, sp);
+        else scan_lists_kernel<OP_L2, 4><<<grid, N_THREADS, scan_smem_bytes<4>(), st>>>(h->tmap, sp);
+    } else {
+        if (S == 1) scan_lists_kernel<OP_DOT, 1><<<grid, N_THREADS, scan_smem_bytes<1>(), st>>>(h->tmap, sp);
+        else scan_lists_kernel<OP_DOT, 4><<<grid, N_THREADS, scan_smem_bytes<4>(), st>>>(h->tmap, sp);
+    }
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_merge(const MergeParams& mp, cudaStream_t st) {
+    const int warps = 8;
+    const int grid = (mp.Q + warps - 1) / warps;
+    if (mp.Q <= 0) return 0;
+    if (mp.k <= 32) merge_topk_kernel<1><<<grid, warps * 32, 0, st>>>(mp);
+    else merge_topk_kernel<4><<<grid, warps * 32, 0, st>>>(mp);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+// Runs grouping + scan. On return ws.part_key / ws.probe_offsets / ws.probe_slot describe the partial
+// lists; *P_out is the number of (query, list) pairs.
+static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
+                            int store_local, long long* d_cmp, long long* P_out, cudaStream_t st) {
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_REQUIRE(Q >= 0 && Q < (1ll << 31), "Q out of range");
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
+    Workspace& ws = h->ws;
+    const int B = h->B;
+    const int warps = 8;
+    const int qgrid = (int)((Q + warps - 1) / warps);
+    if (int rc = ws.nsel.ensure((size_t)(Q + 1) * 4)) return rc;
+    if (int rc = ws.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
+    if (int rc = ws.group_offsets.ensure((size_t)(B + 1) * 8)) return rc;
+    if (int rc = ws.list_count.ensure((size_t)(B + 1) * 4)) return rc;
+    if (int rc = ws.cursor.ensure((size_t)(B + 1) * 4)) return rc;
+    if (int rc = ws.n_items.ensure(128)) return rc;
+    LIRA_CUDA_OK(cudaMemsetAsync(ws.list_count.p, 0, (size_t)(B + 1) * 4, st));
+    LIRA_CUDA_OK(cudaMemsetAsync(ws.cursor.p, 0, (size_t)(B + 1) * 4, st));
+    LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.p, 0, 128, st));
+    long long P = 0;
+    if (Q == 0) { *P_out = 0; return 0; }
+
+    if (ps.kind == 0) {
+        LIRA_REQUIRE(ps.mode >= 0 && ps.mode <= 2, "unknown selection mode");
+        if (ps.mode == LIRA_SELECT_TOPN) LIRA_REQUIRE(ps.value >= 1 && ps.value <= 128, "top-nprobe must be in [1, 128]");
+        if (int rc = ws.sel.ensure((size_t)Q * B * 4)) return rc;
+        SelectParams sp{ps.d_scores, ps.lds, (int)Q, B, ps.mode, ps.value, h->d_offsets, ws.sel.as<int>(),
+                        ws.nsel.as<int>(), d_cmp, ws.list_count.as<int>()};
+        select_kernel<4><<<qgrid, warps * 32, 0, st>>>(sp);
+        LIRA_LAUNCH_CHECK();
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.nsel.as<int>(), ws.probe_offsets.as<long long>(), (int)Q);
+        LIRA_LAUNCH_CHECK();
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
+        LIRA_LAUNCH_CHECK();
+        LIRA_CUDA_OK(cudaMemcpyAsync(&P, ws.probe_offsets.as<long long>() + Q, 8, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    } else if (ps.kind == 1) {
+        P = ps.P;
+        int* bad = ws.n_items.as<int>() + 8;
+        csr_hist_kernel<<<qgrid, warps * 32, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, h->d_offsets, (int)Q, B,
+                                                      ws.list_count.as<int>(), d_cmp, ws.nsel.as<int>(), bad);
+        LIRA_LAUNCH_CHECK();
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
+        LIRA_LAUNCH_CHECK();
+    } else {
+        P = Q * (long long)B;
+    }
+    LIRA_REQUIRE(P < (1ll << 31), "too many (query, list) pairs in one call; split the query batch");
+    *P_out = P;
+    const size_t Ps = (size_t)std::max<long long>(P, 1);
+    if (int rc = ws.group_queries.ensure(Ps * 4)) return rc;
+    if (int rc = ws.probe_slot.ensure(Ps * 4)) return rc;
+    if (int rc = ws.part_key.ensure(Ps * k * 8)) return rc;
+    const size_t max_items = Ps / SCAN_TM_MAX + B + 1;
+    if (int rc = ws.items.ensure(max_items * sizeof(ScanItem))) return rc;
+
+    const long long* probe_offsets = nullptr;
+    if (ps.kind == 0) {
+        ScatterParams sc{ws.sel.as<int>(), ws.nsel.as<int>(), ws.probe_offsets.as<long long>(),
+                         ws.group_offsets.as<long long>(), ws.cursor.as<int>(), ws.group_queries.as<int>(),
+                         ws.probe_slot.as<int>(), (int)Q, B};
+        scatter_groups_kernel<<<qgrid, warps * 32, 0, st>>>(sc);
+        LIRA_LAUNCH_CHECK();
+        probe_offsets = ws.probe_offsets.as<long long>();
+    } else if (ps.kind == 1) {
+        scatter_csr_kernel<<<qgrid, warps * 32, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids,
+                                                         ws.group_offsets.as<long long>(), ws.cursor.as<int>(),
+                                                         ws.group_queries.as<int>(), ws.probe_slot.as<int>(), (int)Q, B);
+        LIRA_LAUNCH_CHECK();
+        probe_offsets = ps.d_probe_offsets;
+    } else {
+        uniform_groups_kernel<<<grid_for(B + 1, 256), 256, 0, st>>>(ws.group_offsets.as<long long>(), B, Q);
+        LIRA_LAUNCH_CHECK();
+        fill_all_pairs_kernel<<<grid_for(P, 256), 256, 0, st>>>((int)Q, B, ws.group_queries.as<int>(),
+                                                                ws.probe_slot.as<int>());
+        LIRA_LAUNCH_CHECK();
+        iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(ws.probe_offsets.as<long long>(), Q, B);
+        LIRA_LAUNCH_CHECK();
+        probe_offsets = ws.probe_offsets.as<long long>();
+    }
+    (void)probe_offsets;
+    build_items_kernel<<<1, 1024, 0, st>>>(h->d_list_order, ws.group_offsets.as<long long>(), h->d_offsets, B,
+                                           ws.items.as<ScanItem>(), ws.n_items.as<int>(),
+                                           (unsigned long long*)((char*)ws.n_items.p + 64));
+    LIRA_LAUNCH_CHECK();
+
+    ScanParams sp;
+    sp.q = d_q;
+    sp.ldq = ldq;
+    sp.d = h->ds;
+    sp.group_queries = ws.group_queries.as<int>();
+    sp.list_offsets = h->d_offsets;
+    sp.list_ids = h->ids;
+    sp.items = ws.items.as<ScanItem>();
+    sp.n_items = ws.n_items.as<int>();
+    sp.part_key = ws.part_key.as<unsigned long long>();
+    sp.k = k;
+    sp.store_local = store_local;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    if (int rc = launch_scan(h, sp, k, st)) return rc;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    return 0;
+}
+
+static int search_core(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
+                       int dedup, float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st) {
+    long long P = 0;
+    h->last_Q = Q;
+    h->last_k = k;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
+    if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, d_cmp, &P, st)) return rc;
+    if (Q == 0) return 0;
+    Workspace& ws = h->ws;
+    MergeParams mp;
+    mp.part_key = ws.part_key.as<unsigned long long>();
+    mp.probe_offsets = ps.kind == 1 ? ps.d_probe_offsets : ws.probe_offsets.as<long long>();
+    mp.probe_slot = ws.probe_slot.as<int>();
+    mp.k = k;
+    mp.Q = (int)Q;
+    mp.dedup = dedup;
+    mp.out_dist = d_D;
+    mp.out_ids = d_I;
+    mp.is_ip = h->metric == LIRA_METRIC_IP;
+    if (int rc = launch_merge(mp, st)) return rc;
+    if (d_nprobe) {
+        copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
+        LIRA_LAUNCH_CHECK();
+    }
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
+    return 0;
+}
+
+static int finish_timing(lira_index* h) {
+    if (!h->timing) return 0;
+    LIRA_CUDA_OK(cudaEventSynchronize(h->ev[3]));
+    LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_scan_ms, h->ev[0], h->ev[1]));
+    LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_total_ms, h->ev[2], h->ev[3]));
+    unsigned long long stats[2] = {0, 0};
+    LIRA_CUDA_OK(cudaMemcpy(stats, (char*)h->ws.n_items.p + 64, 16, cudaMemcpyDeviceToHost));
+    // bytes_alg = E_p (4 d + 4) + Q 4 d + Q k 8
+    h->last_scan_bytes = (long long)stats[0] * (4ll * h->d + 4) + h->last_Q * (4ll * h->d + 8ll * h->last_k);
+    h->last_scan_pairs = (long long)stats[1];
+    return 0;
+}
+
+// upload a host [n, d] fp32 matrix into a device buffer with row stride ds (zero padded)
+static int upload_rows(DevBuf& buf, const float* host, long long n, int d, int ds, cudaStream_t st) {
+    if (int rc = buf.ensure((size_t)std::max<long long>(n, 1) * ds * 4)) return rc;
+    if (n == 0) return 0;
+    if (d == ds) {
+        LIRA_CUDA_OK(cudaMemcpyAsync(buf.p, host, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
+    } else {
+        LIRA_CUDA_OK(cudaMemsetAsync(buf.p, 0, (size_t)n * ds * 4, st));
+        LIRA_CUDA_OK(cudaMemcpy2DAsync(buf.p, (size_t)ds * 4, host, (size_t)d * 4, (size_t)d * 4, (size_t)n,
+                                       cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+}
+
+static int index_finish_create(lira_index* h, const long long* offsets) {
+    h->h_offsets.assign(offsets, offsets + h->B + 1);
+    LIRA_CUDA_OK(cudaMalloc(&h->d_offsets, (size_t)(h->B + 1) * 8));
+    LIRA_CUDA_OK(cudaMemcpy(h->d_offsets, offsets, (size_t)(h->B + 1) * 8, cudaMemcpyHostToDevice));
+    std::vector<int> order(h->B);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (offsets[a + 1] - offsets[a]) > (offsets[b + 1] - offsets[b]);
+    });
+    LIRA_CUDA_OK(cudaMalloc(&h->d_list_order, (size_t)std::max(h->B, 1) * 4));
+    LIRA_CUDA_OK(cudaMemcpy(h->d_list_order, order.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
+    if (int rc = make_tmap(&h->tmap, h->vecs, h->E, h->ds, h->ds)) return rc;
+    for (auto& e : h->ev) LIRA_CUDA_OK(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    return 0;
+}
+
+static int validate_offsets(const int64_t* off, int B, long long* E) {
+    LIRA_REQUIRE(off[0] == 0, "list_offsets[0] must be 0");
+    for (int b = 0; b < B; ++b) LIRA_REQUIRE(off[b + 1] >= off[b], "list_offsets must be non-decreasing");
+    *E = off[B];
+    LIRA_REQUIRE(*E < (1ll << 31), "more than 2^31 list entries per index: shard the lists across GPUs");
+    return 0;
+}
+
+}  // namespace lira
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* lira_last_error(void) { return g_err.c_str(); }
+int lira_version(void) { return 100; }
+int lira_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int64_t lira_launch_count(void) { return g_launches.load(); }
+
+int lira_index_create(const float* base, int64_t N, int d, const int64_t* list_offsets, const int32_t* list_ids,
+                      int B, int metric, int device, lira_index_t** out) {
+    LIRA_REQUIRE(out && base && list_offsets && (list_ids || list_offsets[B] == 0), "null argument");
+    LIRA_REQUIRE(N >= 0 && d >= 1 && B >= 1, "bad shape");
+    LIRA_REQUIRE(metric == LIRA_METRIC_L2 || metric == LIRA_METRIC_IP, "metric must be LIRA_METRIC_L2 or LIRA_METRIC_IP");
+    if (int rc = check_device(device)) return rc;
+    long long E = 0;
+    if (int rc = validate_offsets(list_offsets, B, &E)) return rc;
+    for (long long e = 0; e < E; ++e)
+        LIRA_REQUIRE(list_ids[e] >= 0 && list_ids[e] < N, "list id out of range");
+    lira_index* h = new lira_index();
+    h->device = device; h->B = B; h->d = d; h->ds = round_up(d, 4); h->metric = metric; h->E = E; h->owns = true;
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = 2; break; }
+        // base goes up in row chunks and is gathered into list order on the device
+        if (cudaMalloc(&h->vecs, (size_t)std::max<long long>(E, 1) * h->ds * 4) != cudaSuccess) { set_error("cudaMalloc(list vectors) failed"); rc = 2; break; }
+        if (cudaMalloc(&h->ids, (size_t)std::max<long long>(E, 1) * 4) != cudaSuccess) { set_error("cudaMalloc(list ids) failed"); rc = 2; break; }
+        float* d_base = nullptr;
+        if (cudaMalloc(&d_base, (size_t)std::max<long long>(N, 1) * d * 4) != cudaSuccess) { set_error("cudaMalloc(base) failed"); rc = 2; break; }
+        cudaMemcpyAsync(d_base, base, (size_t)N * d * 4, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(h->ids, list_ids, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream);
+        if (E > 0) {
+            gather_rows_kernel<<<grid_for(E * (h->ds / 4), 256, 148 * 16), 256, 0, h->stream>>>(d_base, d, d, h->ids, E, h->vecs, h->ds);
+            g_launches.fetch_add(1);
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_base);
+        if (e != cudaSuccess) { set_error(std::string("index build failed: ") + cudaGetErrorString(e)); rc = 2; break; }
+        std::vector<long long> off(list_offsets, list_offsets + B + 1);
+        rc = index_finish_create(h, off.data());
+    } while (0);
+    if (rc) { lira_index_free(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int lira_index_create_from_assign(const float* base, int64_t N, int d, const int32_t* data_2_bkt, int n_mul, int B,
+                                  int metric, int device, lira_index_t** out) {
+    LIRA_REQUIRE(out && base && data_2_bkt && n_mul >= 1 && B >= 1, "bad argument");
+    // search.cpp:368-386: ids enter each bucket in increasing order, so "sort + unique" reduces to
+    // skipping an id equal to the bucket's last one.
+    std::vector<int64_t> cnt(B + 1, 0);
+    std::vector<int32_t> last(B, -1);
+    for (int64_t i = 0; i < N; ++i)
+        for (int j = 0; j < n_mul; ++j) {
+            const int b = data_2_bkt[i * n_mul + j];
+            if (b < 0) continue;
+            LIRA_REQUIRE(b < B, "bucket id out of range.");
+            if (last[b] == (int32_t)i) continue;
+            last[b] = (int32_t)i;
+            cnt[b + 1]++;
+        }
+    for (int b = 0; b < B; ++b) cnt[b + 1] += cnt[b];
+    std::vector<int32_t> ids((size_t)std::max<int64_t>(cnt[B], 1));
+    std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
+    std::fill(last.begin(), last.end(), -1);
+    for (int64_t i = 0; i < N; ++i)
+        for (int j = 0; j < n_mul; ++j) {
+            const int b = data_2_bkt[i * n_mul + j];
+            if (b < 0 || last[b] == (int32_t)i) continue;
+            last[b] = (int32_t)i;
+            ids[cur[b]++] = (int32_t)i;
+        }
+    return lira_index_create(base, N, d, cnt.data(), ids.data(), B, metric, device, out);
+}
+
+int lira_index_create_dev(const float* d_vecs, int64_t ld, int d, const int64_t* list_offsets, const int32_t* d_ids,
+                          int B, int metric, int device, lira_index_t** out) {
+    LIRA_REQUIRE(out && d_vecs && list_offsets && d_ids && B >= 1 && d >= 1, "bad argument");
+    LIRA_REQUIRE(ld >= d && (ld % 4) == 0 && ((uintptr_t)d_vecs & 15) == 0, "device vectors need ld % 4 == 0 and 16-byte alignment");
+    LIRA_REQUIRE(metric == LIRA_METRIC_L2 || metric == LIRA_METRIC_IP, "metric must be LIRA_METRIC_L2 or LIRA_METRIC_IP");
+    if (int rc = check_device(device)) return rc;
+    long long E = 0;
+    if (int rc = validate_offsets(list_offsets, B, &E)) return rc;
+    lira_index* h = new lira_index();
+    h->device = device; h->B = B; h->d = d; h->ds = (int)ld; h->metric = metric; h->E = E; h->owns = false;
+    h->vecs = const_cast<float*>(d_vecs);
+    h->ids = const_cast<int*>(d_ids);
+    int rc = 0;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = 2; }
+    if (!rc) {
+        std::vector<long long> off(list_offsets, list_offsets + B + 1);
+        rc = index_finish_create(h, off.data());
+    }
+    if (rc) { lira_index_free(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int lira_index_free(lira_index_t* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->owns) { cudaFree(h->vecs); cudaFree(h->ids); }
+    cudaFree(h->d_offsets);
+    cudaFree(h->d_list_order);
+    h->ws.release();
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int64_t lira_index_ntotal(const lira_index_t* h, int list) {
+    if (!h) return -1;
+    if (list < 0) return h->E;
+    if (list >= h->B) return -1;
+    return h->h_offsets[list + 1] - h->h_offsets[list];
+}
+int lira_index_nlist(const lira_index_t* h) { return h ? h->B : -1; }
+int lira_index_dim(const lira_index_t* h) { return h ? h->d : -1; }
+
+int lira_index_set_timing(lira_index_t* h, int enable) {
+    LIRA_REQUIRE(h, "null index");
+    h->timing = enable != 0;
+    return 0;
+}
+int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes, int64_t* scan_pairs) {
+    LIRA_REQUIRE(h, "null index");
+    if (scan_ms) *scan_ms = h->last_scan_ms;
+    if (total_ms) *total_ms = h->last_total_ms;
+    if (scan_bytes) *scan_bytes = h->last_scan_bytes;
+    if (scan_pairs) *scan_pairs = h->last_scan_pairs;
+    return 0;
+}
+
+int lira_index_list_search(lira_index_t* h, int list, const float* q, int64_t nq, int k, float* D, int64_t* I) {
+    LIRA_REQUIRE(h && q && D && I, "null argument");
+    LIRA_REQUIRE(list >= 0 && list < h->B, "list out of range");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    if (int rc = upload_rows(ws.q, q, nq, h->d, h->ds, st)) return rc;
+    // probe sets: every query probes exactly `list`
+    std::vector<long long> po(nq + 1);
+    std::iota(po.begin(), po.end(), 0ll);
+    std::vector<int> pi((size_t)std::max<int64_t>(nq, 1), list);
+    if (int rc = ws.probe_ids.ensure((size_t)(nq + 1) * 4 + (size_t)(nq + 1) * 8 + 64)) return rc;
+    long long* d_po = (long long*)ws.probe_ids.p;
+    int* d_pi = (int*)(d_po + nq + 1);
+    LIRA_CUDA_OK(cudaMemcpyAsync(d_po, po.data(), (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    LIRA_CUDA_OK(cudaMemcpyAsync(d_pi, pi.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+    ProbeSpec ps;
+    ps.kind = 1; ps.d_probe_offsets = d_po; ps.d_probe_ids = d_pi; ps.P = nq;
+    long long P = 0;
+    if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, /*store_local=*/1, nullptr, &P, st)) return rc;
+    if (nq == 0) return 0;
+    if (int rc = ws.D.ensure((size_t)nq * k * 4)) return rc;
+    if (int rc = ws.I.ensure((size_t)nq * k * 8)) return rc;
+    MergeParams mp{ws.part_key.as<unsigned long long>(), d_po, ws.probe_slot.as<int>(), k, (int)nq, 0,
+                   ws.D.as<float>(), ws.I.as<long long>(), h->metric == LIRA_METRIC_IP};
+    if (int rc = launch_merge(mp, st)) return rc;
+    LIRA_CUDA_OK(cudaMemcpyAsync(D, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    LIRA_CUDA_OK(cudaMemcpyAsync(I, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int lira_scan_all_pairs(lira_index_t* h, const float* q, int64_t Q, int k, int64_t* found, int64_t* cmp) {
+    LIRA_REQUIRE(h && q && found, "null argument");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    const int B = h->B;
+    // bound the partial-result workspace: process the queries in batches
+    const long long max_pairs = 64ll << 20;  // 64 Mi (query, list) pairs per batch
+    long long qb = std::max<long long>(1, std::min<long long>(Q, max_pairs / std::max(B, 1)));
+    for (long long q0 = 0; q0 < Q; q0 += qb) {
+        const long long nq = std::min<long long>(qb, Q - q0);
+        if (int rc = upload_rows(ws.q, q + q0 * h->d, nq, h->d, h->ds, st)) return rc;
+        ProbeSpec ps;
+        ps.kind = 2;
+        long long P = 0;
+        if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, 0, nullptr, &P, st)) return rc;
+        if (int rc = ws.I.ensure((size_t)P * k * 8)) return rc;
+        if (int rc = ws.cmp.ensure((size_t)P * 8)) return rc;
+        found_from_partials_kernel<<<grid_for(P * k, 256, 148 * 16), 256, 0, st>>>(
+            ws.part_key.as<unsigned long long>(), ws.probe_slot.as<int>(), h->d_offsets, h->ids, (int)nq, B, k,
+            ws.I.as<long long>(), ws.cmp.as<long long>());
+        LIRA_LAUNCH_CHECK();
+        LIRA_CUDA_OK(cudaMemcpyAsync(found + (size_t)q0 * B * k, ws.I.p, (size_t)P * k * 8, cudaMemcpyDeviceToHost, st));
+        if (cmp) LIRA_CUDA_OK(cudaMemcpyAsync(cmp + (size_t)q0 * B, ws.cmp.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int lira_search_dev(lira_index_t* h, const float* d_q, int64_t ldq, int64_t Q, const int64_t* d_probe_offsets,
+                    const int32_t* d_probe_ids, int64_t P, int k, int dedup, float* d_D, int64_t* d_I, int64_t* d_cmp,
+                    void* stream) {
+    LIRA_REQUIRE(h && d_q && d_probe_offsets && (d_probe_ids || P == 0) && d_D && d_I, "null argument");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    ProbeSpec ps;
+    ps.kind = 1; ps.d_probe_offsets = (const long long*)d_probe_offsets; ps.d_probe_ids = d_probe_ids; ps.P = P;
+    return search_core(h, d_q, ldq, Q, ps, k, dedup, d_D, (long long*)d_I, nullptr, (long long*)d_cmp, st);
+}
+
+int lira_search(lira_index_t* h, const float* q, int64_t Q, const int64_t* probe_offsets, const int32_t* probe_ids,
+                int k, int dedup, float* D, int64_t* I, int64_t* cmp) {
+    LIRA_REQUIRE(h && q && probe_offsets && D && I, "null argument");
+    LIRA_REQUIRE(probe_offsets[0] == 0, "probe_offsets[0] must be 0");
+    const int64_t P = probe_offsets[Q];
+    for (int64_t j = 0; j < P; ++j) LIRA_REQUIRE(probe_ids[j] >= 0 && probe_ids[j] < h->B, "probed list id out of range");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    if (int rc = upload_rows(ws.q, q, Q, h->d, h->ds, st)) return rc;
+    if (int rc = ws.probe_ids.ensure((size_t)(Q + 1) * 8 + (size_t)(P + 1) * 4 + 64)) return rc;
+    long long* d_po = (long long*)ws.probe_ids.p;
+    int* d_pi = (int*)(d_po + Q + 1);
+    LIRA_CUDA_OK(cudaMemcpyAsync(d_po, probe_offsets, (size_t)(Q + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (P) LIRA_CUDA_OK(cudaMemcpyAsync(d_pi, probe_ids, (size_t)P * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = ws.D.ensure((size_t)std::max<int64_t>(Q, 1) * k * 4)) return rc;
+    if (int rc = ws.I.ensure((size_t)std::max<int64_t>(Q, 1) * k * 8)) return rc;
+    if (int rc = ws.cmp.ensure((size_t)std::max<int64_t>(Q, 1) * 8)) return rc;
+    if (int rc = lira_search_dev(h, ws.q.as<float>(), h->ds, Q, (const int64_t*)d_po, d_pi, P, k, dedup, ws.D.as<float>(),
+                                 (int64_t*)ws.I.p, (int64_t*)ws.cmp.p, st)) return rc;
+    if (Q) {
+        LIRA_CUDA_OK(cudaMemcpyAsync(D, ws.D.p, (size_t)Q * k * 4, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaMemcpyAsync(I, ws.I.p, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+        if (cmp) LIRA_CUDA_OK(cudaMemcpyAsync(cmp, ws.cmp.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+    }
+    LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    return finish_timing(h);
+}
+
+// ---- probing model ---------------------------------------------------------------------------
+int lira_model_create(const float* centroids, const float* scaler_mean, const float* scaler_scale, int B, int d,
+                      const float* const weights[12], int device, lira_model_t** out) {
+    LIRA_REQUIRE(out && centroids && weights && B >= 1 && d >= 1, "bad argument");
+    for (int i = 0; i < 12; ++i) LIRA_REQUIRE(weights[i], "null weight tensor");
+    if (int rc = check_device(device)) return rc;
+    lira_model* m = new lira_model();
+    m->device = device; m->B = B; m->Bp = round_up(B, 4); m->d = d; m->ds = round_up(d, 4);
+    const int od[6] = {128, 64, 128, 64, 128, B};
+    const int id[6] = {B, 128, d, 128, 128, 128};
+    int rc = 0;
+    auto up = [&](float** dst, const float* src, int rows, int cols, int ld) -> int {
+        LIRA_CUDA_OK(cudaMalloc(dst, (size_t)rows * ld * 4));
+        LIRA_CUDA_OK(cudaMemset(*dst, 0, (size_t)rows * ld * 4));
+        LIRA_CUDA_OK(cudaMemcpy2D(*dst, (size_t)ld * 4, src, (size_t)cols * 4, (size_t)cols * 4, rows, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    do {
+        if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = 2; break; }
+        if ((rc = up(&m->centroids, centroids, B, d, m->ds))) break;
+        if ((rc = make_tmap(&m->tm_cent, m->centroids, B, m->ds, m->ds))) break;
+        if (scaler_mean && scaler_scale) {
+            if ((rc = up(&m->mean, scaler_mean, 1, B, m->Bp))) break;
+            if ((rc = up(&m->scale, scaler_scale, 1, B, m->Bp))) break;
+        }
+        for (int l = 0; l < 6 && !rc; ++l) {
+            m->out_dim[l] = od[l];
+            m->in_dim[l] = id[l];
+            m->in_ld[l] = round_up(id[l], 4);
+            if ((rc = up(&m->W[l], weights[2 * l], od[l], id[l], m->in_ld[l]))) break;
+            if ((rc = up(&m->bias[l], weights[2 * l + 1], 1, od[l], round_up(od[l], 4)))) break;
+            rc = make_tmap(&m->tm_w[l], m->W[l], od[l], m->in_ld[l], m->in_ld[l]);
+        }
+    } while (0);
+    if (rc) { lira_model_free(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+int lira_model_free(lira_model_t* m) {
+    if (!m) return 0;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->centroids); cudaFree(m->mean); cudaFree(m->scale);
+    for (int l = 0; l < 6; ++l) { cudaFree(m->W[l]); cudaFree(m->bias[l]); }
+    for (DevBuf* b : {&m->feats, &m->h1, &m->cat, &m->h2, &m->h5, &m->scores, &m->q}) b->release();
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return 0;
+}
+
+int lira_centroid_features(const float* q, int64_t Q, const float* centroids, int B, int d, const float* mean,
+                           const float* scale, int device, float* out) {
+    LIRA_REQUIRE(q && centroids && out && B >= 1 && d >= 1 && Q >= 0, "bad argument");
+    LIRA_REQUIRE((mean == nullptr) == (scale == nullptr), "mean and scale must be given together");
+    if (int rc = check_device(device)) return rc;
+    const int ds = round_up(d, 4), Bp = round_up(B, 4);
+    DevBuf cent, mq, ms, dq, dout;
+    cudaStream_t st = nullptr;
+    int rc = 0;
+    auto body = [&]() -> int {
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (int r = upload_rows(cent, centroids, B, d, ds, st)) return r;
+        if (mean) {
+            if (int r = upload_rows(mq, mean, 1, B, Bp, st)) return r;
+            if (int r = upload_rows(ms, scale, 1, B, Bp, st)) return r;
+        }
+        CUtensorMap tm;
+        if (int r = make_tmap(&tm, cent.as<float>(), B, ds, ds)) return r;
+        const long long chunk = 65536;
+        for (long long q0 = 0; q0 < Q; q0 += chunk) {
+            const long long nq = std::min<long long>(chunk, Q - q0);
+            if (int r = upload_rows(dq, q + q0 * d, nq, d, ds, st)) return r;
+            if (int r = dout.ensure((size_t)nq * Bp * 4)) return r;
+            DenseParams p{dq.as<float>(), ds, (int)nq, ds, B, dout.as<float>(), Bp, 0, mean ? mq.as<float>() : nullptr,
+                          mean ? ms.as<float>() : nullptr};
+            if (int r = launch_dense<64, OP_L2, EPI_FEATURE>(tm, p, st)) return r;
+            LIRA_CUDA_OK(cudaMemcpy2DAsync(out + (size_t)q0 * B, (size_t)B * 4, dout.p, (size_t)Bp * 4, (size_t)B * 4,
+                                           (size_t)nq, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    };
+    rc = body();
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (DevBuf* b : {&cent, &mq, &ms, &dq, &dout}) b->release();
+    return rc;
+}
+
+int lira_model_scores(lira_model_t* m, const float* q, int64_t Q, float* scores, float* feats) {
+    LIRA_REQUIRE(m && q && scores && Q >= 0, "bad argument");
+    LIRA_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const long long chunk = 32768;
+    for (long long q0 = 0; q0 < Q; q0 += chunk) {
+        const long long nq = std::min<long long>(chunk, Q - q0);
+        if (int rc = upload_rows(m->q, q + q0 * m->d, nq, m->d, m->ds, st)) return rc;
+        if (int rc = m->scores.ensure((size_t)nq * m->Bp * 4)) return rc;
+        if (int rc = model_forward(m, m->q.as<float>(), m->ds, nq, m->scores.as<float>(), m->Bp, nullptr, st)) return rc;
+        LIRA_CUDA_OK(cudaMemcpy2DAsync(scores + (size_t)q0 * m->B, (size_t)m->B * 4, m->scores.p, (size_t)m->Bp * 4,
+                                       (size_t)m->B * 4, (size_t)nq, cudaMemcpyDeviceToHost, st));
+        if (feats)
+            LIRA_CUDA_OK(cudaMemcpy2DAsync(feats + (size_t)q0 * m->B, (size_t)m->B * 4, m->feats.p, (size_t)m->Bp * 4,
+                                           (size_t)m->B * 4, (size_t)nq, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int lira_select_search_dev(lira_index_t* h, const float* d_scores, int64_t lds, const float* d_q, int64_t ldq, int64_t Q,
+                           int mode, double value, int k, int dedup, float* d_D, int64_t* d_I, int32_t* d_nprobe,
+                           int64_t* d_cmp, void* stream) {
+    LIRA_REQUIRE(h && d_scores && d_q && d_D && d_I, "null argument");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    ProbeSpec ps;
+    ps.kind = 0; ps.d_scores = d_scores; ps.lds = lds; ps.mode = mode; ps.value = value;
+    return search_core(h, d_q, ldq, Q, ps, k, dedup, d_D, (long long*)d_I, d_nprobe, (long long*)d_cmp, st);
+}
+
+int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q, int mode,
+                          double value, int k, int dedup, float* d_D, int64_t* d_I, int32_t* d_nprobe, int64_t* d_cmp,
+                          void* stream) {
+    LIRA_REQUIRE(h && m && d_q && d_D && d_I, "null argument");
+    LIRA_REQUIRE(h->device == m->device && h->B == m->B && h->d == m->d, "index and model disagree on device / B / d");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (int rc = h->ws.scores.ensure((size_t)std::max<int64_t>(Q, 1) * m->Bp * 4)) return rc;
+    if (int rc = model_forward(m, d_q, ldq, Q, h->ws.scores.as<float>(), m->Bp, nullptr, st)) return rc;
+    return lira_select_search_dev(h, h->ws.scores.as<float>(), m->Bp, d_q, ldq, Q, mode, value, k, dedup, d_D, d_I,
+                                  d_nprobe, d_cmp, st);
+}
+
+int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t Q, int mode, double value, int k,
+                      int dedup, float* D, int64_t* I, int32_t* nprobe, int64_t* cmp) {
+    LIRA_REQUIRE(h && m && q && D && I, "null argument");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    const size_t Qs = (size_t)std::max<int64_t>(Q, 1);
+    if (int rc = upload_rows(ws.q, q, Q, h->d, h->ds, st)) return rc;
+    if (int rc = ws.D.ensure(Qs * k * 4)) return rc;
+    if (int rc = ws.I.ensure(Qs * k * 8)) return rc;
+    if (int rc = ws.cmp.ensure(Qs * 8)) return rc;
+    if (int rc = ws.nprobe.ensure(Qs * 4)) return rc;
+    if (int rc = lira_probe_search_dev(h, m, ws.q.as<float>(), h->ds, Q, mode, value, k, dedup, ws.D.as<float>(),
+                                       (int64_t*)ws.I.p, ws.nprobe.as<int>(), (int64_t*)ws.cmp.p, st)) return rc;
+    if (Q) {
+        LIRA_CUDA_OK(cudaMemcpyAsync(D, ws.D.p, (size_t)Q * k * 4, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaMemcpyAsync(I, ws.I.p, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+        if (cmp) LIRA_CUDA_OK(cudaMemcpyAsync(cmp, ws.cmp.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+        if (nprobe) LIRA_CUDA_OK(cudaMemcpyAsync(nprobe, ws.nprobe.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+    }
+    LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    return finish_timing(h);
+}
+
+// ---- exact kNN (SIMT path): the base is cut into segments that play the role of lists --------
+int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d, int k, int metric, int device,
+             float* D, int64_t* I) {
+    LIRA_REQUIRE(base && query && D && I && N >= 1 && Q >= 0 && d >= 1, "bad argument");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per call");
+    if (int rc = check_device(device)) return rc;
+    const int ds = round_up(d, 4);
+    const long long seg = 8192;
+    const int nseg = (int)((N + seg - 1) / seg);
+    std::vector<int64_t> off(nseg + 1);
+    for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
+    DevBuf dbase, dids;
+    lira_index_t* h = nullptr;
+    int rc = 0;
+    auto body = [&]() -> int {
+        cudaStream_t st0 = nullptr;
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+        int r = upload_rows(dbase, base, N, d, ds, st0);
+        if (!r) r = dids.ensure((size_t)N * 4);
+        if (!r) {
+            std::vector<int32_t> ids(N);
+            std::iota(ids.begin(), ids.end(), 0);
+            cudaMemcpyAsync(dids.p, ids.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st0);
+            cudaStreamSynchronize(st0);
+        }
+        cudaStreamDestroy(st0);
+        if (r) return r;
+        if (int r2 = lira_index_create_dev(dbase.as<float>(), ds, d, off.data(), dids.as<int>(), nseg, metric, device, &h)) return r2;
+        cudaStream_t st = h->stream;
+        Workspace& ws = h->ws;
+        const long long max_pairs = 16ll << 20;
+        const long long qb = std::max<long long>(1, std::min<long long>(std::max<int64_t>(Q, 1), max_pairs / nseg));
+        for (long long q0 = 0; q0 < Q; q0 += qb) {
+            const long long nq = std::min<long long>(qb, Q - q0);
+            if (int r3 = upload_rows(ws.q, query + q0 * d, nq, d, ds, st)) return r3;
+            ProbeSpec ps;
+            ps.kind = 2;
+            if (int r3 = ws.D.ensure((size_t)nq * k * 4)) return r3;
+            if (int r3 = ws.I.ensure((size_t)nq * k * 8)) return r3;
+            if (int r3 = search_core(h, ws.q.as<float>(), ds, nq, ps, k, 1, ws.D.as<float>(), ws.I.as<long long>(), nullptr, nullptr, st)) return r3;
+            LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)q0 * k, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)q0 * k, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    };
+    rc = body();
+    if (h) lira_index_free(h);
+    dbase.release();
+    dids.release();
+    return rc;
+}
+
+// ---- multi-GPU merge ---------------------------------------------------------------------------
+namespace {
+__global__ void pack_keys_kernel(const float* D, const long long* I, long long n, int is_ip, unsigned long long* keys) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long id = I[i];
+        keys[i] = id < 0 ? KEY_INF : make_key(is_ip ? -D[i] : D[i], (uint32_t)id);
+    }
+}
+__global__ void rank_slots_kernel(long long* probe_offsets, int* probe_slot, long long Q, int R) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= Q * R; i += (long long)gridDim.x * blockDim.x) {
+        if (i <= Q) probe_offsets[i] = i * R;
+        if (i < Q * R) {
+            const long long q = i / R, r = i % R;
+            probe_slot[i] = (int)(r * Q + q);
+        }
+    }
+}
+struct RankMergeWs {
+    DevBuf po, ps;
+};
+static RankMergeWs g_rm[16];
+}  // namespace
+
+int lira_pack_keys_dev(const float* d_D, const int64_t* d_I, int64_t n, int metric, uint64_t* d_keys, int device,
+                       void* stream) {
+    LIRA_REQUIRE(d_D && d_I && d_keys && n >= 0, "bad argument");
+    if (int rc = check_device(device)) return rc;
+    if (n == 0) return 0;
+    pack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_D, (const long long*)d_I, n, metric == LIRA_METRIC_IP,
+                                                                         (unsigned long long*)d_keys);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+int lira_merge_ranks_dev(const uint64_t* d_keys_in, int R, int64_t Q, int k, int metric, int dedup, float* d_D,
+                         int64_t* d_I, int device, void* stream) {
+    LIRA_REQUIRE(d_keys_in && d_D && d_I && R >= 1 && Q >= 0 && k >= 1 && k <= 128, "bad argument");
+    LIRA_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
+    LIRA_REQUIRE(Q * (long long)R < (1ll << 31), "Q * R too large");
+    if (int rc = check_device(device)) return rc;
+    if (Q == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    RankMergeWs& w = g_rm[device];
+    if (int rc = w.po.ensure((size_t)(Q + 1) * 8)) return rc;
+    if (int rc = w.ps.ensure((size_t)Q * R * 4)) return rc;
+    rank_slots_kernel<<<grid_for(Q * R + 1, 256), 256, 0, st>>>(w.po.as<long long>(), w.ps.as<int>(), Q, R);
+    LIRA_LAUNCH_CHECK();
+    MergeParams mp{(const unsigned long long*)d_keys_in, w.po.as<long long>(), w.ps.as<int>(), k, (int)Q, dedup, d_D,
+                   (long long*)d_I, metric == LIRA_METRIC_IP};
+    return launch_merge(mp, st);
+}
+
+}  // extern "C"

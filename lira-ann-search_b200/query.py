@@ -1,0 +1,165 @@
+"""The query-phase functions the reference defines inside its drivers, with the same call shapes:
+get_cmp_recall (LIRA_smallscale.py:145-174, LIRA_largescale.py:120-149), query_tuning
+(LIRA_smallscale.py:176-241, LIRA_largescale.py:151-179), plus the search.cpp main loop
+(search.cpp:413-549) as `search_sweep`.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from . import _cabi as C
+from .engine import ListView, LiraIndex
+from .utils import KnnDistrIds, fprint
+
+
+def get_cmp_recall(inner_indexes, x_q, xd_id_bkt, cfg):
+    """Search every partition for every query.
+    -> search_time [n_q, n_bkt] f64, cmp_distr_all [n_q, n_bkt] int, found_aknn_id [n_q, n_bkt, k] int (-1 init).
+
+    `inner_indexes` is what create_inner_indexes returned (per-bucket views of one device index): the
+    whole n_q x n_bkt sweep is ONE grouped scan on the GPU instead of n_q*n_bkt faiss calls.
+    A per-pair wall time has no meaning for a batched kernel; search_time[q, b] is the batch time
+    apportioned by list size (t_batch * n_b / sum_b n_b / n_q), so that query_tuning's QPS column,
+    1 / mean_q sum_{b probed} search_time[q, b], is the batch throughput restricted to the probed lists."""
+    n_bkt, k = cfg.n_bkt, cfg.k
+    x_q = np.ascontiguousarray(x_q, np.float32)
+    n_q = len(x_q)
+    views = [v for v in inner_indexes if isinstance(v, ListView)]
+    if len(views) != n_bkt or any(v.index is not views[0].index for v in views):
+        raise ValueError("inner_indexes must come from create_inner_indexes / create_flat_indexes")
+    index: LiraIndex = views[0].index
+    t0 = time.time()
+    found, cmp_ = index.scan_all_pairs(x_q, k)
+    elapsed = time.time() - t0
+    sizes = index.list_sizes().astype(np.float64)
+    total = max(sizes.sum(), 1.0)
+    search_time = np.broadcast_to(elapsed * sizes / total / max(n_q, 1), (n_q, n_bkt)).copy()
+    # reference dtype: np.zeros(..., dtype=int) / np.full(..., -1) -> int64
+    return search_time, cmp_.astype(int), found.astype(int)
+
+
+def _found_mask(knn_distr_id, found_aknn_id, knn_query=None):
+    """in_found[q, j, c]: ground-truth id knn[q, j] was returned by the search of the bucket holding
+    its c-th copy. Equivalent to set(knn_distr_id[q][b]) & set(found_aknn_id[q][b]) summed over b."""
+    if not isinstance(knn_distr_id, KnnDistrIds):
+        raise TypeError("knn_distr_id must come from utils.get_knn_distr_redundancy")
+    knn, member = knn_distr_id.knn, knn_distr_id.member
+    Q, k, n_mul = member.shape
+    qq = np.arange(Q)[:, None, None]
+    safe = np.where(member >= 0, member, 0)
+    got = found_aknn_id[qq, safe]  # [Q, k, n_mul, kfound]
+    return (got == knn[:, :, None, None]).any(-1) & (member >= 0)
+
+
+def _tuning_rows(all_outputs, knn_distr_id, found_aknn_id, search_time, cmp_distr_all, k, thresholds):
+    all_outputs = np.asarray(all_outputs)
+    member = knn_distr_id.member
+    in_found = _found_mask(knn_distr_id, np.asarray(found_aknn_id))
+    safe = np.where(member >= 0, member, 0)
+    qq = np.arange(all_outputs.shape[0])[:, None, None]
+    rows = []
+    for thr in thresholds:
+        probed = all_outputs > thr  # LIRA_smallscale.py:206
+        nprobe = probed.sum(1)
+        cmp_ = (np.asarray(cmp_distr_all) * probed).sum(1)
+        hit = (in_found & probed[qq, safe]).any(-1)  # [Q, k]: id found in >= 1 probed bucket
+        # set semantics (LIRA_smallscale.py:210-214): a repeated ground-truth id counts once
+        knn = knn_distr_id.knn
+        if (np.sort(knn, 1)[:, 1:] == np.sort(knn, 1)[:, :-1]).any():
+            rec = np.array([len(set(knn[q][hit[q]].tolist())) for q in range(len(knn))]) / k
+        else:
+            rec = hit.sum(1) / k
+        t = (np.asarray(search_time) * probed).sum(1) if search_time is not None else None
+        rows.append((thr, nprobe.mean(), rec.mean(), cmp_.mean(), None if t is None else t.mean()))
+    return rows
+
+
+def query_tuning(all_outputs, knn_distr_id, found_aknn_id, search_time, cmp_distr_all, cfg, fw, part=0,
+                 thresholds=None):
+    """Threshold sweep of the small-scale driver (LIRA_smallscale.py:176-241): writes
+    {pth_log}{file_name}_tuning_threshold/{duplicate_type}_{part}.csv with columns
+    threshold,nprobe,Recall,Computations,QPS and returns the DataFrame."""
+    import pandas as pd
+    thresholds = np.arange(0.02, 0.82, 0.02) if thresholds is None else thresholds
+    os.makedirs(cfg.pth_log + cfg.file_name + "_tuning_threshold/", exist_ok=True)
+    fprint("", fw)
+    fprint("=" * 90, fw)
+    fprint(f"Query Tuning Results - Part {part}", fw)
+    fprint(f"Dataset: {cfg.dataset}, n_bkt: {cfg.n_bkt}, metric: {cfg.dis_metric}, "
+           f"redundancy_ratio: {cfg.redundancy_ratio}", fw)
+    fprint(f"Number of queries: {len(all_outputs)}", fw)
+    fprint("=" * 90, fw)
+    out = []
+    for thr, nprobe, rec, cmp_, t in _tuning_rows(all_outputs, knn_distr_id, found_aknn_id, search_time,
+                                                  cmp_distr_all, cfg.k, thresholds):
+        qps = 1.0 / t if t and t > 0 else 0.0
+        fprint(f"threshold: {thr:.3f}, nprobe: {nprobe:.2f}, Recall: {rec:.4f}, Computations: {cmp_:.0f}, "
+               f"QPS: {qps:.2f}", fw)
+        out.append({"threshold": thr, "nprobe": nprobe, "Recall": rec, "Computations": cmp_, "QPS": qps})
+    df = pd.DataFrame(out, columns=["threshold", "nprobe", "Recall", "Computations", "QPS"])
+    csv_path = cfg.pth_log + cfg.file_name + f"_tuning_threshold/{cfg.duplicate_type}_{part}.csv"
+    df.to_csv(csv_path, index=False)
+    fprint(f">> Query tuning CSV saved to: {csv_path}", fw)
+    return df
+
+
+def query_tuning_large(all_outputs, knn_distr_id, found_aknn_id, cmp_distr_all, cfg, part=0, thresholds=None):
+    """Large-scale variant (LIRA_largescale.py:151-179): thresholds arange(0.1, 1.0, 0.02), no QPS column.
+    (The reference reads cmp_distr_all from a module global; it is an argument here.)"""
+    import pandas as pd
+    thresholds = np.arange(0.1, 1.0, 0.02) if thresholds is None else thresholds
+    out = []
+    for thr, nprobe, rec, cmp_, _ in _tuning_rows(all_outputs, knn_distr_id, found_aknn_id, None, cmp_distr_all,
+                                                  cfg.k, thresholds):
+        print(f"threshold: {thr:.3f}, nprobe: {nprobe}, KNN Recall: {rec:.4f}, KNN Computations: {cmp_:.4f}")
+        out.append({"threshold": thr, "nprobe": nprobe, "Recall": rec, "Computations": cmp_})
+    df = pd.DataFrame(out, columns=["threshold", "nprobe", "Recall", "Computations"])
+    os.makedirs(cfg.pth_log + cfg.file_name + "_tuning_threshold/", exist_ok=True)
+    df.to_csv(cfg.pth_log + cfg.file_name + f"_tuning_threshold/{cfg.duplicate_type}_{part}.csv", index=False)
+    return df
+
+
+def recall_at_k(ids, gt, k):
+    """search.cpp:520-528: mean over queries of |gt[q,:k] & result[q]| / k."""
+    ids, gt = np.asarray(ids)[:, :k], np.asarray(gt)[:, :k]
+    hit = (gt[:, :, None] == ids[:, None, :]).any(-1)
+    return float(hit.sum(1).mean() / k)
+
+
+def cpp_thresholds(t_min=0.02, t_max=0.80, t_step=0.02):
+    """search.cpp:413: `for (float thr = t_min; thr <= t_max + 1e-6f; thr += t_step)` in fp32."""
+    out, thr = [], np.float32(t_min)
+    while thr <= np.float32(t_max) + np.float32(1e-6):
+        out.append(float(thr))
+        thr = np.float32(thr + np.float32(t_step))
+    return out
+
+
+def search_sweep(index: LiraIndex, model, x_q, gt_ids, k, thresholds=None, mode=C.SELECT_GE_ARGMAX, dedup=True,
+                 out=print):
+    """search.cpp:413-549: per threshold, run the whole query phase over all queries and report
+    Threshold / avg_recall / avg_nprobe / avg_cmp / avg_time(q) / QPS. Returns the rows as dicts.
+    dedup=False reproduces the reference binary's select-then-collapse behaviour exactly."""
+    thresholds = cpp_thresholds() if thresholds is None else thresholds
+    x_q = np.ascontiguousarray(x_q, np.float32)
+    rows = []
+    for thr in thresholds:
+        t0 = time.perf_counter()
+        _, ids, nprobe, cmp_ = index.probe_search(model, x_q, mode, thr, k, dedup)
+        dt = time.perf_counter() - t0
+        row = {"Threshold": thr, "avg_recall": recall_at_k(ids, gt_ids, k), "avg_nprobe": float(nprobe.mean()),
+               "avg_cmp": float(cmp_.mean()), "avg_time(q)": dt / len(x_q), "QPS": len(x_q) / dt}
+        rows.append(row)
+        if out:
+            out(f"=== Threshold = {thr:g} ===")
+            out(f"Threshold    : {thr:g}")
+            out(f"avg_recall   : {row['avg_recall']:g}")
+            out(f"avg_nprobe   : {row['avg_nprobe']:g}")
+            out(f"avg_cmp      : {row['avg_cmp']:g}")
+            out(f"avg_time(q)  : {row['avg_time(q)']:g} s")
+            out(f"QPS          : {row['QPS']:g} q/s")
+            out("----------------------------------------")
+    return rows

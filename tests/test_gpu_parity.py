@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the
+same seeded inputs and against the golden fixtures produced by the reference's own code.
+Bars: ids bit-exact except for distance ties; fp32 distances within 1e-5 relative; recall identical."""
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import RTOL, assert_topk_equiv, random_lists, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lira_ann_search_b200 as L
+    L._cabi.require_gpu()
+    return L
+
+
+def lists_csr(x_d, cluster_ids):
+    return O.build_lists_from_cluster_ids(x_d, cluster_ids)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1/a2 features, a3 model
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["toy_l2", "toy_ip"])
+def test_features_match_reference(L, golden, case):
+    z = golden(case)
+    raw = L.centroid_features(z["x_q"], z["centroids"])
+    np.testing.assert_allclose(raw, O.features_cpp(z["x_q"], z["centroids"]), rtol=2e-6, atol=1e-6)
+    got = L.centroid_features(z["x_q"], z["centroids"], z["scaler_mean"], z["scaler_scale"])
+    np.testing.assert_allclose(got, z["dist_q_scaled"], rtol=1e-4, atol=1e-4)  # vs the reference's Python
+    np.testing.assert_allclose(got, O.features_cpp(z["x_q"], z["centroids"], z["scaler_mean"], z["scaler_scale"]),
+                               rtol=1e-4, atol=2e-5)  # vs the C++ twin's fp32 arithmetic
+
+
+def test_features_odd_shapes_and_zero_scale(L):
+    rng = np.random.RandomState(1)
+    q, c = rng.randn(131, 10).astype(np.float32), rng.randn(37, 10).astype(np.float32)  # d % 4 != 0, B % 4 != 0
+    mean, scale = rng.rand(37).astype(np.float32), rng.rand(37).astype(np.float32) + 0.5
+    scale[5] = 0.0  # search.cpp:246: scale == 0 acts as 1
+    np.testing.assert_allclose(L.centroid_features(q, c, mean, scale), O.features_cpp(q, c, mean, scale),
+                               rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["toy_l2", "toy_ip"])
+def test_model_scores_match_reference(L, golden, case):
+    z = golden(case)
+    w = [z[f"mlp_{i}"] for i in range(12)]
+    model = L.LiraModel.from_arrays(z["centroids"], z["scaler_mean"], z["scaler_scale"], w)
+    scores, feats = model.scores(z["x_q"], return_features=True)
+    np.testing.assert_allclose(feats, z["dist_q_scaled"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(scores, z["all_outputs"], rtol=1e-4, atol=2e-6)  # reference torch forward
+    _, probs, _ = O.mlp_forward(O.features_cpp(z["x_q"], z["centroids"], z["scaler_mean"], z["scaler_scale"]),
+                                z["x_q"], w)
+    np.testing.assert_allclose(scores, probs, rtol=1e-4, atol=2e-6)  # fp64 arbiter
+
+
+# ---------------------------------------------------------------------------------------------
+# a6/a7 per-list search and the all-pairs sweep
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,part", [("toy_l2", 0), ("toy_l2", 1), ("toy_ip", 1)])
+def test_get_cmp_recall_matches_reference(L, golden, case, part):
+    z = golden(case)
+    k, metric = int(z["k"]), int(z["metric"])
+    off, ids = z[f"lists{part}_off"], z[f"lists{part}_ids"]
+    index = L.LiraIndex.from_csr(z["x_d"], off, ids, metric)
+    found, cmp_ = index.scan_all_pairs(z["x_q"], k)
+    assert np.array_equal(cmp_, z[f"cmp{part}"])
+    ref = z[f"found{part}"]
+    if case == "toy_l2":  # integer data: fp32 arithmetic is exact, so the result must be bit-identical
+        assert np.array_equal(found, ref)
+    else:  # float data: identical except where two candidates tie within the tolerance
+        bad = np.nonzero((found != ref).any(-1))
+        for qi, b in zip(*bad):
+            q = z["x_q"][qi].astype(np.float64)
+            a = (z["x_d"][found[qi, b]].astype(np.float64) * q).sum(1)
+            r = (z["x_d"][ref[qi, b]].astype(np.float64) * q).sum(1)
+            np.testing.assert_allclose(a, r, rtol=RTOL, atol=RTOL)
+
+
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("k", [1, 10, 33, 100])
+def test_list_search_is_indexflat(L, metric, k):
+    rng = np.random.RandomState(k)
+    x_d, x_q = synth(1500, 20, 70, seed=7 + k, integer=(metric == O.L2))
+    cl = random_lists(len(x_d), 6, rng, empty=(2,))
+    cl[4] = cl[4][:5]  # shorter than k for k >= 10
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_cluster_ids(x_d, cl, metric)
+    assert [index.ntotal(b) for b in range(6)] == [len(c) for c in cl]
+    for b in range(6):
+        D, I = index.list_search(b, x_q, k)
+        D_ref, I_ref = O.list_search(vecs[off[b]:off[b + 1]], x_q, k, metric, O.F64)
+        assert_topk_equiv(D, I, D_ref, I_ref, x_q, vecs[off[b]:off[b + 1]], metric)
+        if metric == O.L2:  # integer data: exact, including tie order (lower position first)
+            assert np.array_equal(I, I_ref)
+
+
+def test_list_search_views_have_the_faiss_surface(L):
+    x_d, x_q = synth(600, 16, 5, seed=3)
+    cl = random_lists(600, 4, np.random.RandomState(0))
+
+    class Cfg:
+        n_bkt, k, dis_metric = 4, 7, "L2"
+    inner = L.create_inner_indexes(x_d, cl, Cfg)
+    assert len(inner) == 4 and inner[1].ntotal == len(cl[1])
+    D, I = inner[1].search(x_q[0].reshape(1, -1), 7)
+    D_ref, I_ref = O.list_search(x_d[cl[1]], x_q[:1], 7, O.L2, O.F64)
+    assert np.array_equal(I, I_ref) and np.allclose(D, D_ref)
+    _, cmp_, found = L.get_cmp_recall(inner, x_q, cl, Cfg)
+    off, ids, vecs = lists_csr(x_d, cl)
+    f_ref, c_ref = O.scan_all_pairs(off, ids, vecs, x_q, 7, O.L2, O.F64)
+    assert np.array_equal(found, f_ref) and np.array_equal(cmp_, c_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# a10 online search with explicit probe sets
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,integer", [(O.L2, True), (O.L2, False), (O.IP, False)])
+@pytest.mark.parametrize("dedup", [1, 0])
+def test_search_matches_oracle(L, metric, integer, dedup):
+    rng = np.random.RandomState(11)
+    x_d, x_q = synth(5000, 24, 333, seed=5, integer=integer)
+    B, k = 40, 10
+    cl = random_lists(len(x_d), B, rng, redundancy=0.5, empty=(7,))
+    off, ids, vecs = lists_csr(x_d, cl)
+    nprobe = rng.randint(0, 9, len(x_q))  # ragged, some queries probe nothing
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    pids = np.concatenate([rng.choice(B, n, replace=False) for n in nprobe] + [np.empty(0, int)]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    D, I, cmp_ = index.search(x_q, poff, pids, k, dedup=bool(dedup))
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, dedup)
+    assert np.array_equal(cmp_, cmp_ref)
+    if dedup:
+        assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, metric)
+        if integer:
+            assert np.array_equal(I, I_ref)
+    else:  # select-then-collapse: compare as sets per query (slot stealing depends on exact tie order)
+        if integer:
+            assert np.array_equal(I, I_ref)
+        else:
+            assert np.mean([set(a[a >= 0]) == set(b[b >= 0]) for a, b in zip(I, I_ref)]) > 0.98
+
+
+def test_search_large_group_tiles_and_k100(L):
+    """Every query probes the same few lists -> groups larger than one 64-row tile; k = 100 path."""
+    x_d, x_q = synth(4000, 32, 203, seed=9, integer=False)
+    B, k = 8, 100
+    cl = random_lists(len(x_d), B, np.random.RandomState(2), redundancy=1.0)
+    off, ids, vecs = lists_csr(x_d, cl)
+    poff = np.arange(len(x_q) + 1, dtype=np.int64) * 3
+    pids = np.tile(np.array([1, 4, 6], np.int32), len(x_q))
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    D, I, _ = index.search(x_q, poff, pids, k)
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, k, O.L2, O.F64, 1)
+    assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, O.L2)
+
+
+def test_duplicate_vectors_and_dimension_padding(L):
+    """Exact duplicates (ties broken by position / id) and d not a multiple of 4."""
+    rng = np.random.RandomState(4)
+    base = rng.randint(0, 4, (300, 6)).astype(np.float32)  # many exact ties
+    base = np.concatenate([base, base[:50]])  # duplicated rows
+    x_q = rng.randint(0, 4, (40, 6)).astype(np.float32)
+    cl = random_lists(len(base), 5, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(base, cl)
+    index = L.LiraIndex.from_csr(base, off, ids, O.L2)
+    found, _ = index.scan_all_pairs(x_q, 10)
+    f_ref, _ = O.scan_all_pairs(off, ids, vecs, x_q, 10, O.L2, O.F64)
+    assert np.array_equal(found, f_ref)
+    poff = np.arange(len(x_q) + 1, dtype=np.int64) * 5
+    pids = np.tile(np.arange(5, dtype=np.int32), len(x_q))
+    D, I, _ = index.search(x_q, poff, pids, 10)
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
+
+
+def test_empty_inputs(L):
+    x_d, x_q = synth(200, 8, 4, seed=1)
+    cl = [[], list(range(200)), []]
+    index = L.LiraIndex.from_cluster_ids(x_d, cl, O.L2)
+    D, I = index.list_search(0, x_q, 3)
+    assert (I == -1).all() and np.isinf(D).all()
+    D, I, cmp_ = index.search(x_q, np.zeros(5, np.int64), np.empty(0, np.int32), 3)
+    assert (I == -1).all() and (cmp_ == 0).all()
+    found, cmp_ = index.scan_all_pairs(x_q, 3)
+    assert (found[:, 0] == -1).all() and (found[:, 2] == -1).all() and (cmp_[:, 1] == 200).all()
+    D, I = index.list_search(1, x_q[:0], 3)
+    assert D.shape == (0, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole query phase
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["toy_l2", "toy_ip"])
+def test_query_phase_matches_reference_search_cpp(L, golden, case):
+    """features -> MLP -> '>=' select + argmax fallback -> scan -> select-then-collapse -> recall, against the
+    stdout of the unmodified reference search.cpp on the same artifacts (tests/golden/*.npz: cpp_rows)."""
+    z = golden(case)
+    k, B, metric = int(z["k"]), int(z["n_bkt"]), int(z["metric"])
+    w = [z[f"mlp_{i}"] for i in range(12)]
+    index = L.LiraIndex.from_data_2_bkt(z["x_d"], z["d2b1"], B, metric)
+    model = L.LiraModel.from_arrays(z["centroids"], z["scaler_mean"], z["scaler_scale"], w)
+    scores = model.scores(z["x_q"])
+    rows = L.search_sweep(index, model, z["x_q"], z["gt"], k, mode=L.SELECT_GE_ARGMAX, dedup=False, out=None)
+    ref = z["cpp_rows"]
+    assert len(rows) == len(ref) == 40
+    Q = len(z["x_q"])
+    for row, r in zip(rows, ref):
+        # a score within 1e-6 of the threshold may fall on either side (fp32 MLP rounding)
+        edge = int((np.abs(scores.astype(np.float64) - row["Threshold"]) < 1e-6).sum())
+        assert abs(row["avg_nprobe"] - r[2]) <= edge / Q + 1e-5 * max(1.0, r[2])
+        if edge == 0:
+            assert abs(row["avg_cmp"] - r[3]) <= 1e-5 * max(1.0, r[3])
+            assert abs(row["avg_recall"] - r[1]) <= (1e-5 if case == "toy_l2" else 2.0 / (k * Q))
+
+
+@pytest.mark.parametrize("mode,value", [(0, 0.3), (1, 0.3), (1, 0.999999), (2, 1), (2, 5), (2, 40)])
+def test_probe_search_selection_modes(L, golden, mode, value):
+    z = golden("toy_l2")
+    k, B, metric = int(z["k"]), int(z["n_bkt"]), int(z["metric"])
+    w = [z[f"mlp_{i}"] for i in range(12)]
+    index = L.LiraIndex.from_data_2_bkt(z["x_d"], z["d2b1"], B, metric)
+    model = L.LiraModel.from_arrays(z["centroids"], z["scaler_mean"], z["scaler_scale"], w)
+    scores = model.scores(z["x_q"])
+    D, I, nprobe, cmp_ = index.probe_search(model, z["x_q"], mode, value, k)
+    # oracle selection on the GPU's own fp32 scores (selection is exact arithmetic on given scores)
+    poff, pids = O.select(scores, mode, value)
+    assert np.array_equal(nprobe, np.diff(poff))
+    off, ids, vecs = O.build_lists_from_data_2_bkt(z["x_d"], z["d2b1"], B)
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, z["x_q"], poff, pids, k, metric, O.F64, 1)
+    assert np.array_equal(cmp_, cmp_ref)
+    assert np.array_equal(I, I_ref) and np.allclose(D, D_ref, rtol=RTOL)
+
+
+def test_query_tuning_matches_reference_csv(L, golden, tmp_path):
+    """create_inner_indexes -> get_cmp_recall -> query_tuning with the reference's call shapes against the
+    CSV the reference's own query_tuning wrote for the same index (tests/golden: tuning1)."""
+    z = golden("toy_l2")
+    k, B = int(z["k"]), int(z["n_bkt"])
+    off, ids = z["lists1_off"], z["lists1_ids"]
+    cluster_ids = [ids[off[b]:off[b + 1]].tolist() for b in range(B)]
+
+    class Cfg:
+        n_bkt, dis_metric, dataset, redundancy_ratio, duplicate_type = B, "L2", "toy", 0.25, "model"
+        pth_log, file_name = str(tmp_path) + "/", "toy"
+    Cfg.k = k
+    inner = L.create_inner_indexes(z["x_d"], cluster_ids, Cfg)
+    search_time, cmp_all, found = L.get_cmp_recall(inner, z["x_q"], cluster_ids, Cfg)
+    assert found.shape == (len(z["x_q"]), B, k) and np.array_equal(found, z["found1"])
+    cnt, knn_ids = L.get_knn_distr_redundancy(z["gt"][:, :k], z["d2b1"], Cfg)
+    assert np.array_equal(cnt, z["knn_cnt1"])
+    df = L.query_tuning(z["all_outputs"], knn_ids, found, search_time, cmp_all, Cfg, None, part=1)
+    got = df[["threshold", "nprobe", "Recall", "Computations"]].to_numpy(np.float64)
+    np.testing.assert_allclose(got, z["tuning1"], rtol=1e-9, atol=1e-12)
+    assert (df["QPS"] > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# a11 exact kNN
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,integer,k", [(O.L2, True, 11), (O.L2, False, 100), (O.IP, False, 10)])
+def test_knn_matches_oracle(L, metric, integer, k):
+    x_d, x_q = synth(20000, 32, 150, seed=21, integer=integer)
+    D, I = L.knn(x_d, x_q, k, metric)
+    D_ref, I_ref = O.knn(x_d, x_q, k, metric, O.F64)
+    assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, metric)
+    if integer:
+        assert np.array_equal(I, I_ref)
+
+
+def test_self_knn_drops_column_zero_like_compute_knn(L):
+    x_d, _ = synth(9000, 16, 1, seed=2, integer=False)
+    _, I = L.knn(x_d, x_d[:500], 6, O.L2)
+    assert np.array_equal(I[:, 0], np.arange(500))  # self first (distance 0)
+    _, I_ref = O.knn(x_d, x_d[:500], 6, O.L2, O.F64)
+    assert np.mean(I[:, 1:] == I_ref[:, 1:]) > 0.999
+EOF
+echo written
