@@ -278,5 +278,3 @@ def test_self_knn_drops_column_zero_like_compute_knn(L):
     assert np.array_equal(I[:, 0], np.arange(500))  # self first (distance 0)
     _, I_ref = O.knn(x_d, x_d[:500], 6, O.L2, O.F64)
     assert np.mean(I[:, 1:] == I_ref[:, 1:]) > 0.999
-EOF
-echo written
