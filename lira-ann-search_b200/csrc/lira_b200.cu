@@ -123,7 +123,7 @@ struct lira_index {
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
     Workspace ws;
-    bool timing = false;
+    bool timing = false, timing_pending = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_scan_ms = 0.f, last_total_ms = 0.f;
     long long last_scan_bytes = 0, last_scan_pairs = 0, last_Q = 0;
@@ -438,12 +438,16 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
         copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
         LIRA_LAUNCH_CHECK();
     }
-    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
+    if (h->timing) {
+        LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
+        h->timing_pending = true;
+    }
     return 0;
 }
 
 static int finish_timing(lira_index* h) {
-    if (!h->timing) return 0;
+    if (!h->timing || !h->timing_pending) return 0;
+    h->timing_pending = false;
     LIRA_CUDA_OK(cudaEventSynchronize(h->ev[3]));
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_scan_ms, h->ev[0], h->ev[1]));
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_total_ms, h->ev[2], h->ev[3]));
@@ -633,8 +637,11 @@ int lira_index_set_timing(lira_index_t* h, int enable) {
     h->timing = enable != 0;
     return 0;
 }
-int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes, int64_t* scan_pairs) {
-    LIRA_REQUIRE(h, "null index");
+int lira_index_last_timing(const lira_index_t* hc, float* scan_ms, float* total_ms, int64_t* scan_bytes, int64_t* scan_pairs) {
+    LIRA_REQUIRE(hc, "null index");
+    lira_index_t* h = const_cast<lira_index_t*>(hc);
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    if (int rc = finish_timing(h)) return rc;
     if (scan_ms) *scan_ms = h->last_scan_ms;
     if (total_ms) *total_ms = h->last_total_ms;
     if (scan_bytes) *scan_bytes = h->last_scan_bytes;

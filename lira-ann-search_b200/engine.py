@@ -13,6 +13,14 @@ import numpy as np
 from . import _cabi as C
 
 
+def _stream_handle(device, stream=None) -> int:
+    """cudaStream_t to hand to a *_dev entry point: torch's current stream on `device`. The legacy default
+    stream is passed as cudaStreamLegacy (0x1) because NULL means "the handle's own stream" in the C ABI."""
+    import torch
+    st = stream if stream is not None else torch.cuda.current_stream(device).cuda_stream
+    return int(st) if int(st) != 0 else 1
+
+
 def _metric_code(metric) -> int:
     if isinstance(metric, str):
         return C.METRIC_IP if metric.lower() in ("inner_product", "ip", "dot", "dot_product") else C.METRIC_L2
@@ -156,7 +164,7 @@ class LiraIndex:
                    torch.empty((Q,), dtype=torch.int32, device=d_q.device),
                    torch.empty((Q,), dtype=torch.int64, device=d_q.device))
         D, I, npb, cmp_ = out
-        st = stream if stream is not None else torch.cuda.current_stream(d_q.device).cuda_stream
+        st = _stream_handle(d_q.device, stream)
         C.check(C.lib().lira_probe_search_dev(self._h, model._h, d_q.data_ptr(), d_q.stride(0), Q, int(mode),
                                               float(value), int(k), int(bool(dedup)), D.data_ptr(), I.data_ptr(),
                                               npb.data_ptr(), cmp_.data_ptr(), st))
@@ -171,7 +179,7 @@ class LiraIndex:
                    torch.empty((Q,), dtype=torch.int32, device=d_q.device),
                    torch.empty((Q,), dtype=torch.int64, device=d_q.device))
         D, I, npb, cmp_ = out
-        st = stream if stream is not None else torch.cuda.current_stream(d_q.device).cuda_stream
+        st = _stream_handle(d_q.device, stream)
         C.check(C.lib().lira_select_search_dev(self._h, d_scores.data_ptr(), d_scores.stride(0), d_q.data_ptr(),
                                                d_q.stride(0), Q, int(mode), float(value), int(k), int(bool(dedup)),
                                                D.data_ptr(), I.data_ptr(), npb.data_ptr(), cmp_.data_ptr(), st))
@@ -183,7 +191,7 @@ class LiraIndex:
         D = torch.empty((Q, k), dtype=torch.float32, device=d_q.device)
         I = torch.empty((Q, k), dtype=torch.int64, device=d_q.device)
         cmp_ = torch.empty((Q,), dtype=torch.int64, device=d_q.device)
-        st = stream if stream is not None else torch.cuda.current_stream(d_q.device).cuda_stream
+        st = _stream_handle(d_q.device, stream)
         C.check(C.lib().lira_search_dev(self._h, d_q.data_ptr(), d_q.stride(0), Q, d_probe_offsets.data_ptr(),
                                         d_probe_ids.data_ptr(), int(d_probe_ids.numel()), int(k), int(bool(dedup)),
                                         D.data_ptr(), I.data_ptr(), cmp_.data_ptr(), st))

@@ -64,7 +64,8 @@ def pack_keys(D, I, metric, device):
     """(D[Q,k] f32, I[Q,k] i64) torch CUDA tensors -> int64 tensor of ordered (score, id) keys."""
     import torch
     keys = torch.empty(D.shape, dtype=torch.int64, device=D.device)
-    st = torch.cuda.current_stream(D.device).cuda_stream
+    from .engine import _stream_handle
+    st = _stream_handle(D.device)
     m = C.METRIC_IP if str(metric).lower() in ("1", "ip", "inner_product") else C.METRIC_L2
     C.check(C.lib().lira_pack_keys_dev(D.data_ptr(), I.data_ptr(), D.numel(), m, keys.data_ptr(), device, st))
     return keys
@@ -81,7 +82,8 @@ def allgather_merge(D, I, k, metric="L2", dedup=True, device=0, group=None):
     Q = keys.shape[0]
     D_out = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
     I_out = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
-    st = torch.cuda.current_stream(keys.device).cuda_stream
+    from .engine import _stream_handle
+    st = _stream_handle(keys.device)
     m = C.METRIC_IP if str(metric).lower() in ("1", "ip", "inner_product") else C.METRIC_L2
     C.check(C.lib().lira_merge_ranks_dev(gathered.data_ptr(), world, Q, int(k), m, int(bool(dedup)),
                                          D_out.data_ptr(), I_out.data_ptr(), device, st))
