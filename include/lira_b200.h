@@ -142,6 +142,17 @@ int64_t lira_launch_count(void);
 int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes,
                            int64_t* scan_pairs);
 int lira_index_set_timing(lira_index_t* h, int enable);
+/* The online search (lira_search*, lira_probe_search*, lira_select_search*) has two exact implementations
+ * of the list scan: fp32 CUDA cores (always valid) and tcgen05 tensor cores (taken for batches of >= 256
+ * queries when every stored value and every query value is an integer of at most 11 bits and d <= 128, so
+ * that TF32 products and fp32 sums are exact and both paths return identical bits).
+ * set_use_tensor_cores(0) pins the CUDA-core scan; last_path reports which one ran (0 CUDA cores, 1 tensor
+ * cores); tensor_core_eligible tells whether the stored vectors qualify. */
+int lira_index_set_use_tensor_cores(lira_index_t* h, int enable);
+int lira_index_last_path(const lira_index_t* h);
+int lira_index_last_redo(const lira_index_t* h); /* queries of the last tensor-core batch whose candidate buffer
+                                                    overflowed and that were answered by the CUDA-core scan */
+int lira_index_tensor_core_eligible(const lira_index_t* h);
 
 #ifdef __cplusplus
 }

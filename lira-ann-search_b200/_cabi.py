@@ -53,6 +53,10 @@ SIGNATURES = {
     "lira_launch_count": (c_i64, []),
     "lira_index_last_timing": (c_int, [c_vp, c_f32p, c_f32p, c_i64p, c_i64p]),
     "lira_index_set_timing": (c_int, [c_vp, c_int]),
+    "lira_index_set_use_tensor_cores": (c_int, [c_vp, c_int]),
+    "lira_index_last_path": (c_int, [c_vp]),
+    "lira_index_last_redo": (c_int, [c_vp]),
+    "lira_index_tensor_core_eligible": (c_int, [c_vp]),
 }
 
 _lib = None

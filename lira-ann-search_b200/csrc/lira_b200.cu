@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "probe_kernels.cuh"
+#include "tc_scan_kernels.cuh"
 
 namespace lira {
 
@@ -99,10 +100,11 @@ struct DevBuf {
 
 struct Workspace {
     DevBuf q, sel, nsel, cmp, list_count, cursor, group_offsets, probe_offsets, group_queries, probe_slot, items,
-        n_items, part_key, D, I, scores, probe_ids, nprobe;
+        n_items, part_key, D, I, scores, probe_ids, nprobe, top1, thr, gq, cand_key, cand_count, qnorm, flags, redo;
     void release() {
         for (DevBuf* b : {&q, &sel, &nsel, &cmp, &list_count, &cursor, &group_offsets, &probe_offsets, &group_queries,
-                          &probe_slot, &items, &n_items, &part_key, &D, &I, &scores, &probe_ids, &nprobe})
+                          &probe_slot, &items, &n_items, &part_key, &D, &I, &scores, &probe_ids, &nprobe, &top1, &thr, &gq,
+                          &cand_key, &cand_count, &qnorm, &flags, &redo})
             b->release();
     }
 };
@@ -122,7 +124,12 @@ struct lira_index {
     std::vector<long long> h_offsets;
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
-    Workspace ws;
+    Workspace ws, ws_seed;
+    float* vnorm = nullptr;      // |v|^2 per list entry (tensor-core path)
+    bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
+    bool use_tc = true;
+    int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
+    int last_redo = 0;           // queries of the last tensor-core batch redone on the CUDA cores
     bool timing = false, timing_pending = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_scan_ms = 0.f, last_total_ms = 0.f;
@@ -162,6 +169,7 @@ static int init_kernels(int device) {
     rc |= set_smem(scan_lists_kernel<OP_DOT, 1>, scan_smem_bytes<1>());
     rc |= set_smem(scan_lists_kernel<OP_L2, 4>, scan_smem_bytes<4>());
     rc |= set_smem(scan_lists_kernel<OP_DOT, 4>, scan_smem_bytes<4>());
+    rc |= set_smem(tc_scan_kernel, TC_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
@@ -243,10 +251,11 @@ struct ProbeSpec {
 };
 
 __global__ void csr_hist_kernel(const long long* probe_offsets, const int* probe_ids, const long long* list_offsets,
-                                int Q, int B, int* list_count, long long* cmp, int* nsel, int* bad) {
+                                int Q, int B, int* list_count, long long* cmp, int* nsel, int* bad, const int* mask) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
+    if (mask && !mask[q]) return;
     long long c = 0;
     const long long lo = probe_offsets[q], hi = probe_offsets[q + 1];
     for (long long j = lo + lane; j < hi; j += 32) {
@@ -264,10 +273,11 @@ __global__ void csr_hist_kernel(const long long* probe_offsets, const int* probe
 }
 
 __global__ void scatter_csr_kernel(const long long* probe_offsets, const int* probe_ids, const long long* group_offsets,
-                                   int* cursor, int* group_queries, int* probe_slot, int Q, int B) {
+                                   int* cursor, int* group_queries, int* probe_slot, int Q, int B, const int* mask) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
+    if (mask && !mask[q]) return;
     for (long long j = probe_offsets[q] + lane; j < probe_offsets[q + 1]; j += 32) {
         const int b = probe_ids[j];
         if (b < 0 || b >= B) continue;
@@ -309,18 +319,18 @@ static int launch_merge(const MergeParams& mp, cudaStream_t st) {
     return 0;
 }
 
-// Runs grouping + scan. On return ws.part_key / ws.probe_offsets / ws.probe_slot describe the partial
-// lists; *P_out is the number of (query, list) pairs.
-static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
-                            int store_local, long long* d_cmp, long long* P_out, cudaStream_t st) {
-    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+// Selection (or explicit / exhaustive probe sets) -> per-list query groups -> work items of `tile` query
+// rows. On return ws.group_queries / ws.probe_slot / ws.items / ws.n_items are set and *P_out is the number
+// of (query, list) pairs. `probe_offsets_out` is the CSR the merge must use.
+static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const ProbeSpec& ps, int tile, long long* d_cmp,
+                          long long* P_out, const long long** probe_offsets_out, int* extra_flag_host,
+                          const int* d_extra_flag, const int* d_mask, cudaStream_t st) {
     LIRA_REQUIRE(Q >= 0 && Q < (1ll << 31), "Q out of range");
-    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
-    Workspace& ws = h->ws;
     const int B = h->B;
     const int warps = 8;
     const int qgrid = (int)((Q + warps - 1) / warps);
     if (int rc = ws.nsel.ensure((size_t)(Q + 1) * 4)) return rc;
+    if (int rc = ws.top1.ensure((size_t)(Q + 1) * 8)) return rc;  // seed ids: two per query
     if (int rc = ws.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
     if (int rc = ws.group_offsets.ensure((size_t)(B + 1) * 8)) return rc;
     if (int rc = ws.list_count.ensure((size_t)(B + 1) * 4)) return rc;
@@ -330,30 +340,38 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
     LIRA_CUDA_OK(cudaMemsetAsync(ws.cursor.p, 0, (size_t)(B + 1) * 4, st));
     LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.p, 0, 128, st));
     long long P = 0;
-    if (Q == 0) { *P_out = 0; return 0; }
+    *P_out = 0;
+    if (Q == 0) return 0;
 
     if (ps.kind == 0) {
         LIRA_REQUIRE(ps.mode >= 0 && ps.mode <= 2, "unknown selection mode");
         if (ps.mode == LIRA_SELECT_TOPN) LIRA_REQUIRE(ps.value >= 1 && ps.value <= 128, "top-nprobe must be in [1, 128]");
         if (int rc = ws.sel.ensure((size_t)Q * B * 4)) return rc;
         SelectParams sp{ps.d_scores, ps.lds, (int)Q, B, ps.mode, ps.value, h->d_offsets, ws.sel.as<int>(),
-                        ws.nsel.as<int>(), d_cmp, ws.list_count.as<int>()};
+                        ws.nsel.as<int>(), d_cmp, ws.list_count.as<int>(), ws.top1.as<int>(), d_mask};
         select_kernel<4><<<qgrid, warps * 32, 0, st>>>(sp);
         LIRA_LAUNCH_CHECK();
         exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.nsel.as<int>(), ws.probe_offsets.as<long long>(), (int)Q);
         LIRA_LAUNCH_CHECK();
         exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
         LIRA_LAUNCH_CHECK();
+        // the one host round trip of the query phase: P sizes the partial-result buffers
         LIRA_CUDA_OK(cudaMemcpyAsync(&P, ws.probe_offsets.as<long long>() + Q, 8, cudaMemcpyDeviceToHost, st));
+        if (extra_flag_host && d_extra_flag)
+            LIRA_CUDA_OK(cudaMemcpyAsync(extra_flag_host, d_extra_flag, 4, cudaMemcpyDeviceToHost, st));
         LIRA_CUDA_OK(cudaStreamSynchronize(st));
     } else if (ps.kind == 1) {
         P = ps.P;
         int* bad = ws.n_items.as<int>() + 8;
         csr_hist_kernel<<<qgrid, warps * 32, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, h->d_offsets, (int)Q, B,
-                                                      ws.list_count.as<int>(), d_cmp, ws.nsel.as<int>(), bad);
+                                                      ws.list_count.as<int>(), d_cmp, ws.nsel.as<int>(), bad, d_mask);
         LIRA_LAUNCH_CHECK();
         exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
         LIRA_LAUNCH_CHECK();
+        if (extra_flag_host && d_extra_flag) {
+            LIRA_CUDA_OK(cudaMemcpyAsync(extra_flag_host, d_extra_flag, 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
     } else {
         P = Q * (long long)B;
     }
@@ -362,24 +380,22 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
     const size_t Ps = (size_t)std::max<long long>(P, 1);
     if (int rc = ws.group_queries.ensure(Ps * 4)) return rc;
     if (int rc = ws.probe_slot.ensure(Ps * 4)) return rc;
-    if (int rc = ws.part_key.ensure(Ps * k * 8)) return rc;
-    const size_t max_items = Ps / SCAN_TM_MAX + B + 1;
+    const size_t max_items = Ps / 8 + B + 1;  // generous: also covers a later re-tiling with a smaller tile
     if (int rc = ws.items.ensure(max_items * sizeof(ScanItem))) return rc;
 
-    const long long* probe_offsets = nullptr;
     if (ps.kind == 0) {
         ScatterParams sc{ws.sel.as<int>(), ws.nsel.as<int>(), ws.probe_offsets.as<long long>(),
                          ws.group_offsets.as<long long>(), ws.cursor.as<int>(), ws.group_queries.as<int>(),
                          ws.probe_slot.as<int>(), (int)Q, B};
         scatter_groups_kernel<<<qgrid, warps * 32, 0, st>>>(sc);
         LIRA_LAUNCH_CHECK();
-        probe_offsets = ws.probe_offsets.as<long long>();
+        *probe_offsets_out = ws.probe_offsets.as<long long>();
     } else if (ps.kind == 1) {
         scatter_csr_kernel<<<qgrid, warps * 32, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids,
                                                          ws.group_offsets.as<long long>(), ws.cursor.as<int>(),
-                                                         ws.group_queries.as<int>(), ws.probe_slot.as<int>(), (int)Q, B);
+                                                         ws.group_queries.as<int>(), ws.probe_slot.as<int>(), (int)Q, B, d_mask);
         LIRA_LAUNCH_CHECK();
-        probe_offsets = ps.d_probe_offsets;
+        *probe_offsets_out = ps.d_probe_offsets;
     } else {
         uniform_groups_kernel<<<grid_for(B + 1, 256), 256, 0, st>>>(ws.group_offsets.as<long long>(), B, Q);
         LIRA_LAUNCH_CHECK();
@@ -388,14 +404,20 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
         LIRA_LAUNCH_CHECK();
         iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(ws.probe_offsets.as<long long>(), Q, B);
         LIRA_LAUNCH_CHECK();
-        probe_offsets = ws.probe_offsets.as<long long>();
+        *probe_offsets_out = ws.probe_offsets.as<long long>();
     }
-    (void)probe_offsets;
-    build_items_kernel<<<1, 1024, 0, st>>>(h->d_list_order, ws.group_offsets.as<long long>(), h->d_offsets, B,
+    build_items_kernel<<<1, 1024, 0, st>>>(h->d_list_order, ws.group_offsets.as<long long>(), h->d_offsets, B, tile,
                                            ws.items.as<ScanItem>(), ws.n_items.as<int>(),
                                            (unsigned long long*)((char*)ws.n_items.p + 64));
     LIRA_LAUNCH_CHECK();
+    return 0;
+}
 
+// exact CUDA-core scan of the prepared work items -> ws.part_key[P, k]
+static int simt_scan(lira_index* h, Workspace& ws, const float* d_q, long long ldq, long long P, int k, int store_local,
+                     int max_rows, bool timed, cudaStream_t st) {
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
+    if (int rc = ws.part_key.ensure((size_t)std::max<long long>(P, 1) * k * 8)) return rc;
     ScanParams sp;
     sp.q = d_q;
     sp.ldq = ldq;
@@ -408,35 +430,158 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
     sp.part_key = ws.part_key.as<unsigned long long>();
     sp.k = k;
     sp.store_local = store_local;
-    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    sp.max_rows = max_rows;
+    if (timed && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
     if (int rc = launch_scan(h, sp, k, st)) return rc;
+    if (timed && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    return 0;
+}
+
+// grouping + exact scan (get_cmp_recall, list_search, kNN, and the online path on the CUDA cores)
+static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
+                            int store_local, long long* d_cmp, long long* P_out, const long long** po_out,
+                            cudaStream_t st, const int* d_mask = nullptr) {
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    const long long* po = nullptr;
+    if (int rc = prepare_groups(h, h->ws, Q, ps, SCAN_TM_MAX, d_cmp, P_out, &po, nullptr, nullptr, d_mask, st)) return rc;
+    if (po_out) *po_out = po;
+    if (Q == 0) return 0;
+    return simt_scan(h, h->ws, d_q, ldq, *P_out, k, store_local, 0, true, st);
+}
+
+static constexpr int TC_SEED_ROWS = 384;   // rows of each of the two best probed lists scanned exactly for the seed bound
+static constexpr int TC_CAND_CAP = 1024;   // candidate slots per query
+
+// The online query path on the tensor cores (tc_scan_kernels.cuh). *done = true when results were produced
+// for every query whose ws.redo flag is 0; *n_redo counts the queries (flag 1) whose candidate buffer
+// overflowed and that the caller must answer with the exact CUDA-core path. *done = false (no error) when
+// the batch does not qualify at all.
+static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k, int dedup,
+                     float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, bool* done, int* n_redo,
+                     cudaStream_t st) {
+    *done = false;
+    *n_redo = 0;
+    if (!h->tc_ok || h->ds > TC_MAX_KB * KC || Q < 256 || ps.kind == 2) return 0;
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
+    Workspace& ws = h->ws;
+    if (int rc = ws.qnorm.ensure((size_t)Q * 4)) return rc;
+    if (int rc = ws.flags.ensure(64)) return rc;
+    if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
+    int one_zero[2] = {1, 0};  // [0] query batch exactly representable, [1] number of overflowed queries
+    LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 8, cudaMemcpyHostToDevice, st));
+    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>());
+    LIRA_LAUNCH_CHECK();
+    long long P = 0;
+    const long long* po = nullptr;
+    int q_exact = 1;
+    if (int rc = prepare_groups(h, ws, Q, ps, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st)) return rc;
+    if (!q_exact || P == 0) return 0;  // not exact in TF32 (or nothing probed): exact CUDA-core path
+    if (ps.kind == 1) {
+        first_probes_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, (int)Q, ws.top1.as<int>());
+        LIRA_LAUNCH_CHECK();
+    }
+    if (d_nprobe) {
+        copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
+        LIRA_LAUNCH_CHECK();
+    }
+    // ---- seed: exact scan of the first rows of every query's two best lists -> T[q] ----
+    Workspace& sw = h->ws_seed;
+    if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
+    iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, 2);
+    LIRA_LAUNCH_CHECK();
+    ProbeSpec seed;
+    seed.kind = 1;
+    seed.d_probe_offsets = sw.probe_offsets.as<long long>();
+    seed.d_probe_ids = ws.top1.as<int>();
+    seed.P = 2 * Q;
+    long long Pseed = 0;
+    const long long* po_seed = nullptr;
+    // (prepare_groups re-ensures sw.probe_offsets with the same size: no reallocation, content kept)
+    if (int rc = prepare_groups(h, sw, Q, seed, SCAN_TM_MAX, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
+    if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, TC_SEED_ROWS, false, st)) return rc;
+    if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
+    seed_threshold_kernel<<<grid_for(Q, 128), 128, 0, st>>>(sw.part_key.as<unsigned long long>(), sw.probe_slot.as<int>(),
+                                                            ws.top1.as<int>(), (int)Q, k, ws.thr.as<float>());
+    LIRA_LAUNCH_CHECK();
+    // ---- queries in group order (one TMA box per tile) ----
+    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->ds * 4)) return rc;
+    gather_group_queries_kernel<<<grid_for(P * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
+                                                                                        ws.gq.as<float>());
+    LIRA_LAUNCH_CHECK();
+    CUtensorMap tmap_q;
+    if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
+    // ---- filter on the tensor cores ----
+    if (int rc = ws.cand_key.ensure((size_t)Q * TC_CAND_CAP * 8)) return rc;
+    if (int rc = ws.cand_count.ensure((size_t)Q * 4)) return rc;
+    LIRA_CUDA_OK(cudaMemsetAsync(ws.cand_count.p, 0, (size_t)Q * 4, st));
+    TcParams tp;
+    tp.group_queries = ws.group_queries.as<int>();
+    tp.list_offsets = h->d_offsets;
+    tp.items = ws.items.as<ScanItem>();
+    tp.n_items = ws.n_items.as<int>();
+    tp.nk = (h->ds + KC - 1) / KC;
+    tp.vnorm = h->vnorm;
+    tp.qnorm = ws.qnorm.as<float>();
+    tp.thr = ws.thr.as<float>();
+    tp.cand_key = ws.cand_key.as<unsigned long long>();
+    tp.cand_count = ws.cand_count.as<int>();
+    tp.cap = TC_CAND_CAP;
+    tp.is_ip = h->metric == LIRA_METRIC_IP;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    tc_scan_kernel<<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, tp);
+    LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    // ---- refine ----
+    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), TC_CAND_CAP, h->ids, k, (int)Q, dedup,
+                    h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1};
+    const int warps = 8;
+    if (k <= 32) refine_topk_kernel<1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else refine_topk_kernel<4><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    LIRA_LAUNCH_CHECK();
+    LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
+    LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    h->last_path = 1;
+    h->last_redo = *n_redo;
+    *done = true;
     return 0;
 }
 
 static int search_core(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
                        int dedup, float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st) {
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
     long long P = 0;
     h->last_Q = Q;
     h->last_k = k;
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
-    if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, d_cmp, &P, st)) return rc;
-    if (Q == 0) return 0;
-    Workspace& ws = h->ws;
-    MergeParams mp;
-    mp.part_key = ws.part_key.as<unsigned long long>();
-    mp.probe_offsets = ps.kind == 1 ? ps.d_probe_offsets : ws.probe_offsets.as<long long>();
-    mp.probe_slot = ws.probe_slot.as<int>();
-    mp.k = k;
-    mp.Q = (int)Q;
-    mp.dedup = dedup;
-    mp.out_dist = d_D;
-    mp.out_ids = d_I;
-    mp.is_ip = h->metric == LIRA_METRIC_IP;
-    if (int rc = launch_merge(mp, st)) return rc;
-    if (d_nprobe) {
-        copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
-        LIRA_LAUNCH_CHECK();
+    bool done = false;
+    int n_redo = 0;
+    if (h->use_tc) {
+        if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, st)) return rc;
+    }
+    if (!done || n_redo > 0) {
+        // exact CUDA-core path: the whole batch, or only the queries the tensor-core pass flagged
+        const int* mask = done ? h->ws.redo.as<int>() : nullptr;
+        if (!done) h->last_path = 0;
+        const long long* po = nullptr;
+        if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, done ? nullptr : d_cmp, &P, &po, st, mask)) return rc;
+        if (Q == 0) return 0;
+        Workspace& ws = h->ws;
+        MergeParams mp;
+        mp.part_key = ws.part_key.as<unsigned long long>();
+        mp.probe_offsets = po;
+        mp.probe_slot = ws.probe_slot.as<int>();
+        mp.k = k;
+        mp.Q = (int)Q;
+        mp.dedup = dedup;
+        mp.out_dist = d_D;
+        mp.out_ids = d_I;
+        mp.is_ip = h->metric == LIRA_METRIC_IP;
+        mp.mask = mask;
+        if (int rc = launch_merge(mp, st)) return rc;
+        if (d_nprobe && !done) {
+            copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
+            LIRA_LAUNCH_CHECK();
+        }
     }
     if (h->timing) {
         LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
@@ -486,6 +631,20 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     LIRA_CUDA_OK(cudaMemcpy(h->d_list_order, order.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
     if (int rc = make_tmap(&h->tmap, h->vecs, h->E, h->ds, h->ds)) return rc;
     for (auto& e : h->ev) LIRA_CUDA_OK(cudaEventCreate(&e));
+    // |v|^2 per entry and the exactness flag that gates the tensor-core path
+    LIRA_CUDA_OK(cudaMalloc(&h->vnorm, (size_t)std::max<long long>(h->E, 1) * 4));
+    int* d_flag = nullptr;
+    LIRA_CUDA_OK(cudaMalloc(&d_flag, 4));
+    int one = 1;
+    LIRA_CUDA_OK(cudaMemcpy(d_flag, &one, 4, cudaMemcpyHostToDevice));
+    if (h->E > 0) {
+        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag);
+        g_launches.fetch_add(1);
+    }
+    LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
+    LIRA_CUDA_OK(cudaMemcpy(&one, d_flag, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_flag);
+    h->tc_ok = (one == 1) && h->E > 0;
     cudaDeviceProp prop;
     LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
     h->num_sms = prop.multiProcessorCount;
@@ -616,7 +775,9 @@ int lira_index_free(lira_index_t* h) {
     if (h->owns) { cudaFree(h->vecs); cudaFree(h->ids); }
     cudaFree(h->d_offsets);
     cudaFree(h->d_list_order);
+    cudaFree(h->vnorm);
     h->ws.release();
+    h->ws_seed.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -631,6 +792,15 @@ int64_t lira_index_ntotal(const lira_index_t* h, int list) {
 }
 int lira_index_nlist(const lira_index_t* h) { return h ? h->B : -1; }
 int lira_index_dim(const lira_index_t* h) { return h ? h->d : -1; }
+
+int lira_index_set_use_tensor_cores(lira_index_t* h, int enable) {
+    LIRA_REQUIRE(h, "null index");
+    h->use_tc = enable != 0;
+    return 0;
+}
+int lira_index_last_path(const lira_index_t* h) { return h ? h->last_path : -1; }
+int lira_index_last_redo(const lira_index_t* h) { return h ? h->last_redo : -1; }
+int lira_index_tensor_core_eligible(const lira_index_t* h) { return h ? (h->tc_ok && h->ds <= TC_MAX_KB * KC ? 1 : 0) : -1; }
 
 int lira_index_set_timing(lira_index_t* h, int enable) {
     LIRA_REQUIRE(h, "null index");
@@ -668,12 +838,12 @@ int lira_index_list_search(lira_index_t* h, int list, const float* q, int64_t nq
     ProbeSpec ps;
     ps.kind = 1; ps.d_probe_offsets = d_po; ps.d_probe_ids = d_pi; ps.P = nq;
     long long P = 0;
-    if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, /*store_local=*/1, nullptr, &P, st)) return rc;
+    if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, /*store_local=*/1, nullptr, &P, nullptr, st)) return rc;
     if (nq == 0) return 0;
     if (int rc = ws.D.ensure((size_t)nq * k * 4)) return rc;
     if (int rc = ws.I.ensure((size_t)nq * k * 8)) return rc;
     MergeParams mp{ws.part_key.as<unsigned long long>(), d_po, ws.probe_slot.as<int>(), k, (int)nq, 0,
-                   ws.D.as<float>(), ws.I.as<long long>(), h->metric == LIRA_METRIC_IP};
+                   ws.D.as<float>(), ws.I.as<long long>(), h->metric == LIRA_METRIC_IP, nullptr};
     if (int rc = launch_merge(mp, st)) return rc;
     LIRA_CUDA_OK(cudaMemcpyAsync(D, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaMemcpyAsync(I, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -696,7 +866,7 @@ int lira_scan_all_pairs(lira_index_t* h, const float* q, int64_t Q, int k, int64
         ProbeSpec ps;
         ps.kind = 2;
         long long P = 0;
-        if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, 0, nullptr, &P, st)) return rc;
+        if (int rc = run_grouped_scan(h, ws.q.as<float>(), h->ds, nq, ps, k, 0, nullptr, &P, nullptr, st)) return rc;
         if (int rc = ws.I.ensure((size_t)P * k * 8)) return rc;
         if (int rc = ws.cmp.ensure((size_t)P * 8)) return rc;
         found_from_partials_kernel<<<grid_for(P * k, 256, 148 * 16), 256, 0, st>>>(
@@ -1009,7 +1179,7 @@ int lira_merge_ranks_dev(const uint64_t* d_keys_in, int R, int64_t Q, int k, int
     rank_slots_kernel<<<grid_for(Q * R + 1, 256), 256, 0, st>>>(w.po.as<long long>(), w.ps.as<int>(), Q, R);
     LIRA_LAUNCH_CHECK();
     MergeParams mp{(const unsigned long long*)d_keys_in, w.po.as<long long>(), w.ps.as<int>(), k, (int)Q, dedup, d_D,
-                   (long long*)d_I, metric == LIRA_METRIC_IP};
+                   (long long*)d_I, metric == LIRA_METRIC_IP, nullptr};
     return launch_merge(mp, st);
 }
 

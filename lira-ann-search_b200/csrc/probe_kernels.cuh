@@ -113,7 +113,28 @@ struct SelectParams {
     int* nsel;            // [Q]
     long long* cmp;       // [Q] sum of probed list sizes (search.cpp:477, LIRA_smallscale.py:208)
     int* list_count;      // [B] histogram (atomic)
+    int* seed_ids;        // [Q, 2] the two best-scoring selected partitions (-1 padded); may be null
+    const int* mask;      // optional [Q]: queries with mask[q] == 0 select nothing
 };
+
+// the two smallest keys of a warp's per-lane (k1 <= k2) pairs, broadcast to all lanes
+__device__ __forceinline__ void warp_two_smallest(unsigned long long k1, unsigned long long k2, unsigned long long& m1,
+                                                  unsigned long long& m2) {
+    unsigned long long a = k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = shfl_u64(a, (threadIdx.x & 31) ^ o);
+        a = t < a ? t : a;
+    }
+    m1 = a;
+    unsigned long long b = (k1 == m1) ? k2 : k1;  // keys are unique (partition id in the low word)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = shfl_u64(b, (threadIdx.x & 31) ^ o);
+        b = t < b ? t : b;
+    }
+    m2 = b;
+}
 
 template <int S>
 __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
@@ -124,6 +145,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     int* sel = p.sel + (size_t)q * p.B;
     int n = 0;
     long long cmp = 0;
+    if (p.mask && !p.mask[q]) {
+        if (lane == 0) p.nsel[q] = 0;
+        return;
+    }
     if (p.mode == SEL_TOPN) {
         int want = (int)p.value;
         if (want > p.B) want = p.B;
@@ -158,9 +183,17 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
             }
         }
         n = want;
+        if (p.seed_ids) {
+            const unsigned long long b0 = shfl_u64(key[0], 0), b1 = shfl_u64(key[0], 1);
+            if (lane == 0) {
+                p.seed_ids[2 * q + 0] = (b0 == KEY_INF || want < 1) ? -1 : (int)key_pos(b0);
+                p.seed_ids[2 * q + 1] = (b1 == KEY_INF || want < 2) ? -1 : (int)key_pos(b1);
+            }
+        }
     } else {
         float best = -INFINITY;
         int best_b = 0;
+        unsigned long long h1 = KEY_INF, h2 = KEY_INF;  // this lane's two best selected partitions
         for (int b0 = 0; b0 < p.B; b0 += 32) {
             const int b = b0 + lane;
             bool hit = false;
@@ -176,17 +209,29 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
                 sel[n + __popc(mm & ((1u << lane) - 1u))] = b;
                 atomicAdd(p.list_count + b, 1);
                 cmp += p.list_offsets[b + 1] - p.list_offsets[b];
+                const unsigned long long hk = make_key(-s[b], (uint32_t)b);
+                if (hk < h1) { h2 = h1; h1 = hk; } else if (hk < h2) { h2 = hk; }
             }
             n += __popc(mm);
         }
-        if (p.mode == SEL_GE_ARGMAX && n == 0) {
-            // argmax fallback, first maximum wins (search.cpp:456-466)
+        // global argmax, first maximum wins (search.cpp:456-466); it is always selected when anything is
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int obb = __shfl_xor_sync(0xffffffffu, best_b, o);
-                if (ob > best || (ob == best && obb < best_b)) { best = ob; best_b = obb; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int obb = __shfl_xor_sync(0xffffffffu, best_b, o);
+            if (ob > best || (ob == best && obb < best_b)) { best = ob; best_b = obb; }
+        }
+        if (p.seed_ids) {
+            unsigned long long m1, m2;
+            warp_two_smallest(h1, h2, m1, m2);
+            if (lane == 0) {
+                int s0 = m1 == KEY_INF ? -1 : (int)key_pos(m1);
+                if (n == 0 && p.mode == SEL_GE_ARGMAX) s0 = best_b;
+                p.seed_ids[2 * q + 0] = s0;
+                p.seed_ids[2 * q + 1] = m2 == KEY_INF ? -1 : (int)key_pos(m2);
             }
+        }
+        if (p.mode == SEL_GE_ARGMAX && n == 0) {
             if (lane == 0) {
                 sel[0] = best_b;
                 atomicAdd(p.list_count + best_b, 1);
@@ -274,7 +319,7 @@ __device__ __forceinline__ int tile_class(int rem) { return rem > 32 ? 64 : rem 
 // stats[0] += entries in the union of probed lists (E_p), stats[1] += (query, vector) pairs -- the
 // algorithmic work of SURVEY.md 8(d), reported by lira_index_last_timing.
 __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order, const long long* group_offsets,
-                                                           const long long* list_offsets, int B, ScanItem* items,
+                                                           const long long* list_offsets, int B, int tile, ScanItem* items,
                                                            int* n_items_out, unsigned long long* stats) {
     __shared__ int warp_sum[32];
     __shared__ int carry_s;
@@ -288,7 +333,7 @@ __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order
             b = list_order[i];
             g = (int)(group_offsets[b + 1] - group_offsets[b]);
             // (a list with no vectors but a non-empty group still gets items: its all-INF rows must be written)
-            cnt = (g + SCAN_TM_MAX - 1) / SCAN_TM_MAX;
+            cnt = (g + tile - 1) / tile;
             if (g > 0 && stats) {
                 const unsigned long long nb = (unsigned long long)(list_offsets[b + 1] - list_offsets[b]);
                 atomicAdd(stats + 0, nb);
@@ -318,12 +363,12 @@ __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order
         if (i < B) {
             const int gb = (int)group_offsets[b];
             for (int t = 0; t < cnt; ++t) {
-                const int left = g - t * SCAN_TM_MAX;
+                const int left = g - t * tile;
                 ScanItem it;
                 it.list = b;
-                it.q_begin = gb + t * SCAN_TM_MAX;
-                it.q_count = left < SCAN_TM_MAX ? left : SCAN_TM_MAX;
-                it.tm = tile_class(it.q_count);
+                it.q_begin = gb + t * tile;
+                it.q_count = left < tile ? left : tile;
+                it.tm = tile > SCAN_TM_MAX ? tile : tile_class(it.q_count);
                 items[at + t] = it;
             }
         }

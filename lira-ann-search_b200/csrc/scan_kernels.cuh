@@ -34,6 +34,7 @@ struct ScanParams {
     unsigned long long* part_key;  // [P, k] output: sorted keys (score, id-or-position), KEY_INF padded
     int k;
     int store_local;             // 1: low word = position in list (IndexFlat label), 0: global id
+    int max_rows;                // > 0: scan only the first max_rows entries of each list (seed pass)
 };
 
 static constexpr int SCAN_TM_MAX = 64;
@@ -107,7 +108,9 @@ __device__ __forceinline__ void scan_item_producer(const ScanParams& p, const Sc
         const int r = (lane >> 3) + 4 * t;
         arow[t] = (r < it.q_count) ? __ldg(p.group_queries + it.q_begin + r) : -1;
     }
-    const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+    const long long lo = p.list_offsets[it.list];
+    long long hi = p.list_offsets[it.list + 1];
+    if (p.max_rows > 0 && hi - lo > p.max_rows) hi = lo + p.max_rows;
     const int nk = (p.d + KC - 1) / KC;
     for (long long row0 = lo; row0 < hi; row0 += TN)
         for (int kc = 0; kc < nk; ++kc)
@@ -122,7 +125,9 @@ __device__ __forceinline__ void scan_item_consumer(const ScanParams& p, const Sc
                                                    int lane) {
     using C = TileCfg<TM>;
     const int tid = warp * 32 + lane;
-    const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+    const long long lo = p.list_offsets[it.list];
+    long long hi = p.list_offsets[it.list + 1];
+    if (p.max_rows > 0 && hi - lo > p.max_rows) hi = lo + p.max_rows;
     const int nk = (p.d + KC - 1) / KC;
     const int k = p.k;
     int q0, v0;
@@ -260,6 +265,7 @@ struct MergeParams {
     float* out_dist;                     // [Q, k] metric value (L2sq or IP)
     long long* out_ids;                  // [Q, k]
     int is_ip;
+    const int* mask;                     // optional [Q]: only queries with mask[q] != 0 are written
 };
 
 template <int S>
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= p.Q) return;
+    if (p.mask && !p.mask[q]) return;
     const int k = p.k;
     unsigned long long key[S];
 #pragma unroll

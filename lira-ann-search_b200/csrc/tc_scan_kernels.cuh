@@ -1,0 +1,405 @@
+// K2-TC: the grouped list scan on the 5th-generation tensor cores (tcgen05 + TMEM), used for large
+// query batches where the fp32 CUDA-core scan is compute-bound by an order of magnitude.
+//
+//   seed     an exact CUDA-core scan (scan_lists_kernel) over the first rows of every query's best
+//            probed list gives T[q], a valid upper bound of the final k-th best score (any k real
+//            candidates bound it).
+//   filter   this file: for a tile of 128 queries x one inverted list, D = Q_tile . V^T is computed by
+//            tcgen05.mma kind::tf32 straight from the fp32 rows that TMA staged in shared memory
+//            (128-byte swizzle, K-major), accumulators in TMEM (4 x 128 columns, so the epilogue of one
+//            chunk overlaps the MMAs of the next three). Epilogue warps read their query row with
+//            tcgen05.ld and keep only the candidates with  |q|^2 + |v|^2 - 2 q.v <= T[q]
+//            (one FADD + compare per pair); survivors are appended to the query's candidate buffer.
+//   refine   per query: candidates -> exact top-k with id de-duplication.
+//
+// Exactness: this path is taken only when every stored vector and every query of the batch is exactly
+// representable in TF32 (e.g. SIFT / BigANN-style small integers). Then every product and partial sum
+// is an integer below 2^24, the tensor-core result equals the fp32 direct-difference result bit for
+// bit, and ids and distances are identical to the CUDA-core path. Other data keeps the exact
+// CUDA-core scan (scan_kernels.cuh).
+#pragma once
+#include "scan_kernels.cuh"
+
+namespace lira {
+
+static constexpr int TC_M = 128;         // queries per tile (UMMA M, TMEM lanes)
+static constexpr int TC_N = 128;         // vectors per chunk (UMMA N, TMEM columns per accumulator)
+static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128 = 512 columns)
+static constexpr int TC_NSTAGE = 5;      // B ring stages (16 KiB each)
+static constexpr int TC_MAX_KB = 4;      // K blocks of 32 floats resident per A tile: d <= 128
+static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
+static constexpr int TC_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+
+static constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES   // A, double buffered
+                                        + (size_t)TC_NSTAGE * B_STAGE_BYTES     // B ring
+                                        + (size_t)TC_NACC * TC_N * 4            // |v|^2 / 2 per column
+                                        + 256;                                  // barriers + tmem slot
+
+struct TcParams {
+    const int* group_queries;        // [P] query id per slot
+    const long long* list_offsets;   // [B+1]
+    const ScanItem* items;           // tiles of up to 128 queries
+    const int* n_items;
+    int nk;                          // K blocks (ceil(d / 32)), <= TC_MAX_KB
+    const float* vnorm;              // [E] |v|^2 (fp32, sequential order)
+    const float* qnorm;              // [Q] |q|^2
+    const float* thr;                // [Q] seed bound T[q] on the k-th best score
+    unsigned long long* cand_key;    // [Q, cap] (score, list entry) keys
+    int* cand_count;                 // [Q]
+    int cap;
+    int is_ip;
+};
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    uint8_t* sA = smem_raw;                                              // [2][TC_MAX_KB][128 x 128 B]
+    uint8_t* sB = sA + (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES;            // [TC_NSTAGE][128 x 128 B]
+    float* hv_s = (float*)(sB + (size_t)TC_NSTAGE * B_STAGE_BYTES);      // [TC_NACC][128]
+    uint64_t* bars = (uint64_t*)(hv_s + TC_NACC * TC_N);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* b_full = bars + 4;        // [TC_NSTAGE]
+    uint64_t* b_empty = bars + 4 + TC_NSTAGE;
+    uint64_t* t_full = bars + 4 + 2 * TC_NSTAGE;   // [TC_NACC]
+    uint64_t* t_empty = t_full + TC_NACC;
+    uint32_t* tmem_slot = (uint32_t*)(t_empty + TC_NACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_items = *p.n_items;
+    const int nk = p.nk;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane) =====
+        if (lane == 0) {
+            PipeState bs{0, 0};
+            int n = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
+                const ScanItem it = p.items[i];
+                const int ab = n & 1;
+                mbar_wait(&a_empty[ab], ((n >> 1) & 1) ^ 1u);
+                mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
+                for (int kb = 0; kb < nk; ++kb)
+                    tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * KC, it.q_begin, &a_full[ab]);
+                const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+                for (long long row0 = lo; row0 < hi; row0 += TC_N)
+                    for (int kb = 0; kb < nk; ++kb) {
+                        mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
+                        mbar_arrive_expect_tx(&b_full[bs.stage], B_STAGE_BYTES);
+                        tma_load_2d(sB + (size_t)bs.stage * B_STAGE_BYTES, &tmap_v, kb * KC, (int)row0, &b_full[bs.stage]);
+                        bs.advance(TC_NSTAGE);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            PipeState bs{0, 0};
+            int n = 0;
+            uint32_t m = 0;  // running chunk counter -> accumulator slot and phase
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
+                const ScanItem it = p.items[i];
+                const int ab = n & 1;
+                mbar_wait(&a_full[ab], (n >> 1) & 1);
+                tc_fence_after();
+                const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+                for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
+                    const uint32_t acc = m & (TC_NACC - 1);
+                    mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TC_N;
+                    for (int kb = 0; kb < nk; ++kb) {
+                        mbar_wait(&b_full[bs.stage], bs.phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)bs.stage * B_STAGE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)  // 4 x K = 8 tf32 (32 bytes) inside the 128-byte swizzle row
+                            tc_mma_tf32(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC,
+                                        (kb | j) ? 1u : 0u);
+                        tc_commit(&b_empty[bs.stage]);  // frees the B stage when these MMAs have read it
+                        bs.advance(TC_NSTAGE);
+                    }
+                    tc_commit(&t_full[acc]);            // accumulator complete -> epilogue
+                }
+                tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> threshold filter -> candidate append =====
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;          // query row of this thread inside the tile
+        const int et = threadIdx.x - 128;          // 0..127
+        uint32_t m = 0;
+        for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+            const ScanItem it = p.items[i];
+            const bool row_ok = row < it.q_count;
+            int q = 0;
+            float qn = 0.f, hq = 0.f;
+            if (row_ok) {
+                q = __ldg(p.group_queries + it.q_begin + row);
+                const float T = __ldg(p.thr + q);
+                if (p.is_ip) { hq = -T; }               // -dot <= T  <=>  dot >= -T
+                else { qn = __ldg(p.qnorm + q); hq = 0.5f * (qn - T); }  // dot >= (|q|^2 + |v|^2 - T) / 2
+            }
+            const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
+                const uint32_t acc = m & (TC_NACC - 1);
+                // stage |v|^2 / 2 of this chunk's columns (+inf past the end of the list: never passes)
+                {
+                    const long long e = row0 + et;
+                    float h = INFINITY;
+                    if (e < hi) h = p.is_ip ? 0.0f : 0.5f * __ldg(p.vnorm + e);
+                    hv_s[acc * TC_N + et] = h;
+                }
+                named_bar_sync(2, 128);
+                mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
+#pragma unroll 1
+                for (int g = 0; g < TC_N / 32; ++g) {
+                    float v[32];
+                    tc_ld32(taddr + g * 32, v);
+                    if (g == TC_N / 32 - 1) {  // all of this warp's reads of the accumulator are complete
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&t_empty[acc]);
+                    }
+                    if (row_ok) {
+                        float hvr[32];
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 t = *reinterpret_cast<const float4*>(hv_s + acc * TC_N + g * 32 + c4 * 4);
+                            hvr[c4 * 4 + 0] = t.x; hvr[c4 * 4 + 1] = t.y; hvr[c4 * 4 + 2] = t.z; hvr[c4 * 4 + 3] = t.w;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float h = hvr[c];
+                            if (v[c] >= h + hq) {
+                                const float score = p.is_ip ? -v[c] : fmaf(-2.0f, v[c], qn + 2.0f * h);
+                                const int slot = atomicAdd(p.cand_count + q, 1);
+                                if (slot < p.cap)
+                                    p.cand_key[(size_t)q * p.cap + slot] = make_key(score, (uint32_t)(row0 + g * 32 + c));
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(2, 128);  // hv_s[acc] may be rewritten four chunks later only after everyone left
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- helpers around the filter --------------------------------------------------------------------
+// |x|^2 per row in fp32 (sequential order); *exact_flag is cleared unless every value is an integer of at
+// most 11 bits (exact in TF32) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
+// path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit
+__global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, long long n, float* __restrict__ out,
+                                 int* __restrict__ exact_flag) {
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* r = x + i * ld;
+        float s = 0.f;
+        for (int j = 0; j < d; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(r + j);
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
+            bad |= !(fabsf(v.x) <= 2047.f && fabsf(v.y) <= 2047.f && fabsf(v.z) <= 2047.f && fabsf(v.w) <= 2047.f);
+        }
+        out[i] = s;
+        bad |= !(s < 4194304.0f);  // |x|^2 < 2^22  =>  |q|^2 + |v|^2 + 2|q.v| < 2^24
+    }
+    if (bad && exact_flag) *exact_flag = 0;
+}
+
+// gq[slot, :] = q[group_queries[slot], :]  (queries in group order, so a tile of a group is one TMA box)
+__global__ void gather_group_queries_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
+                                            long long P, float* __restrict__ gq) {
+    const int per_row = ds / 4;
+    const long long total = P * per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / per_row;
+        const int c = (int)(i % per_row) * 4;
+        *reinterpret_cast<float4*>(gq + s * ds + c) =
+            *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+    }
+}
+
+// T[q] = k-th best exact score over DISTINCT ids of the seed scan's (up to) two partial lists of the query,
+// +inf when fewer than k distinct candidates were seen. Any k real candidates bound the final k-th score.
+__global__ void seed_threshold_kernel(const unsigned long long* part_key, const int* probe_slot, const int* seed_ids, int Q,
+                                      int k, float* thr) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
+        const unsigned long long* a = seed_ids[2 * q] >= 0 ? part_key + (size_t)probe_slot[2 * q] * k : nullptr;
+        const unsigned long long* b = seed_ids[2 * q + 1] >= 0 ? part_key + (size_t)probe_slot[2 * q + 1] * k : nullptr;
+        int ia = 0, ib = 0, n = 0;
+        unsigned long long last = KEY_INF, kth = KEY_INF;
+        while (n < k) {
+            const unsigned long long xa = (a && ia < k) ? a[ia] : KEY_INF;
+            const unsigned long long xb = (b && ib < k) ? b[ib] : KEY_INF;
+            const unsigned long long x = xa < xb ? xa : xb;
+            if (x == KEY_INF) break;
+            if (xa < xb) ++ia; else ++ib;
+            if (x == last) continue;  // the same id in both lists (learned redundancy): identical key
+            last = x;
+            kth = x;
+            ++n;
+        }
+        thr[q] = (n == k) ? key_score(kth) : INFINITY;
+    }
+}
+
+// explicit probe sets: seed with the first two probed lists of each query
+__global__ void first_probes_kernel(const long long* probe_offsets, const int* probe_ids, int Q, int* seed_ids) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
+        const long long lo = probe_offsets[q], hi = probe_offsets[q + 1];
+        seed_ids[2 * q + 0] = hi > lo ? probe_ids[lo] : -1;
+        seed_ids[2 * q + 1] = hi > lo + 1 ? probe_ids[lo + 1] : -1;
+    }
+}
+
+// refine: candidates (score, list entry) of a query -> exact top-k over distinct ids. One warp per query.
+struct RefineParams {
+    const unsigned long long* cand_key;
+    const int* cand_count;
+    int cap;
+    const int* list_ids;
+    int k, Q, dedup, is_ip;
+    float* out_dist;
+    long long* out_ids;
+    int* redo;      // [Q] 1 when the query had more candidates than `cap` (its row is left for the exact path)
+    int* n_redo;    // number of such queries
+};
+
+template <int S>
+__global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.Q) return;
+    const int k = p.k;
+    int n = p.cand_count[q];
+    if (n > p.cap) {
+        if (lane == 0) { p.redo[q] = 1; atomicAdd(p.n_redo, 1); }
+        return;
+    }
+    if (lane == 0) p.redo[q] = 0;
+    unsigned long long key[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) key[s] = KEY_INF;
+    unsigned long long kth = KEY_INF;
+    const unsigned long long* src = p.cand_key + (size_t)q * p.cap;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        unsigned long long x = KEY_INF;
+        if (e < n) {
+            const unsigned long long c = src[e];
+            x = (c & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(c));  // entry -> global id
+        }
+        uint32_t mm = __ballot_sync(0xffffffffu, x < kth);
+        while (mm) {
+            const int sl = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const unsigned long long y = shfl_u64(x, sl);
+            if (!(y < kth)) continue;
+            bool dup = false;
+            if (p.dedup) {
+                bool mine = false;
+#pragma unroll
+                for (int s = 0; s < S; ++s) mine |= (key[s] == y);
+                dup = __any_sync(0xffffffffu, mine);
+            }
+            if (!dup) {
+                warp_sorted_insert<S>(key, y, lane);
+                kth = warp_sorted_get<S>(key, k - 1);
+            }
+        }
+    }
+    bool valid[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int e = s * 32 + lane;
+        unsigned long long prev = shfl_up_u64(key[s], 1);
+        if (s > 0) {
+            const unsigned long long carry = shfl_u64(key[s - 1], 31);
+            if (lane == 0) prev = carry;
+        }
+        const bool is_first = (e == 0) || (prev != key[s]);
+        valid[s] = (e < k) && (key[s] != KEY_INF) && (p.dedup || is_first);
+    }
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid[s]);
+        if (valid[s]) {
+            const int o = base + __popc(vm & ((1u << lane) - 1u));
+            const float sc = key_score(key[s]);
+            p.out_dist[(size_t)q * k + o] = p.is_ip ? -sc : sc;
+            p.out_ids[(size_t)q * k + o] = (long long)(int)key_pos(key[s]);
+        }
+        base += __popc(vm);
+    }
+    for (int o = base + lane; o < k; o += 32) {
+        p.out_dist[(size_t)q * k + o] = p.is_ip ? -INFINITY : INFINITY;
+        p.out_ids[(size_t)q * k + o] = -1;
+    }
+}
+
+}  // namespace lira

@@ -197,6 +197,23 @@ class LiraIndex:
                                         D.data_ptr(), I.data_ptr(), cmp_.data_ptr(), st))
         return D, I, cmp_
 
+    # ---- scan implementation choice ---------------------------------------------------------
+    def set_use_tensor_cores(self, enable=True):
+        """Pin the exact CUDA-core scan (False) or allow the tcgen05 scan where it is exact (True, default)."""
+        C.check(C.lib().lira_index_set_use_tensor_cores(self._h, int(bool(enable))))
+
+    @property
+    def last_path(self) -> str:
+        return {0: "cuda-core", 1: "tensor-core"}.get(int(C.lib().lira_index_last_path(self._h)), "?")
+
+    @property
+    def last_redo(self) -> int:
+        return int(C.lib().lira_index_last_redo(self._h))
+
+    @property
+    def tensor_core_eligible(self) -> bool:
+        return bool(C.lib().lira_index_tensor_core_eligible(self._h))
+
     # ---- instrumentation ------------------------------------------------------------------
     def set_timing(self, enable=True):
         C.check(C.lib().lira_index_set_timing(self._h, int(enable)))

@@ -278,3 +278,74 @@ def test_self_knn_drops_column_zero_like_compute_knn(L):
     assert np.array_equal(I[:, 0], np.arange(500))  # self first (distance 0)
     _, I_ref = O.knn(x_d, x_d[:500], 6, O.L2, O.F64)
     assert np.mean(I[:, 1:] == I_ref[:, 1:]) > 0.999
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) scan path: must return the same bits as the exact CUDA-core scan
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("k,d", [(10, 128), (10, 96), (100, 64), (1, 20)])
+def test_tensor_core_scan_is_bit_identical(L, metric, k, d):
+    rng = np.random.RandomState(17 + k + d)
+    x_d, x_q = synth(30000, d, 700, seed=31 + d, integer=True)
+    B = 24
+    cl = random_lists(len(x_d), B, rng, redundancy=0.5, empty=(5,))
+    cl[3] = cl[3][:7]  # a list shorter than k
+    off, ids, vecs = lists_csr(x_d, cl)
+    nprobe = rng.randint(0, 7, len(x_q))
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    pids = np.concatenate([rng.choice(B, n, replace=False) for n in nprobe] + [np.empty(0, int)]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    assert index.tensor_core_eligible
+    D, I, cmp_ = index.search(x_q, poff, pids, k)
+    assert index.last_path == "tensor-core"
+    index.set_use_tensor_cores(False)
+    D2, I2, cmp2 = index.search(x_q, poff, pids, k)
+    assert index.last_path == "cuda-core"
+    assert np.array_equal(I, I2) and np.array_equal(D, D2) and np.array_equal(cmp_, cmp2)
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
+    # select-then-collapse semantics as well
+    index.set_use_tensor_cores(True)
+    D0, I0, _ = index.search(x_q, poff, pids, k, dedup=False)
+    I0_ref, D0_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 0)
+    assert np.array_equal(I0, I0_ref) and np.array_equal(D0, D0_ref)
+
+
+def test_tensor_core_path_is_not_taken_for_inexact_data(L):
+    x_d, x_q = synth(8000, 32, 300, seed=8, integer=False)  # real-valued: not exact in TF32
+    cl = random_lists(len(x_d), 8, np.random.RandomState(1))
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    assert not index.tensor_core_eligible
+    poff = np.arange(len(x_q) + 1, dtype=np.int64) * 2
+    pids = np.tile(np.array([0, 3], np.int32), len(x_q))
+    D, I, _ = index.search(x_q, poff, pids, 10)
+    assert index.last_path == "cuda-core"
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
+    assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, O.L2)
+    # integer base but a real-valued query batch: the batch check sends it to the CUDA cores
+    xi, _ = synth(8000, 32, 300, seed=8, integer=True)
+    index2 = L.LiraIndex.from_csr(xi, off, ids, O.L2)
+    assert index2.tensor_core_eligible
+    D, I, _ = index2.search(x_q, poff, pids, 10)
+    assert index2.last_path == "cuda-core"
+
+
+def test_tensor_core_query_phase_matches_cuda_cores(L, golden):
+    """Whole query phase (features -> MLP -> select -> scan) through both scan implementations."""
+    z = golden("toy_l2")
+    k, B, metric = int(z["k"]), int(z["n_bkt"]), int(z["metric"])
+    w = [z[f"mlp_{i}"] for i in range(12)]
+    index = L.LiraIndex.from_data_2_bkt(z["x_d"], z["d2b1"], B, metric)
+    model = L.LiraModel.from_arrays(z["centroids"], z["scaler_mean"], z["scaler_scale"], w)
+    q = np.tile(z["x_q"], (6, 1))  # 384 queries: above the tensor-core batch threshold
+    for mode, value in [(0, 0.1), (1, 0.5), (2, 6)]:
+        index.set_use_tensor_cores(True)
+        a = index.probe_search(model, q, mode, value, k)
+        assert index.last_path == "tensor-core"
+        index.set_use_tensor_cores(False)
+        b = index.probe_search(model, q, mode, value, k)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
