@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -169,7 +171,8 @@ static int init_kernels(int device) {
     rc |= set_smem(scan_lists_kernel<OP_DOT, 1>, scan_smem_bytes<1>());
     rc |= set_smem(scan_lists_kernel<OP_L2, 4>, scan_smem_bytes<4>());
     rc |= set_smem(scan_lists_kernel<OP_DOT, 4>, scan_smem_bytes<4>());
-    rc |= set_smem(tc_scan_kernel, TC_SMEM_BYTES);
+    rc |= set_smem(tc_scan_kernel<false>, TC_SMEM_BYTES);
+    rc |= set_smem(tc_scan_kernel<true>, TC_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
@@ -440,17 +443,18 @@ static int simt_scan(lira_index* h, Workspace& ws, const float* d_q, long long l
 // grouping + exact scan (get_cmp_recall, list_search, kNN, and the online path on the CUDA cores)
 static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
                             int store_local, long long* d_cmp, long long* P_out, const long long** po_out,
-                            cudaStream_t st, const int* d_mask = nullptr) {
+                            cudaStream_t st, const int* d_mask = nullptr, bool timed = true) {
     LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
     const long long* po = nullptr;
     if (int rc = prepare_groups(h, h->ws, Q, ps, SCAN_TM_MAX, d_cmp, P_out, &po, nullptr, nullptr, d_mask, st)) return rc;
     if (po_out) *po_out = po;
     if (Q == 0) return 0;
-    return simt_scan(h, h->ws, d_q, ldq, *P_out, k, store_local, 0, true, st);
+    return simt_scan(h, h->ws, d_q, ldq, *P_out, k, store_local, 0, timed, st);
 }
 
-static constexpr int TC_SEED_ROWS = 384;   // rows of each of the two best probed lists scanned exactly for the seed bound
-static constexpr int TC_CAND_CAP = 1024;   // candidate slots per query
+static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows of each of the two best probed lists
+static constexpr int TC_SEED_ROWS_TC = 1024;  // tensor-core seed (k <= 16): rows of the best probed list
+static constexpr int TC_CAND_CAP = 4096;   // candidate slots per query
 
 // The online query path on the tensor cores (tc_scan_kernels.cuh). *done = true when results were produced
 // for every query whose ws.redo flag is 0; *n_redo counts the queries (flag 1) whose candidate buffer
@@ -484,25 +488,69 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
         LIRA_LAUNCH_CHECK();
     }
-    // ---- seed: exact scan of the first rows of every query's two best lists -> T[q] ----
-    Workspace& sw = h->ws_seed;
-    if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
-    iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, 2);
-    LIRA_LAUNCH_CHECK();
-    ProbeSpec seed;
-    seed.kind = 1;
-    seed.d_probe_offsets = sw.probe_offsets.as<long long>();
-    seed.d_probe_ids = ws.top1.as<int>();
-    seed.P = 2 * Q;
-    long long Pseed = 0;
-    const long long* po_seed = nullptr;
-    // (prepare_groups re-ensures sw.probe_offsets with the same size: no reallocation, content kept)
-    if (int rc = prepare_groups(h, sw, Q, seed, SCAN_TM_MAX, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
-    if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, TC_SEED_ROWS, false, st)) return rc;
     if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
-    seed_threshold_kernel<<<grid_for(Q, 128), 128, 0, st>>>(sw.part_key.as<unsigned long long>(), sw.probe_slot.as<int>(),
-                                                            ws.top1.as<int>(), (int)Q, k, ws.thr.as<float>());
-    LIRA_LAUNCH_CHECK();
+    const int nk = (h->ds + KC - 1) / KC;
+    Workspace& sw = h->ws_seed;
+    if (k <= TC_G) {
+        // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
+        if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
+        if (int rc = sw.probe_ids.ensure((size_t)(Q + 1) * 4)) return rc;
+        iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, 1);
+        LIRA_LAUNCH_CHECK();
+        first_of_pairs_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.top1.as<int>(), (int)Q, sw.probe_ids.as<int>());
+        LIRA_LAUNCH_CHECK();
+        fill_f32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<float>(), Q, INFINITY);
+        LIRA_LAUNCH_CHECK();
+        ProbeSpec seed;
+        seed.kind = 1;
+        seed.d_probe_offsets = sw.probe_offsets.as<long long>();
+        seed.d_probe_ids = sw.probe_ids.as<int>();
+        seed.P = Q;
+        long long Pseed = 0;
+        const long long* po_seed = nullptr;
+        if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
+        if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->ds * 4)) return rc;
+        gather_group_queries_kernel<<<grid_for(Pseed * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(
+            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.gq.as<float>());
+        LIRA_LAUNCH_CHECK();
+        CUtensorMap tmap_sq;
+        if (int rc = make_tmap(&tmap_sq, sw.gq.as<float>(), Pseed, h->ds, h->ds)) return rc;
+        TcParams sp;
+        sp.group_queries = sw.group_queries.as<int>();
+        sp.list_offsets = h->d_offsets;
+        sp.items = sw.items.as<ScanItem>();
+        sp.n_items = sw.n_items.as<int>();
+        sp.work_counter = sw.n_items.as<int>() + 1;
+        sp.nk = nk;
+        sp.max_rows = TC_SEED_ROWS_TC;
+        sp.vnorm = h->vnorm;
+        sp.qnorm = ws.qnorm.as<float>();
+        sp.thr = ws.thr.as<float>();
+        sp.cand_key = nullptr;
+        sp.cand_count = nullptr;
+        sp.cap = 0;
+        sp.k = k;
+        sp.is_ip = h->metric == LIRA_METRIC_IP;
+        tc_scan_kernel<true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap, sp);
+        LIRA_LAUNCH_CHECK();
+    } else {
+        // ---- seed on the CUDA cores (k > 16): exact scan of the first rows of the two best lists ----
+        if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
+        iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, 2);
+        LIRA_LAUNCH_CHECK();
+        ProbeSpec seed;
+        seed.kind = 1;
+        seed.d_probe_offsets = sw.probe_offsets.as<long long>();
+        seed.d_probe_ids = ws.top1.as<int>();
+        seed.P = 2 * Q;
+        long long Pseed = 0;
+        const long long* po_seed = nullptr;
+        if (int rc = prepare_groups(h, sw, Q, seed, SCAN_TM_MAX, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
+        if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, TC_SEED_ROWS, false, st)) return rc;
+        seed_threshold_kernel<<<grid_for(Q, 128), 128, 0, st>>>(sw.part_key.as<unsigned long long>(), sw.probe_slot.as<int>(),
+                                                                ws.top1.as<int>(), (int)Q, k, ws.thr.as<float>());
+        LIRA_LAUNCH_CHECK();
+    }
     // ---- queries in group order (one TMA box per tile) ----
     if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->ds * 4)) return rc;
     gather_group_queries_kernel<<<grid_for(P * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
@@ -519,16 +567,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.list_offsets = h->d_offsets;
     tp.items = ws.items.as<ScanItem>();
     tp.n_items = ws.n_items.as<int>();
-    tp.nk = (h->ds + KC - 1) / KC;
+    tp.work_counter = ws.n_items.as<int>() + 1;
+    tp.nk = nk;
+    tp.max_rows = 0;
     tp.vnorm = h->vnorm;
     tp.qnorm = ws.qnorm.as<float>();
     tp.thr = ws.thr.as<float>();
     tp.cand_key = ws.cand_key.as<unsigned long long>();
     tp.cand_count = ws.cand_count.as<int>();
     tp.cap = TC_CAND_CAP;
+    tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    tc_scan_kernel<<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, tp);
+    tc_scan_kernel<false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, tp);
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
@@ -540,6 +591,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_LAUNCH_CHECK();
     LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    if (getenv("LIRA_DEBUG")) {
+        std::vector<int> cc(Q);
+        std::vector<float> th(Q);
+        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+        std::vector<int> sorted(cc);
+        std::sort(sorted.begin(), sorted.end());
+        long long tot = 0, ninf = 0;
+        for (int c : cc) tot += c;
+        for (float t : th) ninf += std::isinf(t);
+        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f p50 %d p90 %d p99 %d max %d; T=inf for %lld; redo %d\n",
+                Q, P, (double)tot / Q, sorted[Q / 2], sorted[Q * 9 / 10], sorted[Q * 99 / 100], sorted[Q - 1], ninf, *n_redo);
+    }
     h->last_path = 1;
     h->last_redo = *n_redo;
     *done = true;
@@ -563,7 +627,7 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
         const int* mask = done ? h->ws.redo.as<int>() : nullptr;
         if (!done) h->last_path = 0;
         const long long* po = nullptr;
-        if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, done ? nullptr : d_cmp, &P, &po, st, mask)) return rc;
+        if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, done ? nullptr : d_cmp, &P, &po, st, mask, !done)) return rc;
         if (Q == 0) return 0;
         Workspace& ws = h->ws;
         MergeParams mp;

@@ -30,23 +30,29 @@ static constexpr int TC_MAX_KB = 4;      // K blocks of 32 floats resident per A
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
 static constexpr int TC_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
 
+static constexpr int TC_CB = 16;         // per-row staging slots for survivors (flushed with ONE atomic per 16)
+
 static constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES   // A, double buffered
                                         + (size_t)TC_NSTAGE * B_STAGE_BYTES     // B ring
                                         + (size_t)TC_NACC * TC_N * 4            // |v|^2 / 2 per column
-                                        + 256;                                  // barriers + tmem slot
+                                        + (size_t)TC_M * TC_CB * 8              // survivor staging, one row per thread
+                                        + 512;                                  // barriers, item queue, tmem slot
 
 struct TcParams {
     const int* group_queries;        // [P] query id per slot
     const long long* list_offsets;   // [B+1]
-    const ScanItem* items;           // tiles of up to 128 queries
+    const ScanItem* items;           // tiles of up to 128 queries, most expensive first
     const int* n_items;
+    int* work_counter;               // zeroed before launch: dynamic item scheduler
     int nk;                          // K blocks (ceil(d / 32)), <= TC_MAX_KB
+    int max_rows;                    // > 0: only the first max_rows entries of each list (seed pass)
     const float* vnorm;              // [E] |v|^2 (fp32, sequential order)
     const float* qnorm;              // [Q] |q|^2
-    const float* thr;                // [Q] seed bound T[q] on the k-th best score
+    float* thr;                      // [Q] bound T[q] on the k-th best score: read (filter) / written (seed)
     unsigned long long* cand_key;    // [Q, cap] (score, list entry) keys
     int* cand_count;                 // [Q]
     int cap;
+    int k;
     int is_ip;
 };
 
@@ -67,8 +73,8 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// asynchronous TMEM -> register load of 32 consecutive columns of this thread's lane; pair with tc_ld_wait()
+__device__ __forceinline__ void tc_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -78,35 +84,84 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// wait for the outstanding TMEM loads; r[] is threaded through the asm so that no use of the loaded
+// registers can be scheduled above the wait
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
 static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
+static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / norm loader / epilogue)
+static constexpr int TC_NH = 4;   // |v|^2/2 ring depth
+static constexpr int TC_G = 16;   // seed pass: group minima per row (needs k <= 16)
+
+// Process 32 columns held in r[] for this thread's row.
+//   t = |v|^2/2 - q.v  (L2; score = |q|^2 + 2 t)      t = -q.v (IP; score = t)
+// SEED: running minima of 16 column groups (no divergence).  !SEED: survivors with t <= tq.
+template <bool SEED>
+__device__ __forceinline__ void tc_process32(const uint32_t (&r)[32], const float* hv, float tq, float (&gmin)[TC_G],
+                                             uint32_t& mask) {
+    mask = 0;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 h = *reinterpret_cast<const float4*>(hv + c4 * 4);
+        const float t0 = h.x - __uint_as_float(r[c4 * 4 + 0]);
+        const float t1 = h.y - __uint_as_float(r[c4 * 4 + 1]);
+        const float t2 = h.z - __uint_as_float(r[c4 * 4 + 2]);
+        const float t3 = h.w - __uint_as_float(r[c4 * 4 + 3]);
+        if (SEED) {
+            gmin[(c4 * 4 + 0) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 0) & (TC_G - 1)], t0);
+            gmin[(c4 * 4 + 1) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 1) & (TC_G - 1)], t1);
+            gmin[(c4 * 4 + 2) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 2) & (TC_G - 1)], t2);
+            gmin[(c4 * 4 + 3) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 3) & (TC_G - 1)], t3);
+        } else {
+            mask |= (t0 <= tq) ? (1u << (c4 * 4 + 0)) : 0u;
+            mask |= (t1 <= tq) ? (1u << (c4 * 4 + 1)) : 0u;
+            mask |= (t2 <= tq) ? (1u << (c4 * 4 + 2)) : 0u;
+            mask |= (t3 <= tq) ? (1u << (c4 * 4 + 3)) : 0u;
+        }
+    }
+}
+
+template <bool SEED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* sA = smem_raw;                                              // [2][TC_MAX_KB][128 x 128 B]
     uint8_t* sB = sA + (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES;            // [TC_NSTAGE][128 x 128 B]
-    float* hv_s = (float*)(sB + (size_t)TC_NSTAGE * B_STAGE_BYTES);      // [TC_NACC][128]
-    uint64_t* bars = (uint64_t*)(hv_s + TC_NACC * TC_N);
-    uint64_t* a_full = bars;            // [2]
-    uint64_t* a_empty = bars + 2;       // [2]
-    uint64_t* b_full = bars + 4;        // [TC_NSTAGE]
-    uint64_t* b_empty = bars + 4 + TC_NSTAGE;
-    uint64_t* t_full = bars + 4 + 2 * TC_NSTAGE;   // [TC_NACC]
-    uint64_t* t_empty = t_full + TC_NACC;
-    uint32_t* tmem_slot = (uint32_t*)(t_empty + TC_NACC);
+    float* hv_s = (float*)(sB + (size_t)TC_NSTAGE * B_STAGE_BYTES);      // [TC_NH][128]
+    unsigned long long* cb_s = (unsigned long long*)(hv_s + TC_NH * TC_N);  // [128][TC_CB]
+    uint64_t* bars = (uint64_t*)(cb_s + TC_M * TC_CB);
+    uint64_t* a_full = bars;                        // [2]
+    uint64_t* a_empty = a_full + 2;                 // [2]
+    uint64_t* b_full = a_empty + 2;                 // [TC_NSTAGE]
+    uint64_t* b_empty = b_full + TC_NSTAGE;         // [TC_NSTAGE]
+    uint64_t* t_full = b_empty + TC_NSTAGE;         // [TC_NACC]
+    uint64_t* t_empty = t_full + TC_NACC;           // [TC_NACC]
+    uint64_t* h_full = t_empty + TC_NACC;           // [TC_NH]
+    uint64_t* h_empty = h_full + TC_NH;             // [TC_NH]
+    uint64_t* i_full = h_empty + TC_NH;             // [TC_NQ]
+    uint64_t* i_empty = i_full + TC_NQ;             // [TC_NQ]
+    ScanItem* iq = (ScanItem*)(i_empty + TC_NQ);    // [TC_NQ]
+    uint32_t* tmem_slot = (uint32_t*)(iq + TC_NQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 4); }
+        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 6); }  // MMA + loader + 4 epilogue warps
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -121,19 +176,34 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const int n_items = *p.n_items;
     const int nk = p.nk;
 
+    // list range of an item, clipped for the seed pass
+    auto item_rows = [&](const ScanItem& it, long long& lo, long long& hi) {
+        lo = p.list_offsets[it.list];
+        hi = p.list_offsets[it.list + 1];
+        if (p.max_rows > 0 && hi - lo > p.max_rows) hi = lo + p.max_rows;
+    };
+
     if (warp == 0) {
-        // ===== TMA producer (one elected lane) =====
+        // ===== scheduler + TMA producer (one elected lane) =====
         if (lane == 0) {
             PipeState bs{0, 0};
-            int n = 0;
-            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
-                const ScanItem it = p.items[i];
+            for (int n = 0;; ++n) {
+                const int idx = atomicAdd(p.work_counter, 1);
+                ScanItem it;
+                if (idx < n_items) it = p.items[idx];
+                else { it.list = -1; it.q_begin = 0; it.q_count = 0; it.tm = 0; }
+                const int qs = n % TC_NQ;
+                mbar_wait(&i_empty[qs], ((n / TC_NQ) & 1) ^ 1u);
+                iq[qs] = it;
+                mbar_arrive(&i_full[qs]);
+                if (it.list < 0) break;
                 const int ab = n & 1;
                 mbar_wait(&a_empty[ab], ((n >> 1) & 1) ^ 1u);
                 mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
                 for (int kb = 0; kb < nk; ++kb)
                     tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * KC, it.q_begin, &a_full[ab]);
-                const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+                long long lo, hi;
+                item_rows(it, lo, hi);
                 for (long long row0 = lo; row0 < hi; row0 += TC_N)
                     for (int kb = 0; kb < nk; ++kb) {
                         mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
@@ -147,14 +217,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
             PipeState bs{0, 0};
-            int n = 0;
             uint32_t m = 0;  // running chunk counter -> accumulator slot and phase
-            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
-                const ScanItem it = p.items[i];
+            for (int n = 0;; ++n) {
+                const int qs = n % TC_NQ;
+                mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
+                const ScanItem it = iq[qs];
+                mbar_arrive(&i_empty[qs]);
+                if (it.list < 0) break;
                 const int ab = n & 1;
                 mbar_wait(&a_full[ab], (n >> 1) & 1);
                 tc_fence_after();
-                const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+                long long lo, hi;
+                item_rows(it, lo, hi);
                 for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                     const uint32_t acc = m & (TC_NACC - 1);
                     mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
@@ -177,66 +251,135 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
             }
         }
+    } else if (warp == 2) {
+        // ===== |v|^2/2 loader: keeps the epilogue off the global-memory latency path =====
+        uint32_t m = 0;
+        for (int n = 0;; ++n) {
+            const int qs = n % TC_NQ;
+            mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
+            const ScanItem it = iq[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[qs]);
+            if (it.list < 0) break;
+            long long lo, hi;
+            item_rows(it, lo, hi);
+            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
+                const int hs = m % TC_NH;
+                mbar_wait(&h_empty[hs], ((m / TC_NH) & 1) ^ 1u);
+#pragma unroll
+                for (int j = 0; j < TC_N / 32; ++j) {
+                    const long long e = row0 + lane + 32 * j;
+                    // past the end of the list: NaN, so that neither `t <= tq` (even for tq = +inf) nor fminf picks it
+                    float h = __int_as_float(0x7fc00000);
+                    if (e < hi) h = p.is_ip ? 0.0f : 0.5f * __ldg(p.vnorm + e);
+                    hv_s[hs * TC_N + lane + 32 * j] = h;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_full[hs]);
+            }
+        }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> threshold filter -> candidate append =====
+        // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
+        // A thread owns one query row for the whole work item. Filter: survivors are rare, so the hot loop only
+        // builds a 32-bit pass mask per 32 columns (FADD + FSETP per pair, no divergence); survivors go to the
+        // row's shared-memory staging slots and reach the query's global candidate buffer TC_CB at a time (one
+        // atomicAdd per flush instead of one per survivor, which would serialise the warp on L2 latency).
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
-        const int et = threadIdx.x - 128;          // 0..127
+        unsigned long long* cb = cb_s + row * TC_CB;
         uint32_t m = 0;
-        for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
-            const ScanItem it = p.items[i];
+        for (int n = 0;; ++n) {
+            const int qs = n % TC_NQ;
+            mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
+            const ScanItem it = iq[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[qs]);
+            if (it.list < 0) break;
             const bool row_ok = row < it.q_count;
-            int q = 0;
-            float qn = 0.f, hq = 0.f;
+            int q = 0, cnt = 0;
+            float qn = 0.f, tq = -INFINITY;
+            float gmin[TC_G];
+#pragma unroll
+            for (int g = 0; g < TC_G; ++g) gmin[g] = INFINITY;
             if (row_ok) {
                 q = __ldg(p.group_queries + it.q_begin + row);
-                const float T = __ldg(p.thr + q);
-                if (p.is_ip) { hq = -T; }               // -dot <= T  <=>  dot >= -T
-                else { qn = __ldg(p.qnorm + q); hq = 0.5f * (qn - T); }  // dot >= (|q|^2 + |v|^2 - T) / 2
+                if (!p.is_ip) qn = __ldg(p.qnorm + q);
+                if (!SEED) {
+                    const float T = p.thr[q];
+                    tq = p.is_ip ? T : 0.5f * (T - qn);   // score <= T  <=>  t <= tq
+                }
             }
-            const long long lo = p.list_offsets[it.list], hi = p.list_offsets[it.list + 1];
+            auto flush = [&]() {
+                const int base = atomicAdd(p.cand_count + q, cnt);
+                for (int j = 0; j < cnt; ++j)
+                    if (base + j < p.cap) p.cand_key[(size_t)q * p.cap + base + j] = cb[(j + row) & (TC_CB - 1)];
+                cnt = 0;
+            };
+            long long lo, hi;
+            item_rows(it, lo, hi);
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
-                // stage |v|^2 / 2 of this chunk's columns (+inf past the end of the list: never passes)
-                {
-                    const long long e = row0 + et;
-                    float h = INFINITY;
-                    if (e < hi) h = p.is_ip ? 0.0f : 0.5f * __ldg(p.vnorm + e);
-                    hv_s[acc * TC_N + et] = h;
-                }
-                named_bar_sync(2, 128);
+                const int hs = m % TC_NH;
+                const float* hv = hv_s + hs * TC_N;
+                mbar_wait(&h_full[hs], (m / TC_NH) & 1);
                 mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
-#pragma unroll 1
+                uint32_t ra[32], rb[32];
+                tc_ld32_async(taddr, ra);
+                tc_ld_wait(ra);
+#pragma unroll
                 for (int g = 0; g < TC_N / 32; ++g) {
-                    float v[32];
-                    tc_ld32(taddr + g * 32, v);
-                    if (g == TC_N / 32 - 1) {  // all of this warp's reads of the accumulator are complete
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&t_empty[acc]);
+                    // prefetch the next 32 columns while this group is processed
+                    if (g + 1 < TC_N / 32) {
+                        if (g & 1) tc_ld32_async(taddr + (g + 1) * 32, ra);
+                        else tc_ld32_async(taddr + (g + 1) * 32, rb);
                     }
-                    if (row_ok) {
-                        float hvr[32];
+                    uint32_t mask;
+                    if (g & 1) tc_process32<SEED>(rb, hv + g * 32, tq, gmin, mask);
+                    else tc_process32<SEED>(ra, hv + g * 32, tq, gmin, mask);
+                    if (!SEED) {
+                        if (!row_ok) mask = 0;
+                        while (mask) {
+                            const int c = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            uint32_t bits = 0;
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 t = *reinterpret_cast<const float4*>(hv_s + acc * TC_N + g * 32 + c4 * 4);
-                            hvr[c4 * 4 + 0] = t.x; hvr[c4 * 4 + 1] = t.y; hvr[c4 * 4 + 2] = t.z; hvr[c4 * 4 + 3] = t.w;
+                            for (int cc = 0; cc < 32; ++cc) bits = (cc == c) ? ((g & 1) ? rb[cc] : ra[cc]) : bits;
+                            const float t = hv[g * 32 + c] - __uint_as_float(bits);
+                            const float score = p.is_ip ? t : fmaf(2.0f, t, qn);
+                            cb[(cnt + row) & (TC_CB - 1)] = make_key(score, (uint32_t)(row0 + g * 32 + c));
+                            if (++cnt == TC_CB) flush();
                         }
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float h = hvr[c];
-                            if (v[c] >= h + hq) {
-                                const float score = p.is_ip ? -v[c] : fmaf(-2.0f, v[c], qn + 2.0f * h);
-                                const int slot = atomicAdd(p.cand_count + q, 1);
-                                if (slot < p.cap)
-                                    p.cand_key[(size_t)q * p.cap + slot] = make_key(score, (uint32_t)(row0 + g * 32 + c));
-                            }
-                        }
+                    }
+                    if (g + 1 < TC_N / 32) {
+                        if (g & 1) tc_ld_wait(ra);
+                        else tc_ld_wait(rb);
                     }
                 }
-                named_bar_sync(2, 128);  // hv_s[acc] may be rewritten four chunks later only after everyone left
+                // this warp is done with the accumulator and the norm slot
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&h_empty[hs]); }
+            }
+            if (SEED) {
+                // T = k-th smallest of the 16 group minima: 16 distinct entries of ONE list, so k real candidates
+                // are at or below it. (score = |q|^2 + 2 t for L2, t for IP)
+                float tk = INFINITY;
+                if (row_ok) {
+                    for (int j = 0; j < p.k; ++j) {  // extract the minimum k times
+                        float mn = INFINITY;
+                        int at = 0;
+#pragma unroll
+                        for (int g = 0; g < TC_G; ++g) { if (gmin[g] < mn) { mn = gmin[g]; at = g; } }
+                        tk = mn;
+#pragma unroll
+                        for (int g = 0; g < TC_G; ++g) gmin[g] = (g == at) ? INFINITY : gmin[g];
+                    }
+                    p.thr[q] = p.is_ip ? tk : fmaf(2.0f, tk, qn);
+                }
+            } else if (cnt) {
+                flush();
             }
         }
     }
@@ -305,6 +448,14 @@ __global__ void seed_threshold_kernel(const unsigned long long* part_key, const 
         }
         thr[q] = (n == k) ? key_score(kth) : INFINITY;
     }
+}
+
+__global__ void fill_f32_kernel(float* x, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+}
+// seed1[q] = seed_ids[2 q]: the single best list per query for the tensor-core seed pass
+__global__ void first_of_pairs_kernel(const int* seed_ids, int Q, int* seed1) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) seed1[q] = seed_ids[2 * q];
 }
 
 // explicit probe sets: seed with the first two probed lists of each query
