@@ -112,22 +112,33 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU box.
+// try_wait is issued WITHOUT a suspend-time hint: with a hint ptxas emits NANOSLEEP between polls and every
+// wait then costs up to the hinted time in wake-up latency (measured: ~2 us per wait, 5x on the whole scan).
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    // each try_wait may suspend up to ~2 us; 2^22 tries bound a stuck wait to a few seconds
+    uint64_t t0 = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x7D0;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
+        if ((spin & 0xFFFu) == 0xFFFu) {  // every 4096 failed polls: wall-clock guard (5 s)
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 5000000000ull) __trap();
+        }
     }
-    __trap();
 }
 
 // 2-D tiled TMA load: box lands in smem, completion bytes are counted on `bar`.

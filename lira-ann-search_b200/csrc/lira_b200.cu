@@ -127,6 +127,7 @@ struct lira_index {
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
     Workspace ws, ws_seed;
+    DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
     float* vnorm = nullptr;      // |v|^2 per list entry (tensor-core path)
     bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
     bool use_tc = true;
@@ -440,6 +441,13 @@ static int simt_scan(lira_index* h, Workspace& ws, const float* d_q, long long l
     return 0;
 }
 
+static int save_stats(lira_index* h, Workspace& ws, cudaStream_t st) {
+    if (!h->timing) return 0;
+    if (int rc = h->stats.ensure(16)) return rc;
+    LIRA_CUDA_OK(cudaMemcpyAsync(h->stats.p, (char*)ws.n_items.p + 64, 16, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 // grouping + exact scan (get_cmp_recall, list_search, kNN, and the online path on the CUDA cores)
 static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
                             int store_local, long long* d_cmp, long long* P_out, const long long** po_out,
@@ -449,6 +457,7 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
     if (int rc = prepare_groups(h, h->ws, Q, ps, SCAN_TM_MAX, d_cmp, P_out, &po, nullptr, nullptr, d_mask, st)) return rc;
     if (po_out) *po_out = po;
     if (Q == 0) return 0;
+    if (timed) if (int rc = save_stats(h, h->ws, st)) return rc;
     return simt_scan(h, h->ws, d_q, ldq, *P_out, k, store_local, 0, timed, st);
 }
 
@@ -480,6 +489,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     int q_exact = 1;
     if (int rc = prepare_groups(h, ws, Q, ps, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st)) return rc;
     if (!q_exact || P == 0) return 0;  // not exact in TF32 (or nothing probed): exact CUDA-core path
+    if (int rc = save_stats(h, ws, st)) return rc;
     if (ps.kind == 1) {
         first_probes_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, (int)Q, ws.top1.as<int>());
         LIRA_LAUNCH_CHECK();
@@ -491,7 +501,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
     const int nk = (h->ds + KC - 1) / KC;
     Workspace& sw = h->ws_seed;
-    if (k <= TC_G) {
+    if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
         if (int rc = sw.probe_ids.ensure((size_t)(Q + 1) * 4)) return rc;
@@ -499,7 +509,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         LIRA_LAUNCH_CHECK();
         first_of_pairs_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.top1.as<int>(), (int)Q, sw.probe_ids.as<int>());
         LIRA_LAUNCH_CHECK();
-        fill_f32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<float>(), Q, INFINITY);
+        fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u /* f32_to_ordered(+inf) */);
         LIRA_LAUNCH_CHECK();
         ProbeSpec seed;
         seed.kind = 1;
@@ -511,7 +521,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
         if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->ds * 4)) return rc;
         gather_group_queries_kernel<<<grid_for(Pseed * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(
-            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.gq.as<float>());
+            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<float>());
         LIRA_LAUNCH_CHECK();
         CUtensorMap tmap_sq;
         if (int rc = make_tmap(&tmap_sq, sw.gq.as<float>(), Pseed, h->ds, h->ds)) return rc;
@@ -525,7 +535,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.max_rows = TC_SEED_ROWS_TC;
         sp.vnorm = h->vnorm;
         sp.qnorm = ws.qnorm.as<float>();
-        sp.thr = ws.thr.as<float>();
+        sp.thr = ws.thr.as<uint32_t>();
         sp.cand_key = nullptr;
         sp.cand_count = nullptr;
         sp.cap = 0;
@@ -548,13 +558,13 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         if (int rc = prepare_groups(h, sw, Q, seed, SCAN_TM_MAX, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
         if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, TC_SEED_ROWS, false, st)) return rc;
         seed_threshold_kernel<<<grid_for(Q, 128), 128, 0, st>>>(sw.part_key.as<unsigned long long>(), sw.probe_slot.as<int>(),
-                                                                ws.top1.as<int>(), (int)Q, k, ws.thr.as<float>());
+                                                                ws.top1.as<int>(), (int)Q, k, ws.thr.as<uint32_t>());
         LIRA_LAUNCH_CHECK();
     }
     // ---- queries in group order (one TMA box per tile) ----
     if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->ds * 4)) return rc;
     gather_group_queries_kernel<<<grid_for(P * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                        ws.gq.as<float>());
+                                                                                        ws.group_offsets.as<long long>() + h->B, ws.gq.as<float>());
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
     if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
@@ -572,7 +582,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.max_rows = 0;
     tp.vnorm = h->vnorm;
     tp.qnorm = ws.qnorm.as<float>();
-    tp.thr = ws.thr.as<float>();
+    tp.thr = ws.thr.as<uint32_t>();
     tp.cand_key = ws.cand_key.as<unsigned long long>();
     tp.cand_count = ws.cand_count.as<int>();
     tp.cap = TC_CAND_CAP;
@@ -593,14 +603,14 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     if (getenv("LIRA_DEBUG")) {
         std::vector<int> cc(Q);
-        std::vector<float> th(Q);
+        std::vector<uint32_t> th(Q);
         cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
         std::vector<int> sorted(cc);
         std::sort(sorted.begin(), sorted.end());
         long long tot = 0, ninf = 0;
         for (int c : cc) tot += c;
-        for (float t : th) ninf += std::isinf(t);
+        for (uint32_t t : th) ninf += (t == 0xFF800000u);
         fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f p50 %d p90 %d p99 %d max %d; T=inf for %lld; redo %d\n",
                 Q, P, (double)tot / Q, sorted[Q / 2], sorted[Q * 9 / 10], sorted[Q * 99 / 100], sorted[Q - 1], ninf, *n_redo);
     }
@@ -661,7 +671,7 @@ static int finish_timing(lira_index* h) {
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_scan_ms, h->ev[0], h->ev[1]));
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_total_ms, h->ev[2], h->ev[3]));
     unsigned long long stats[2] = {0, 0};
-    LIRA_CUDA_OK(cudaMemcpy(stats, (char*)h->ws.n_items.p + 64, 16, cudaMemcpyDeviceToHost));
+    if (h->stats.p) LIRA_CUDA_OK(cudaMemcpy(stats, h->stats.p, 16, cudaMemcpyDeviceToHost));
     // bytes_alg = E_p (4 d + 4) + Q 4 d + Q k 8
     h->last_scan_bytes = (long long)stats[0] * (4ll * h->d + 4) + h->last_Q * (4ll * h->d + 8ll * h->last_k);
     h->last_scan_pairs = (long long)stats[1];
@@ -842,6 +852,7 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->vnorm);
     h->ws.release();
     h->ws_seed.release();
+    h->stats.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -48,7 +48,8 @@ struct TcParams {
     int max_rows;                    // > 0: only the first max_rows entries of each list (seed pass)
     const float* vnorm;              // [E] |v|^2 (fp32, sequential order)
     const float* qnorm;              // [Q] |q|^2
-    float* thr;                      // [Q] bound T[q] on the k-th best score: read (filter) / written (seed)
+    uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
+                                     //     seed pass, read AND tightened (atomicMin) by the filter pass
     unsigned long long* cand_key;    // [Q, cap] (score, list entry) keys
     int* cand_count;                 // [Q]
     int cap;
@@ -102,34 +103,102 @@ static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint
 
 static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / norm loader / epilogue)
 static constexpr int TC_NH = 4;   // |v|^2/2 ring depth
-static constexpr int TC_G = 16;   // seed pass: group minima per row (needs k <= 16)
+static constexpr int TC_G = 64;   // seed pass: group minima per row
+static constexpr int TC_KMAX_TIGHTEN = 16;  // in-kernel threshold tightening (and the tensor-core seed) need k <= 16
 
-// Process 32 columns held in r[] for this thread's row.
+// ---- small static sorting networks (registers only; every index is a compile-time constant) --------
+__device__ __forceinline__ void tc_sort16(float (&v)[16]) {  // bitonic, ascending
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const float a = v[i], b = v[l];
+                    v[i] = up ? fminf(a, b) : fmaxf(a, b);
+                    v[l] = up ? fmaxf(a, b) : fminf(a, b);
+                }
+            }
+}
+// a, b ascending -> a = the 16 smallest of the union, ascending
+__device__ __forceinline__ void tc_merge_low16(float (&a)[16], const float (&b)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fminf(a[i], b[15 - i]);  // bitonic sequence of the 16 smallest
+#pragma unroll
+    for (int j = 8; j > 0; j >>= 1)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int l = i ^ j;
+            if (l > i) {
+                const float x = a[i], y = a[l];
+                a[i] = fminf(x, y);
+                a[l] = fmaxf(x, y);
+            }
+        }
+}
+__device__ __forceinline__ float tc_pick16(const float (&v)[16], int idx) {
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) r = (i == idx) ? v[i] : r;
+    return r;
+}
+
+// t[c] = hv[c] - r[c] for 32 columns of this thread's row, m4[i] = min of columns 4i..4i+3; returns the minimum of
+// all 32 (NaN padding is ignored by fminf).
 //   t = |v|^2/2 - q.v  (L2; score = |q|^2 + 2 t)      t = -q.v (IP; score = t)
-// SEED: running minima of 16 column groups (no divergence).  !SEED: survivors with t <= tq.
-template <bool SEED>
-__device__ __forceinline__ void tc_process32(const uint32_t (&r)[32], const float* hv, float tq, float (&gmin)[TC_G],
-                                             uint32_t& mask) {
-    mask = 0;
+__device__ __forceinline__ float tc_diff32(const uint32_t (&r)[32], const float* hv, float (&t)[32], float (&m4)[8]) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
         const float4 h = *reinterpret_cast<const float4*>(hv + c4 * 4);
-        const float t0 = h.x - __uint_as_float(r[c4 * 4 + 0]);
-        const float t1 = h.y - __uint_as_float(r[c4 * 4 + 1]);
-        const float t2 = h.z - __uint_as_float(r[c4 * 4 + 2]);
-        const float t3 = h.w - __uint_as_float(r[c4 * 4 + 3]);
-        if (SEED) {
-            gmin[(c4 * 4 + 0) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 0) & (TC_G - 1)], t0);
-            gmin[(c4 * 4 + 1) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 1) & (TC_G - 1)], t1);
-            gmin[(c4 * 4 + 2) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 2) & (TC_G - 1)], t2);
-            gmin[(c4 * 4 + 3) & (TC_G - 1)] = fminf(gmin[(c4 * 4 + 3) & (TC_G - 1)], t3);
-        } else {
-            mask |= (t0 <= tq) ? (1u << (c4 * 4 + 0)) : 0u;
-            mask |= (t1 <= tq) ? (1u << (c4 * 4 + 1)) : 0u;
-            mask |= (t2 <= tq) ? (1u << (c4 * 4 + 2)) : 0u;
-            mask |= (t3 <= tq) ? (1u << (c4 * 4 + 3)) : 0u;
+        t[c4 * 4 + 0] = h.x - __uint_as_float(r[c4 * 4 + 0]);
+        t[c4 * 4 + 1] = h.y - __uint_as_float(r[c4 * 4 + 1]);
+        t[c4 * 4 + 2] = h.z - __uint_as_float(r[c4 * 4 + 2]);
+        t[c4 * 4 + 3] = h.w - __uint_as_float(r[c4 * 4 + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m4[i] = fminf(fminf(t[4 * i], t[4 * i + 1]), fminf(t[4 * i + 2], t[4 * i + 3]));
+    return fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+}
+
+// Rare path of the filter epilogue, deliberately NOT inlined (it is instantiated at every column of the unrolled
+// survivor expansion): write the row's staged survivors {t bits, list entry} that are at or below the bound to
+// the query's candidate buffer. With `tighten` (staging buffer full, k <= 16) the k-th smallest staged t first
+// replaces the bound if it is smaller -- the staged entries are TC_CB distinct entries of one list, so k real
+// candidates are at or below it -- and the new bound is published for the query's other rows. Returns the bound.
+struct TcFlushArgs {   // by value: taking the address of the kernel parameter block would demote it to local memory
+    uint32_t* thr;
+    unsigned long long* cand_key;
+    int* cand_count;
+    int cap, k, is_ip;
+};
+__device__ __noinline__ float tc_flush_row(const TcFlushArgs p, const uint2* cb, int row, int cnt, float tq, int q, float qn,
+                                           bool tighten) {
+    if (tighten) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(cb[j].x);
+        tc_sort16(v);
+        const float tk = tc_pick16(v, p.k - 1);
+        if (tk < tq) {
+            tq = tk;
+            atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
         }
     }
+    int nkeep = 0;
+    for (int j = 0; j < cnt; ++j) nkeep += (__uint_as_float(cb[(j + row) & (TC_CB - 1)].x) <= tq) ? 1 : 0;
+    int base = atomicAdd(p.cand_count + q, nkeep);
+    for (int j = 0; j < cnt; ++j) {
+        const uint2 e = cb[(j + row) & (TC_CB - 1)];
+        const float t = __uint_as_float(e.x);
+        if (t <= tq) {
+            if (base < p.cap) p.cand_key[(size_t)q * p.cap + base] = make_key(p.is_ip ? t : fmaf(2.0f, t, qn), e.y);
+            ++base;
+        }
+    }
+    return tq;
 }
 
 template <bool SEED>
@@ -281,12 +350,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
         // A thread owns one query row for the whole work item. Filter: survivors are rare, so the hot loop only
-        // builds a 32-bit pass mask per 32 columns (FADD + FSETP per pair, no divergence); survivors go to the
-        // row's shared-memory staging slots and reach the query's global candidate buffer TC_CB at a time (one
-        // atomicAdd per flush instead of one per survivor, which would serialise the warp on L2 latency).
+        // forms t = |v|^2/2 - q.v and a 3-input-min tree per 32 columns (FADD + FMNMX3, no divergence); a group
+        // whose minimum passes the row's bound is expanded column by column. Survivors go to the row's TC_CB
+        // staging slots in shared memory. A full staging buffer is a chance to TIGHTEN the bound: its k-th
+        // smallest entry bounds the final k-th best (TC_CB distinct entries of one list), so the row keeps only
+        // entries at or below it, continues with the tighter bound and publishes it (atomicMin) for the query's
+        // rows in other lists / CTAs. Heavy-tailed rows therefore cost O(k log n) survivors, not O(n).
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
-        unsigned long long* cb = cb_s + row * TC_CB;
+        uint2* cb = reinterpret_cast<uint2*>(cb_s) + row * TC_CB;   // {t bits, list entry}
+        const TcFlushArgs fa{p.thr, p.cand_key, p.cand_count, p.cap, p.k, p.is_ip};
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -298,23 +371,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const bool row_ok = row < it.q_count;
             int q = 0, cnt = 0;
             float qn = 0.f, tq = -INFINITY;
-            float gmin[TC_G];
+            float gmin[SEED ? TC_G : 1];
 #pragma unroll
-            for (int g = 0; g < TC_G; ++g) gmin[g] = INFINITY;
+            for (int g = 0; g < (SEED ? TC_G : 1); ++g) gmin[g] = INFINITY;
             if (row_ok) {
                 q = __ldg(p.group_queries + it.q_begin + row);
                 if (!p.is_ip) qn = __ldg(p.qnorm + q);
                 if (!SEED) {
-                    const float T = p.thr[q];
+                    const float T = ordered_to_f32(*reinterpret_cast<volatile uint32_t*>(p.thr + q));
                     tq = p.is_ip ? T : 0.5f * (T - qn);   // score <= T  <=>  t <= tq
                 }
             }
-            auto flush = [&]() {
-                const int base = atomicAdd(p.cand_count + q, cnt);
-                for (int j = 0; j < cnt; ++j)
-                    if (base + j < p.cap) p.cand_key[(size_t)q * p.cap + base + j] = cb[(j + row) & (TC_CB - 1)];
-                cnt = 0;
-            };
             long long lo, hi;
             item_rows(it, lo, hi);
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
@@ -335,21 +402,27 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         if (g & 1) tc_ld32_async(taddr + (g + 1) * 32, ra);
                         else tc_ld32_async(taddr + (g + 1) * 32, rb);
                     }
-                    uint32_t mask;
-                    if (g & 1) tc_process32<SEED>(rb, hv + g * 32, tq, gmin, mask);
-                    else tc_process32<SEED>(ra, hv + g * 32, tq, gmin, mask);
-                    if (!SEED) {
-                        if (!row_ok) mask = 0;
-                        while (mask) {
-                            const int c = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            uint32_t bits = 0;
+                    float t[32], m4[8];
+                    const float mn = (g & 1) ? tc_diff32(rb, hv + g * 32, t, m4) : tc_diff32(ra, hv + g * 32, t, m4);
+                    if (SEED) {
 #pragma unroll
-                            for (int cc = 0; cc < 32; ++cc) bits = (cc == c) ? ((g & 1) ? rb[cc] : ra[cc]) : bits;
-                            const float t = hv[g * 32 + c] - __uint_as_float(bits);
-                            const float score = p.is_ip ? t : fmaf(2.0f, t, qn);
-                            cb[(cnt + row) & (TC_CB - 1)] = make_key(score, (uint32_t)(row0 + g * 32 + c));
-                            if (++cnt == TC_CB) flush();
+                        for (int c = 0; c < 32; ++c) gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], t[c]);
+                    } else if (mn <= tq) {   // (tq = -inf for rows past the end of the tile)
+                        const uint32_t e0 = (uint32_t)(row0 + g * 32);
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            if (m4[c4] <= tq) {
+#pragma unroll
+                                for (int c = c4 * 4; c < c4 * 4 + 4; ++c) {
+                                    if (t[c] <= tq) {
+                                        cb[(cnt + row) & (TC_CB - 1)] = make_uint2(__float_as_uint(t[c]), e0 + c);
+                                        if (++cnt == TC_CB) {
+                                            tq = tc_flush_row(fa, cb, row, cnt, tq, q, qn, p.k <= TC_KMAX_TIGHTEN);
+                                            cnt = 0;
+                                        }
+                                    }
+                                }
+                            }
                         }
                     }
                     if (g + 1 < TC_N / 32) {
@@ -363,23 +436,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&h_empty[hs]); }
             }
             if (SEED) {
-                // T = k-th smallest of the 16 group minima: 16 distinct entries of ONE list, so k real candidates
-                // are at or below it. (score = |q|^2 + 2 t for L2, t for IP)
-                float tk = INFINITY;
+                // T = k-th smallest of the 64 group minima: distinct entries of ONE list, so k real candidates
+                // are at or below it. (score = |q|^2 + 2 t for L2, t for IP.) Needs k <= 16.
                 if (row_ok) {
-                    for (int j = 0; j < p.k; ++j) {  // extract the minimum k times
-                        float mn = INFINITY;
-                        int at = 0;
+                    float a[16], b[16];
 #pragma unroll
-                        for (int g = 0; g < TC_G; ++g) { if (gmin[g] < mn) { mn = gmin[g]; at = g; } }
-                        tk = mn;
+                    for (int j = 0; j < 16; ++j) { a[j] = gmin[j]; b[j] = gmin[16 + j]; }
+                    tc_sort16(a); tc_sort16(b); tc_merge_low16(a, b);
+                    float c[16];
 #pragma unroll
-                        for (int g = 0; g < TC_G; ++g) gmin[g] = (g == at) ? INFINITY : gmin[g];
-                    }
-                    p.thr[q] = p.is_ip ? tk : fmaf(2.0f, tk, qn);
+                    for (int j = 0; j < 16; ++j) { b[j] = gmin[32 + j]; c[j] = gmin[48 + j]; }
+                    tc_sort16(b); tc_sort16(c); tc_merge_low16(b, c);
+                    tc_merge_low16(a, b);
+                    const float tk = tc_pick16(a, p.k - 1);
+                    p.thr[q] = f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn));
                 }
             } else if (cnt) {
-                flush();
+                tc_flush_row(fa, cb, row, cnt, tq, q, qn, false);
             }
         }
     }
@@ -414,10 +487,12 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
 }
 
 // gq[slot, :] = q[group_queries[slot], :]  (queries in group order, so a tile of a group is one TMA box)
+// n_slots (device scalar = group_offsets[B]) is the number of valid slots: explicit probe sets may hold invalid
+// (-1) entries, so it can be smaller than the host-side bound P the buffers were sized with.
 __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
-                                            long long P, float* __restrict__ gq) {
+                                            long long P, const long long* __restrict__ n_slots, float* __restrict__ gq) {
     const int per_row = ds / 4;
-    const long long total = P * per_row;
+    const long long total = (*n_slots < P ? *n_slots : P) * per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long s = i / per_row;
         const int c = (int)(i % per_row) * 4;
@@ -429,7 +504,7 @@ __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ld
 // T[q] = k-th best exact score over DISTINCT ids of the seed scan's (up to) two partial lists of the query,
 // +inf when fewer than k distinct candidates were seen. Any k real candidates bound the final k-th score.
 __global__ void seed_threshold_kernel(const unsigned long long* part_key, const int* probe_slot, const int* seed_ids, int Q,
-                                      int k, float* thr) {
+                                      int k, uint32_t* thr) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
         const unsigned long long* a = seed_ids[2 * q] >= 0 ? part_key + (size_t)probe_slot[2 * q] * k : nullptr;
         const unsigned long long* b = seed_ids[2 * q + 1] >= 0 ? part_key + (size_t)probe_slot[2 * q + 1] * k : nullptr;
@@ -446,11 +521,11 @@ __global__ void seed_threshold_kernel(const unsigned long long* part_key, const 
             kth = x;
             ++n;
         }
-        thr[q] = (n == k) ? key_score(kth) : INFINITY;
+        thr[q] = f32_to_ordered((n == k) ? key_score(kth) : INFINITY);
     }
 }
 
-__global__ void fill_f32_kernel(float* x, long long n, float v) {
+__global__ void fill_u32_kernel(uint32_t* x, long long n, uint32_t v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
 }
 // seed1[q] = seed_ids[2 q]: the single best list per query for the tensor-core seed pass
