@@ -128,7 +128,7 @@ struct lira_index {
     cudaStream_t stream = nullptr;
     Workspace ws, ws_seed;
     DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
-    float* vnorm = nullptr;      // |v|^2 per list entry (tensor-core path)
+    float* vnorm = nullptr;      // |v|^2 / 2 per list entry (tensor-core path)
     bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
     bool use_tc = true;
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
@@ -482,7 +482,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
     int one_zero[2] = {1, 0};  // [0] query batch exactly representable, [1] number of overflowed queries
     LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 8, cudaMemcpyHostToDevice, st));
-    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>());
+    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), 1.0f);
     LIRA_LAUNCH_CHECK();
     long long P = 0;
     const long long* po = nullptr;
@@ -712,7 +712,7 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     int one = 1;
     LIRA_CUDA_OK(cudaMemcpy(d_flag, &one, 4, cudaMemcpyHostToDevice));
     if (h->E > 0) {
-        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag);
+        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, 0.5f);
         g_launches.fetch_add(1);
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));

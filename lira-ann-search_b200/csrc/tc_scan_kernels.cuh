@@ -46,7 +46,7 @@ struct TcParams {
     int* work_counter;               // zeroed before launch: dynamic item scheduler
     int nk;                          // K blocks (ceil(d / 32)), <= TC_MAX_KB
     int max_rows;                    // > 0: only the first max_rows entries of each list (seed pass)
-    const float* vnorm;              // [E] |v|^2 (fp32, sequential order)
+    const float* vnorm;              // [E] |v|^2 / 2 (fp32, sequential order)
     const float* qnorm;              // [Q] |q|^2
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
                                      //     seed pass, read AND tightened (atomicMin) by the filter pass
@@ -229,7 +229,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 4); }
+        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], 4); }  // every loader lane arrives
         for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 6); }  // MMA + loader + 4 epilogue warps
         mbar_fence_init();
     }
@@ -335,16 +335,25 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const int hs = m % TC_NH;
                 mbar_wait(&h_empty[hs], ((m / TC_NH) & 1) ^ 1u);
+                float* dst = hv_s + hs * TC_N;
+                if (!p.is_ip && row0 + TC_N <= hi) {
+                    // full chunk: asynchronous copies, the barrier is signalled by the copy engine, and the warp
+                    // moves on to the next chunk at once (TC_NH chunks of norms in flight)
 #pragma unroll
-                for (int j = 0; j < TC_N / 32; ++j) {
-                    const long long e = row0 + lane + 32 * j;
-                    // past the end of the list: NaN, so that neither `t <= tq` (even for tq = +inf) nor fminf picks it
-                    float h = __int_as_float(0x7fc00000);
-                    if (e < hi) h = p.is_ip ? 0.0f : 0.5f * __ldg(p.vnorm + e);
-                    hv_s[hs * TC_N + lane + 32 * j] = h;
+                    for (int j = 0; j < TC_N / 32; ++j)
+                        cp_async_4(smem_u32(dst + lane + 32 * j), p.vnorm + row0 + lane + 32 * j);
+                    cp_async_mbar_arrive_noinc(&h_full[hs]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TC_N / 32; ++j) {
+                        const long long e = row0 + lane + 32 * j;
+                        // past the end of the list: NaN, so that neither `t <= tq` (even for tq = +inf) nor fminf picks it
+                        float h = __int_as_float(0x7fc00000);
+                        if (e < hi) h = p.is_ip ? 0.0f : __ldg(p.vnorm + e);
+                        dst[lane + 32 * j] = h;
+                    }
+                    mbar_arrive(&h_full[hs]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&h_full[hs]);
             }
         }
     } else if (warp >= 4) {
@@ -404,18 +413,41 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     }
                     float t[32], m4[8];
                     const float mn = (g & 1) ? tc_diff32(rb, hv + g * 32, t, m4) : tc_diff32(ra, hv + g * 32, t, m4);
+                    // the prefetch has had the arithmetic above to land; no TMEM load is in flight across the
+                    // (rare) out-of-line flush call below, whose register saves must not race the load's writes
+                    if (g + 1 < TC_N / 32) {
+                        if (g & 1) tc_ld_wait(ra);
+                        else tc_ld_wait(rb);
+                    }
                     if (SEED) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], t[c]);
-                    } else if (mn <= tq) {   // (tq = -inf for rows past the end of the tile)
-                        const uint32_t e0 = (uint32_t)(row0 + g * 32);
+                    } else if (__any_sync(0xffffffffu, mn <= tq)) {
+                        // Survivors: about one per 1024 pairs, i.e. this branch is taken for roughly every other
+                        // group, so it is straight-line code: a lane picks its first passing 4-column block with
+                        // a select tree (no dynamic register indexing), tests the block's 4 values and stages the
+                        // ones at or below the bound; a lane with several passing blocks (rare) goes round again.
+                        // (tq = -inf for rows past the end of the tile, so they never pass.)
+                        uint32_t qm = 0;
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            if (m4[c4] <= tq) {
+                        for (int i = 0; i < 8; ++i) qm |= (m4[i] <= tq) ? (1u << i) : 0u;
+                        do {
+                            const int j = __ffs(qm) - 1;   // -1: nothing (left) for this lane
+                            qm &= qm - 1;
+                            float s4[4];
 #pragma unroll
-                                for (int c = c4 * 4; c < c4 * 4 + 4; ++c) {
-                                    if (t[c] <= tq) {
-                                        cb[(cnt + row) & (TC_CB - 1)] = make_uint2(__float_as_uint(t[c]), e0 + c);
+                            for (int u = 0; u < 4; ++u) {
+                                const float x0 = (j & 1) ? t[4 + u] : t[u], x1 = (j & 1) ? t[12 + u] : t[8 + u];
+                                const float x2 = (j & 1) ? t[20 + u] : t[16 + u], x3 = (j & 1) ? t[28 + u] : t[24 + u];
+                                const float y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
+                                s4[u] = (j & 4) ? y1 : y0;
+                            }
+                            if (j >= 0) {
+                                const uint32_t e0 = (uint32_t)(row0 + g * 32 + j * 4);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (s4[u] <= tq) {
+                                        cb[(cnt + row) & (TC_CB - 1)] = make_uint2(__float_as_uint(s4[u]), e0 + u);
                                         if (++cnt == TC_CB) {
                                             tq = tc_flush_row(fa, cb, row, cnt, tq, q, qn, p.k <= TC_KMAX_TIGHTEN);
                                             cnt = 0;
@@ -423,11 +455,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                     }
                                 }
                             }
-                        }
-                    }
-                    if (g + 1 < TC_N / 32) {
-                        if (g & 1) tc_ld_wait(ra);
-                        else tc_ld_wait(rb);
+                        } while (__any_sync(0xffffffffu, qm != 0));
                     }
                 }
                 // this warp is done with the accumulator and the norm slot
@@ -469,7 +497,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // most 11 bits (exact in TF32) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
 // path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit
 __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, long long n, float* __restrict__ out,
-                                 int* __restrict__ exact_flag) {
+                                 int* __restrict__ exact_flag, float out_scale) {
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float* r = x + i * ld;
@@ -480,7 +508,7 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
             bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
             bad |= !(fabsf(v.x) <= 2047.f && fabsf(v.y) <= 2047.f && fabsf(v.z) <= 2047.f && fabsf(v.w) <= 2047.f);
         }
-        out[i] = s;
+        out[i] = s * out_scale;
         bad |= !(s < 4194304.0f);  // |x|^2 < 2^22  =>  |q|^2 + |v|^2 + 2|q.v| < 2^24
     }
     if (bad && exact_flag) *exact_flag = 0;
