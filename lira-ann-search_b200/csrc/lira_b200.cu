@@ -284,7 +284,7 @@ __global__ void scatter_csr_kernel(const long long* probe_offsets, const int* pr
     if (mask && !mask[q]) return;
     for (long long j = probe_offsets[q] + lane; j < probe_offsets[q + 1]; j += 32) {
         const int b = probe_ids[j];
-        if (b < 0 || b >= B) continue;
+        if (b < 0 || b >= B) { probe_slot[j] = -1; continue; }
         const int pos = (int)group_offsets[b] + atomicAdd(cursor + b, 1);
         group_queries[pos] = q;
         probe_slot[j] = pos;
@@ -463,7 +463,6 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
 
 static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows of each of the two best probed lists
 static constexpr int TC_SEED_ROWS_TC = 1024;  // tensor-core seed (k <= 16): rows of the best probed list
-static constexpr int TC_CAND_CAP = 4096;   // candidate slots per query
 
 // The online query path on the tensor cores (tc_scan_kernels.cuh). *done = true when results were produced
 // for every query whose ws.redo flag is 0; *n_redo counts the queries (flag 1) whose candidate buffer
@@ -569,9 +568,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     CUtensorMap tmap_q;
     if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
     // ---- filter on the tensor cores ----
-    if (int rc = ws.cand_key.ensure((size_t)Q * TC_CAND_CAP * 8)) return rc;
-    if (int rc = ws.cand_count.ensure((size_t)Q * 4)) return rc;
-    LIRA_CUDA_OK(cudaMemsetAsync(ws.cand_count.p, 0, (size_t)Q * 4, st));
+    // one private candidate region per (pair, column half); every valid pair's owner writes its count
+    if (int rc = ws.cand_key.ensure((size_t)P * 2 * TC_CAPP * 8)) return rc;
+    if (int rc = ws.cand_count.ensure((size_t)P * 2 * 4)) return rc;
     TcParams tp;
     tp.group_queries = ws.group_queries.as<int>();
     tp.list_offsets = h->d_offsets;
@@ -585,7 +584,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.thr = ws.thr.as<uint32_t>();
     tp.cand_key = ws.cand_key.as<unsigned long long>();
     tp.cand_count = ws.cand_count.as<int>();
-    tp.cap = TC_CAND_CAP;
+    tp.cap = TC_CAPP;
     tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
@@ -593,8 +592,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
-    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), TC_CAND_CAP, h->ids, k, (int)Q, dedup,
-                    h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1};
+    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), TC_CAPP, po, ws.probe_slot.as<int>(), h->ids, k,
+                    (int)Q, dedup, h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1};
     const int warps = 8;
     if (k <= 32) refine_topk_kernel<1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else refine_topk_kernel<4><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
@@ -602,17 +601,14 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     if (getenv("LIRA_DEBUG")) {
-        std::vector<int> cc(Q);
-        std::vector<uint32_t> th(Q);
-        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+        std::vector<int> cc((size_t)P * 2);
+        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * 2 * 4, cudaMemcpyDeviceToHost);
         std::vector<int> sorted(cc);
         std::sort(sorted.begin(), sorted.end());
-        long long tot = 0, ninf = 0;
+        long long tot = 0;
         for (int c : cc) tot += c;
-        for (uint32_t t : th) ninf += (t == 0xFF800000u);
-        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f p50 %d p90 %d p99 %d max %d; T=inf for %lld; redo %d\n",
-                Q, P, (double)tot / Q, sorted[Q / 2], sorted[Q * 9 / 10], sorted[Q * 99 / 100], sorted[Q - 1], ninf, *n_redo);
+        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, half) p50 %d p99 %d max %d; redo %d\n",
+                Q, P, (double)tot / Q, sorted[P], sorted[(size_t)(P * 2 * 0.99)], sorted[P * 2 - 1], *n_redo);
     }
     h->last_path = 1;
     h->last_redo = *n_redo;

@@ -280,7 +280,9 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
     for (int s = 0; s < S; ++s) key[s] = KEY_INF;
     unsigned long long kth = KEY_INF;
     for (long long j = p.probe_offsets[q]; j < p.probe_offsets[q + 1]; ++j) {
-        const unsigned long long* src = p.part_key + (size_t)p.probe_slot[j] * k;
+        const int slot = p.probe_slot[j];
+        if (slot < 0) continue;  // invalid probe
+        const unsigned long long* src = p.part_key + (size_t)slot * k;
         for (int e0 = 0; e0 < k; e0 += 32) {
             const int e = e0 + lane;
             const unsigned long long x = (e < k) ? src[e] : KEY_INF;

@@ -25,17 +25,18 @@ namespace lira {
 static constexpr int TC_M = 128;         // queries per tile (UMMA M, TMEM lanes)
 static constexpr int TC_N = 128;         // vectors per chunk (UMMA N, TMEM columns per accumulator)
 static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128 = 512 columns)
-static constexpr int TC_NSTAGE = 5;      // B ring stages (16 KiB each)
+static constexpr int TC_NSTAGE = 6;      // B ring stages (16 KiB each)
 static constexpr int TC_MAX_KB = 4;      // K blocks of 32 floats resident per A tile: d <= 128
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
-static constexpr int TC_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+static constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc + norm loader, warps 4-11 epilogue
+static constexpr int TC_EPI_WARPS = 8;    // two per TMEM lane quadrant, each takes half of the 128 accumulator columns
 
-static constexpr int TC_CB = 16;         // per-row staging slots for survivors (flushed with ONE atomic per 16)
+static constexpr int TC_CB = 16;         // a row's best survivors kept in a sorted register chain (k <= 16)
+static constexpr int TC_CAPP = 64;       // candidate slots per (query, list) pair and column half (16 used when k <= 16)
 
 static constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES   // A, double buffered
                                         + (size_t)TC_NSTAGE * B_STAGE_BYTES     // B ring
-                                        + (size_t)TC_NACC * TC_N * 4            // |v|^2 / 2 per column
-                                        + (size_t)TC_M * TC_CB * 8              // survivor staging, one row per thread
+                                        + (size_t)4 * TC_N * 4                  // |v|^2 / 2 per column (TC_NH slots)
                                         + 512;                                  // barriers, item queue, tmem slot
 
 struct TcParams {
@@ -50,8 +51,8 @@ struct TcParams {
     const float* qnorm;              // [Q] |q|^2
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
                                      //     seed pass, read AND tightened (atomicMin) by the filter pass
-    unsigned long long* cand_key;    // [Q, cap] (score, list entry) keys
-    int* cand_count;                 // [Q]
+    unsigned long long* cand_key;    // [2 P, cap] (score, list entry) keys: one private region per (pair, column half)
+    int* cand_count;                 // [2 P] survivors of the region's owner (may exceed cap: the query is then redone)
     int cap;
     int k;
     int is_ip;
@@ -163,44 +164,6 @@ __device__ __forceinline__ float tc_diff32(const uint32_t (&r)[32], const float*
     return fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
 }
 
-// Rare path of the filter epilogue, deliberately NOT inlined (it is instantiated at every column of the unrolled
-// survivor expansion): write the row's staged survivors {t bits, list entry} that are at or below the bound to
-// the query's candidate buffer. With `tighten` (staging buffer full, k <= 16) the k-th smallest staged t first
-// replaces the bound if it is smaller -- the staged entries are TC_CB distinct entries of one list, so k real
-// candidates are at or below it -- and the new bound is published for the query's other rows. Returns the bound.
-struct TcFlushArgs {   // by value: taking the address of the kernel parameter block would demote it to local memory
-    uint32_t* thr;
-    unsigned long long* cand_key;
-    int* cand_count;
-    int cap, k, is_ip;
-};
-__device__ __noinline__ float tc_flush_row(const TcFlushArgs p, const uint2* cb, int row, int cnt, float tq, int q, float qn,
-                                           bool tighten) {
-    if (tighten) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(cb[j].x);
-        tc_sort16(v);
-        const float tk = tc_pick16(v, p.k - 1);
-        if (tk < tq) {
-            tq = tk;
-            atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
-        }
-    }
-    int nkeep = 0;
-    for (int j = 0; j < cnt; ++j) nkeep += (__uint_as_float(cb[(j + row) & (TC_CB - 1)].x) <= tq) ? 1 : 0;
-    int base = atomicAdd(p.cand_count + q, nkeep);
-    for (int j = 0; j < cnt; ++j) {
-        const uint2 e = cb[(j + row) & (TC_CB - 1)];
-        const float t = __uint_as_float(e.x);
-        if (t <= tq) {
-            if (base < p.cap) p.cand_key[(size_t)q * p.cap + base] = make_key(p.is_ip ? t : fmaf(2.0f, t, qn), e.y);
-            ++base;
-        }
-    }
-    return tq;
-}
-
 template <bool SEED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
@@ -209,8 +172,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint8_t* sA = smem_raw;                                              // [2][TC_MAX_KB][128 x 128 B]
     uint8_t* sB = sA + (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES;            // [TC_NSTAGE][128 x 128 B]
     float* hv_s = (float*)(sB + (size_t)TC_NSTAGE * B_STAGE_BYTES);      // [TC_NH][128]
-    unsigned long long* cb_s = (unsigned long long*)(hv_s + TC_NH * TC_N);  // [128][TC_CB]
-    uint64_t* bars = (uint64_t*)(cb_s + TC_M * TC_CB);
+    uint64_t* bars = (uint64_t*)(hv_s + TC_NH * TC_N);
     uint64_t* a_full = bars;                        // [2]
     uint64_t* a_empty = a_full + 2;                 // [2]
     uint64_t* b_full = a_empty + 2;                 // [TC_NSTAGE]
@@ -228,9 +190,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], 4); }  // every loader lane arrives
-        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 6); }  // MMA + loader + 4 epilogue warps
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], TC_EPI_WARPS); }  // every loader lane arrives
+        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + TC_EPI_WARPS); }  // MMA + loader + epilogue warps
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -358,17 +320,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
-        // A thread owns one query row for the whole work item. Filter: survivors are rare, so the hot loop only
-        // forms t = |v|^2/2 - q.v and a 3-input-min tree per 32 columns (FADD + FMNMX3, no divergence); a group
-        // whose minimum passes the row's bound is expanded column by column. Survivors go to the row's TC_CB
-        // staging slots in shared memory. A full staging buffer is a chance to TIGHTEN the bound: its k-th
-        // smallest entry bounds the final k-th best (TC_CB distinct entries of one list), so the row keeps only
-        // entries at or below it, continues with the tighter bound and publishes it (atomicMin) for the query's
-        // rows in other lists / CTAs. Heavy-tailed rows therefore cost O(k log n) survivors, not O(n).
+        // Two warps per TMEM lane quadrant: a thread owns one query row and one half (64 columns) of every
+        // accumulator of the work item. Filter: the hot loop forms t = |v|^2/2 - q.v and a 3-input-min tree per 32
+        // columns (FADD + FMNMX3, no divergence). About one pair in a thousand survives, i.e. roughly every other
+        // 32-column group of a warp holds one, so the survivor path is straight-line too: a lane picks its first
+        // passing 4-column block with a select tree (no dynamic register indexing) and appends the block's
+        // passing entries to the PRIVATE candidate region of its (query, list, half) -- plain stores, no atomics,
+        // no shared staging. The last 16 survivors' t stay in a register shift chain; every 16th survivor their
+        // k-th smallest TIGHTENS the row's bound and is published (atomicMin) for the query's rows in other lists
+        // and CTAs, so heavy-tailed rows cost O(k log n) survivors, not O(n).
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;          // which 64 of the 128 accumulator columns
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
-        uint2* cb = reinterpret_cast<uint2*>(cb_s) + row * TC_CB;   // {t bits, list entry}
-        const TcFlushArgs fa{p.thr, p.cand_key, p.cand_count, p.cap, p.k, p.is_ip};
+        constexpr int NG = TC_N / 64;              // 32-column groups per thread and chunk (2)
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -383,12 +347,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             float gmin[SEED ? TC_G : 1];
 #pragma unroll
             for (int g = 0; g < (SEED ? TC_G : 1); ++g) gmin[g] = INFINITY;
+            // k <= 16: the row's 16 best survivors so far, ascending in t (exact running top-16 of this thread's
+            // (query, list, half)); t16[k-1] is then an exact bound and is folded into tq after every insertion
+            float t16[TC_CB];
+            uint32_t e16[TC_CB];
+#pragma unroll
+            for (int j = 0; j < TC_CB; ++j) { t16[j] = INFINITY; e16[j] = 0; }
+            bool lost = false;     // an entry that still passed the bound fell off the chain: redo the query exactly
+            const bool keep_mode = p.k <= TC_KMAX_TIGHTEN;
+            unsigned long long* cand = nullptr;
             if (row_ok) {
                 q = __ldg(p.group_queries + it.q_begin + row);
                 if (!p.is_ip) qn = __ldg(p.qnorm + q);
                 if (!SEED) {
                     const float T = ordered_to_f32(*reinterpret_cast<volatile uint32_t*>(p.thr + q));
                     tq = p.is_ip ? T : 0.5f * (T - qn);   // score <= T  <=>  t <= tq
+                    cand = p.cand_key + ((size_t)(it.q_begin + row) * 2 + half) * p.cap;
                 }
             }
             long long lo, hi;
@@ -396,38 +370,25 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
                 const int hs = m % TC_NH;
-                const float* hv = hv_s + hs * TC_N;
+                const float* hv = hv_s + hs * TC_N + half * 64;
                 mbar_wait(&h_full[hs], (m / TC_NH) & 1);
                 mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N + half * 64;
                 uint32_t ra[32], rb[32];
                 tc_ld32_async(taddr, ra);
-                tc_ld_wait(ra);
+                tc_ld32_async(taddr + 32, rb);
+                tc_ld_wait(ra);   // (waits for both loads)
+                tc_ld_wait(rb);
 #pragma unroll
-                for (int g = 0; g < TC_N / 32; ++g) {
-                    // prefetch the next 32 columns while this group is processed
-                    if (g + 1 < TC_N / 32) {
-                        if (g & 1) tc_ld32_async(taddr + (g + 1) * 32, ra);
-                        else tc_ld32_async(taddr + (g + 1) * 32, rb);
-                    }
+                for (int g = 0; g < NG; ++g) {
                     float t[32], m4[8];
                     const float mn = (g & 1) ? tc_diff32(rb, hv + g * 32, t, m4) : tc_diff32(ra, hv + g * 32, t, m4);
-                    // the prefetch has had the arithmetic above to land; no TMEM load is in flight across the
-                    // (rare) out-of-line flush call below, whose register saves must not race the load's writes
-                    if (g + 1 < TC_N / 32) {
-                        if (g & 1) tc_ld_wait(ra);
-                        else tc_ld_wait(rb);
-                    }
                     if (SEED) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], t[c]);
                     } else if (__any_sync(0xffffffffu, mn <= tq)) {
-                        // Survivors: about one per 1024 pairs, i.e. this branch is taken for roughly every other
-                        // group, so it is straight-line code: a lane picks its first passing 4-column block with
-                        // a select tree (no dynamic register indexing), tests the block's 4 values and stages the
-                        // ones at or below the bound; a lane with several passing blocks (rare) goes round again.
-                        // (tq = -inf for rows past the end of the tile, so they never pass.)
+                        // (tq = -inf for rows past the end of the tile, so they never pass)
                         uint32_t qm = 0;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) qm |= (m4[i] <= tq) ? (1u << i) : 0u;
@@ -442,18 +403,41 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 const float y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
                                 s4[u] = (j & 4) ? y1 : y0;
                             }
+                            uint32_t pm = 0;
                             if (j >= 0) {
-                                const uint32_t e0 = (uint32_t)(row0 + g * 32 + j * 4);
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    if (s4[u] <= tq) {
-                                        cb[(cnt + row) & (TC_CB - 1)] = make_uint2(__float_as_uint(s4[u]), e0 + u);
-                                        if (++cnt == TC_CB) {
-                                            tq = tc_flush_row(fa, cb, row, cnt, tq, q, qn, p.k <= TC_KMAX_TIGHTEN);
-                                            cnt = 0;
-                                        }
-                                    }
+                                for (int u = 0; u < 4; ++u) pm |= (s4[u] <= tq) ? (1u << u) : 0u;
+                            }
+                            const uint32_t e0 = (uint32_t)(row0 + half * 64 + g * 32 + j * 4);
+                            while (pm) {
+                                const int u = __ffs(pm) - 1;
+                                pm &= pm - 1;
+                                const float x = (u & 2) ? ((u & 1) ? s4[3] : s4[2]) : ((u & 1) ? s4[1] : s4[0]);
+                                if (!(x <= tq)) continue;   // the bound may have tightened inside this block
+                                if (!keep_mode) {   // k > 16: every survivor goes to the region (overflow -> exact redo)
+                                    if (cnt < p.cap) cand[cnt] = make_key(p.is_ip ? x : fmaf(2.0f, x, qn), e0 + u);
+                                    ++cnt;
+                                    continue;
                                 }
+                                const uint32_t e = e0 + u;
+                                const float vout = fmaxf(x, t16[TC_CB - 1]);   // what leaves (or never enters) the chain
+#pragma unroll
+                                for (int i = TC_CB - 1; i > 0; --i) {
+                                    const bool sh = x < t16[i - 1], in = x < t16[i];
+                                    e16[i] = sh ? e16[i - 1] : (in ? e : e16[i]);
+                                    t16[i] = sh ? t16[i - 1] : (in ? x : t16[i]);
+                                }
+                                {
+                                    const bool in = x < t16[0];
+                                    e16[0] = in ? e : e16[0];
+                                    t16[0] = in ? x : t16[0];
+                                }
+                                const float tk = tc_pick16(t16, p.k - 1);
+                                if (tk < tq) {
+                                    tq = tk;
+                                    atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
+                                }
+                                lost |= (vout <= tq) && (vout < INFINITY);
                             }
                         } while (__any_sync(0xffffffffu, qm != 0));
                     }
@@ -464,8 +448,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&h_empty[hs]); }
             }
             if (SEED) {
-                // T = k-th smallest of the 64 group minima: distinct entries of ONE list, so k real candidates
-                // are at or below it. (score = |q|^2 + 2 t for L2, t for IP.) Needs k <= 16.
+                // T = k-th smallest of this half's 64 group minima: distinct entries of ONE list, so k real
+                // candidates are at or below it (score = |q|^2 + 2 t for L2, t for IP); the two halves of a row
+                // combine by atomicMin. Needs k <= 16.
                 if (row_ok) {
                     float a[16], b[16];
 #pragma unroll
@@ -477,10 +462,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     tc_sort16(b); tc_sort16(c); tc_merge_low16(b, c);
                     tc_merge_low16(a, b);
                     const float tk = tc_pick16(a, p.k - 1);
-                    p.thr[q] = f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn));
+                    atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
                 }
-            } else if (cnt) {
-                tc_flush_row(fa, cb, row, cnt, tq, q, qn, false);
+            } else if (row_ok) {
+                if (keep_mode) {
+                    cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < TC_CB; ++i)
+                        if (t16[i] <= tq && t16[i] < INFINITY) cand[cnt++] = make_key(p.is_ip ? t16[i] : fmaf(2.0f, t16[i], qn), e16[i]);
+                    if (lost) cnt = p.cap + 1;
+                }
+                p.cand_count[(size_t)(it.q_begin + row) * 2 + half] = cnt;
             }
         }
     }
@@ -570,16 +562,19 @@ __global__ void first_probes_kernel(const long long* probe_offsets, const int* p
     }
 }
 
-// refine: candidates (score, list entry) of a query -> exact top-k over distinct ids. One warp per query.
+// refine: the candidate regions (score, list entry) of a query's probed (list, half) pairs -> exact top-k over
+// distinct ids. One warp per query.
 struct RefineParams {
-    const unsigned long long* cand_key;
-    const int* cand_count;
+    const unsigned long long* cand_key;   // [2 P, cap]
+    const int* cand_count;                // [2 P]
     int cap;
+    const long long* probe_offsets;       // [Q+1]
+    const int* probe_slot;                // [P] slot of the j-th probe of a query (-1: invalid probe)
     const int* list_ids;
     int k, Q, dedup, is_ip;
     float* out_dist;
     long long* out_ids;
-    int* redo;      // [Q] 1 when the query had more candidates than `cap` (its row is left for the exact path)
+    int* redo;      // [Q] 1 when a region of the query overflowed `cap` (its row is left for the exact path)
     int* n_redo;    // number of such queries
 };
 
@@ -589,43 +584,65 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= p.Q) return;
     const int k = p.k;
-    int n = p.cand_count[q];
-    if (n > p.cap) {
-        if (lane == 0) { p.redo[q] = 1; atomicAdd(p.n_redo, 1); }
-        return;
-    }
-    if (lane == 0) p.redo[q] = 0;
     unsigned long long key[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) key[s] = KEY_INF;
     unsigned long long kth = KEY_INF;
-    const unsigned long long* src = p.cand_key + (size_t)q * p.cap;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-        const int e = e0 + lane;
-        unsigned long long x = KEY_INF;
-        if (e < n) {
-            const unsigned long long c = src[e];
-            x = (c & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(c));  // entry -> global id
-        }
-        uint32_t mm = __ballot_sync(0xffffffffu, x < kth);
-        while (mm) {
-            const int sl = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const unsigned long long y = shfl_u64(x, sl);
-            if (!(y < kth)) continue;
-            bool dup = false;
-            if (p.dedup) {
-                bool mine = false;
-#pragma unroll
-                for (int s = 0; s < S; ++s) mine |= (key[s] == y);
-                dup = __any_sync(0xffffffffu, mine);
+    bool overflow = false;
+    const long long lo = p.probe_offsets[q], hi = p.probe_offsets[q + 1];
+    for (long long j0 = lo; j0 < hi; j0 += 16) {
+        // 16 probes = 32 regions per pass: lane l looks at region (probe j0 + l/2, half l&1)
+        const long long j = j0 + (lane >> 1);
+        int region = -1, cnt = 0;
+        if (j < hi) {
+            const int slot = p.probe_slot[j];
+            if (slot >= 0) {
+                region = slot * 2 + (lane & 1);
+                cnt = p.cand_count[region];
             }
-            if (!dup) {
-                warp_sorted_insert<S>(key, y, lane);
-                kth = warp_sorted_get<S>(key, k - 1);
+        }
+        overflow |= cnt > p.cap;
+        uint32_t live = __ballot_sync(0xffffffffu, cnt > 0);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            int n = __shfl_sync(0xffffffffu, cnt, src);
+            n = n < p.cap ? n : p.cap;
+            const unsigned long long* srcp = p.cand_key + (size_t)__shfl_sync(0xffffffffu, region, src) * p.cap;
+            for (int e0 = 0; e0 < n; e0 += 32) {
+                const int e = e0 + lane;
+                unsigned long long x = KEY_INF;
+                if (e < n) {
+                    const unsigned long long c = srcp[e];
+                    x = (c & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(c));  // entry -> global id
+                }
+                uint32_t mm = __ballot_sync(0xffffffffu, x < kth);
+                while (mm) {
+                    const int sl = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const unsigned long long y = shfl_u64(x, sl);
+                    if (!(y < kth)) continue;
+                    bool dup = false;
+                    if (p.dedup) {
+                        bool mine = false;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) mine |= (key[s] == y);
+                        dup = __any_sync(0xffffffffu, mine);
+                    }
+                    if (!dup) {
+                        warp_sorted_insert<S>(key, y, lane);
+                        kth = warp_sorted_get<S>(key, k - 1);
+                    }
+                }
             }
         }
     }
+    overflow = __any_sync(0xffffffffu, overflow);
+    if (overflow) {
+        if (lane == 0) { p.redo[q] = 1; atomicAdd(p.n_redo, 1); }
+        return;
+    }
+    if (lane == 0) p.redo[q] = 0;
     bool valid[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
