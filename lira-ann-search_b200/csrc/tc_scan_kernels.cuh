@@ -190,9 +190,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_EPI_WARPS); }
-        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], TC_EPI_WARPS); }  // every loader lane arrives
-        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + TC_EPI_WARPS); }  // MMA + loader + epilogue warps
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SEED ? 4 : TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], SEED ? 4 : TC_EPI_WARPS); }  // every loader lane arrives
+        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + (SEED ? 4 : TC_EPI_WARPS)); }  // MMA + loader + epilogue warps
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -318,7 +318,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && (!SEED || warp < 8)) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
         // Two warps per TMEM lane quadrant: a thread owns one query row and one half (64 columns) of every
         // accumulator of the work item. Filter: the hot loop forms t = |v|^2/2 - q.v and a 3-input-min tree per 32
@@ -330,9 +330,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // k-th smallest TIGHTENS the row's bound and is published (atomicMin) for the query's rows in other lists
         // and CTAs, so heavy-tailed rows cost O(k log n) survivors, not O(n).
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;          // which 64 of the 128 accumulator columns
+        // (the seed pass has no survivor path and one bound per ROW to produce: it runs on 4 warps that take all
+        //  128 columns, so the 64 group minima of a row cover all its 1024 seed entries)
+        const int half = SEED ? 0 : (warp - 4) >> 2;   // which 64 of the 128 accumulator columns
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
-        constexpr int NG = TC_N / 64;              // 32-column groups per thread and chunk (2)
+        constexpr int NG = SEED ? TC_N / 32 : TC_N / 64;   // 32-column groups per thread and chunk
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -371,6 +373,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 const uint32_t acc = m & (TC_NACC - 1);
                 const int hs = m % TC_NH;
                 const float* hv = hv_s + hs * TC_N + half * 64;
+                // pick up the bound the query's rows in other lists / CTAs have published meanwhile (issued before
+                // the waits so that its latency is hidden behind them)
+                uint32_t thr_now = 0xFF800000u;
+                if (!SEED && row_ok) thr_now = *reinterpret_cast<volatile uint32_t*>(p.thr + q);
                 mbar_wait(&h_full[hs], (m / TC_NH) & 1);
                 mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
                 tc_fence_after();
@@ -380,8 +386,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_ld32_async(taddr + 32, rb);
                 tc_ld_wait(ra);   // (waits for both loads)
                 tc_ld_wait(rb);
+                if (!SEED && row_ok) {
+                    const float T = ordered_to_f32(thr_now);
+                    tq = fminf(tq, p.is_ip ? T : 0.5f * (T - qn));
+                }
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
+                    if (SEED && g == 2) {   // second half of the columns (no call is made in the seed pass)
+                        tc_ld32_async(taddr + 64, ra);
+                        tc_ld32_async(taddr + 96, rb);
+                        tc_ld_wait(ra);
+                        tc_ld_wait(rb);
+                    }
                     float t[32], m4[8];
                     const float mn = (g & 1) ? tc_diff32(rb, hv + g * 32, t, m4) : tc_diff32(ra, hv + g * 32, t, m4);
                     if (SEED) {
