@@ -97,6 +97,10 @@ int lira_search_dev(lira_index_t* h, const float* d_q, int64_t ldq, int64_t Q,
 int lira_model_create(const float* centroids, const float* scaler_mean, const float* scaler_scale,
                       int B, int d, const float* const weights[12], int device, lira_model_t** out);
 int lira_model_free(lira_model_t* m);
+/* The forward pass (centroid features + the six Linear layers) has two implementations: fp32 CUDA cores and
+ * tcgen05 tensor cores with error-compensated TF32 (every operand carried as an exact hi + lo pair, three MMAs
+ * per product: fp32-level accuracy). Default: tensor cores. 0 pins the CUDA-core kernels. */
+int lira_model_set_use_tensor_cores(lira_model_t* m, int enable);
 /* get_dist_cid + StandardScaler.transform (utils.py:98-118, 142-167) == compute_l2_to_centroids +
  * standardize_distances (search.cpp:220-250): out[Q,B] fp32. mean/scale NULL -> raw distances.
  * Always Euclidean, also for inner-product datasets (utils.py:115). */

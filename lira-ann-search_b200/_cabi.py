@@ -42,6 +42,7 @@ SIGNATURES = {
     "lira_search_dev": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "lira_model_create": (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, ctypes.POINTER(c_f32p), c_int, ctypes.POINTER(c_vp)]),
     "lira_model_free": (c_int, [c_vp]),
+    "lira_model_set_use_tensor_cores": (c_int, [c_vp, c_int]),
     "lira_centroid_features": (c_int, [c_f32p, c_i64, c_f32p, c_int, c_int, c_f32p, c_f32p, c_int, c_f32p]),
     "lira_model_scores": (c_int, [c_vp, c_f32p, c_i64, c_f32p, c_f32p]),
     "lira_probe_search": (c_int, [c_vp, c_vp, c_f32p, c_i64, c_int, ctypes.c_double, c_int, c_int, c_f32p, c_i64p, c_i32p, c_i64p]),

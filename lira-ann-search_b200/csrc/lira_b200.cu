@@ -15,6 +15,7 @@
 
 #include "probe_kernels.cuh"
 #include "tc_scan_kernels.cuh"
+#include "tc_dense_kernels.cuh"
 
 namespace lira {
 
@@ -151,6 +152,14 @@ struct lira_model {
     CUtensorMap tm_cent, tm_w[6];
     cudaStream_t stream = nullptr;
     DevBuf feats, h1, cat, h2, h5, scores, q;
+    // tensor-core front end (tc_dense_kernels.cuh): error-free hi / lo splits of the static operands ...
+    bool use_tc = true;
+    float *mu = nullptr, *cent_h = nullptr, *cent_l = nullptr, *cn = nullptr;   // centred centroids, |c'|^2
+    float* W_h[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* W_l[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CUtensorMap tm_ch, tm_cl, tm_wh[6], tm_wl[6];
+    // ... and of the activations of the current batch
+    DevBuf qch, qcl, qn, qrh, qrl, fh, fl, h1h, h1l, cath, catl, h2h, h2l, h5h, h5l;
 };
 
 namespace lira {
@@ -177,6 +186,9 @@ static int init_kernels(int device) {
     rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
+    rc |= set_smem(tc_dense_kernel<TD_EPI_FEATURE>, TD_SMEM_BYTES);
+    rc |= set_smem(tc_dense_kernel<TD_EPI_BIAS_RELU>, TD_SMEM_BYTES);
+    rc |= set_smem(tc_dense_kernel<TD_EPI_BIAS_SIGMOID>, TD_SMEM_BYTES);
     if (device < 64) done_dev[device] = (rc == 0);
     return rc;
 }
@@ -206,8 +218,8 @@ static int launch_dense(const CUtensorMap& tm, const DenseParams& p, cudaStream_
     return 0;
 }
 
-static int model_forward(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
-                         float* d_feats_out, cudaStream_t st) {
+static int model_forward_simt(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
+                              float* d_feats_out, long long ldf_out, cudaStream_t st) {
     LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
     const size_t Qs = (size_t)Q;
     if (int rc = m->feats.ensure(Qs * m->Bp * 4)) return rc;
@@ -216,8 +228,8 @@ static int model_forward(lira_model* m, const float* d_q, long long ldq, long lo
     if (int rc = m->h2.ensure(Qs * 128 * 4)) return rc;
     if (int rc = m->h5.ensure(Qs * 128 * 4)) return rc;
     float* feats = d_feats_out ? d_feats_out : m->feats.as<float>();
-    const long long ldf = d_feats_out ? m->B : m->Bp;
-    if (d_feats_out) LIRA_REQUIRE((m->B % 4) == 0, "feats output needs B % 4 == 0");
+    const long long ldf = d_feats_out ? ldf_out : m->Bp;
+    LIRA_REQUIRE((ldf % 4) == 0, "feats output needs a row stride that is a multiple of 4");
     DenseParams p;
     // K0: ||q - c_b||_2, standardised (utils.py:98-118,142-167; search.cpp:220-250)
     p = DenseParams{d_q, ldq, (int)Q, m->ds, m->B, feats, ldf, 0, m->mean, m->scale};
@@ -238,6 +250,77 @@ static int model_forward(lira_model* m, const float* d_q, long long ldq, long lo
     p = DenseParams{m->h5.as<float>(), 128, (int)Q, 128, m->B, d_scores, lds, 0, m->bias[5], nullptr};
     if (int rc = launch_dense<64, OP_DOT, EPI_BIAS_SIGMOID>(m->tm_w[5], p, st)) return rc;
     return 0;
+}
+
+// One layer on the tensor cores: out = epi(A . B^T), A and B given as hi / lo pairs (tc_dense_kernels.cuh).
+template <int EPI>
+static int launch_tc_dense(const float* a_h, const float* a_l, long long M, int K, long long lda, const CUtensorMap& tm_bh,
+                           const CUtensorMap& tm_bl, int N, const TdParams& tp, int num_sms, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    CUtensorMap tm_ah, tm_al;
+    if (int rc = make_tmap(&tm_ah, a_h, M, K, lda)) return rc;
+    if (int rc = make_tmap(&tm_al, a_l, M, K, lda)) return rc;
+    const long long tiles = ((M + TC_M - 1) / TC_M) * ((N + TC_N - 1) / TC_N);
+    const int grid = (int)std::min<long long>(tiles, num_sms);
+    tc_dense_kernel<EPI><<<grid, TD_THREADS, TD_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_bh, tm_bl, tp);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+static int model_forward_tc(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
+                            float* d_feats_out, long long ldf_out, cudaStream_t st) {
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0 && (lds % 4) == 0, "queries / scores must be 16-byte aligned with ld % 4 == 0");
+    LIRA_REQUIRE(!d_feats_out || (ldf_out % 4) == 0, "feats output needs a row stride that is a multiple of 4");
+    const size_t Qs = (size_t)Q;
+    const int ds = m->ds, B = m->B, Bp = m->Bp;
+    for (DevBuf* b : {&m->qch, &m->qcl, &m->qrh, &m->qrl})
+        if (int rc = b->ensure(Qs * ds * 4)) return rc;
+    if (int rc = m->qn.ensure(Qs * 4)) return rc;
+    for (DevBuf* b : {&m->fh, &m->fl})
+        if (int rc = b->ensure(Qs * Bp * 4)) return rc;
+    for (DevBuf* b : {&m->h1h, &m->h1l, &m->cath, &m->catl, &m->h2h, &m->h2l, &m->h5h, &m->h5l})
+        if (int rc = b->ensure(Qs * 128 * 4)) return rc;
+    static int num_sms = 0;
+    if (!num_sms) {
+        cudaDeviceProp prop;
+        LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, m->device));
+        num_sms = prop.multiProcessorCount;
+    }
+    const int warps = 8;
+    const int sgrid = (int)((Q + warps - 1) / warps);
+    // queries: centred split (+ |q'|^2) for the distance features, raw split for vector_net
+    split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, m->mu, m->qch.as<float>(), m->qcl.as<float>(), ds, m->qn.as<float>());
+    LIRA_LAUNCH_CHECK();
+    split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, nullptr, m->qrh.as<float>(), m->qrl.as<float>(), ds, nullptr);
+    LIRA_LAUNCH_CHECK();
+    TdParams tp;
+    // K0: ||q - c_b||_2, standardised (utils.py:98-118,142-167; search.cpp:220-250)
+    tp = TdParams{(int)Q, B, ds, m->fh.as<float>(), m->fl.as<float>(), d_feats_out, Bp, (long)ldf_out, 0,
+                  m->cn, m->mean, m->scale, m->qn.as<float>()};
+    if (int rc = launch_tc_dense<TD_EPI_FEATURE>(m->qch.as<float>(), m->qcl.as<float>(), Q, ds, ds, m->tm_ch, m->tm_cl, B, tp, num_sms, st)) return rc;
+    // distance_net (model_probing.py:12-17)
+    tp = TdParams{(int)Q, 128, B, m->h1h.as<float>(), m->h1l.as<float>(), nullptr, 128, 0, 0, m->bias[0], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->fh.as<float>(), m->fl.as<float>(), Q, B, Bp, m->tm_wh[0], m->tm_wl[0], 128, tp, num_sms, st)) return rc;
+    tp = TdParams{(int)Q, 64, 128, m->cath.as<float>(), m->catl.as<float>(), nullptr, 128, 0, 0, m->bias[1], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->h1h.as<float>(), m->h1l.as<float>(), Q, 128, 128, m->tm_wh[1], m->tm_wl[1], 64, tp, num_sms, st)) return rc;
+    // vector_net (model_probing.py:19-24)
+    tp = TdParams{(int)Q, 128, m->d, m->h2h.as<float>(), m->h2l.as<float>(), nullptr, 128, 0, 0, m->bias[2], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->qrh.as<float>(), m->qrl.as<float>(), Q, m->d, ds, m->tm_wh[2], m->tm_wl[2], 128, tp, num_sms, st)) return rc;
+    tp = TdParams{(int)Q, 64, 128, m->cath.as<float>(), m->catl.as<float>(), nullptr, 128, 0, 64, m->bias[3], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->h2h.as<float>(), m->h2l.as<float>(), Q, 128, 128, m->tm_wh[3], m->tm_wl[3], 64, tp, num_sms, st)) return rc;
+    // fc (model_probing.py:26-31): cat -> 128 -> B, sigmoid
+    tp = TdParams{(int)Q, 128, 128, m->h5h.as<float>(), m->h5l.as<float>(), nullptr, 128, 0, 0, m->bias[4], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->cath.as<float>(), m->catl.as<float>(), Q, 128, 128, m->tm_wh[4], m->tm_wl[4], 128, tp, num_sms, st)) return rc;
+    tp = TdParams{(int)Q, B, 128, nullptr, nullptr, d_scores, 0, (long)lds, 0, m->bias[5], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_SIGMOID>(m->h5h.as<float>(), m->h5l.as<float>(), Q, 128, 128, m->tm_wh[5], m->tm_wl[5], B, tp, num_sms, st)) return rc;
+    return 0;
+}
+
+static int model_forward(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
+                         float* d_feats_out, long long ldf_out, cudaStream_t st) {
+    if (Q <= 0) return 0;
+    if (m->use_tc) return model_forward_tc(m, d_q, ldq, Q, d_scores, lds, d_feats_out, ldf_out, st);
+    return model_forward_simt(m, d_q, ldq, Q, d_scores, lds, d_feats_out, ldf_out, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1024,9 +1107,57 @@ int lira_model_create(const float* centroids, const float* scaler_mean, const fl
             if ((rc = up(&m->bias[l], weights[2 * l + 1], 1, od[l], round_up(od[l], 4)))) break;
             rc = make_tmap(&m->tm_w[l], m->W[l], od[l], m->in_ld[l], m->in_ld[l]);
         }
+        if (rc) break;
+        // tensor-core front end: error-free hi / lo splits of the static operands (tc_dense_kernels.cuh)
+        auto split_up = [&](float** dh, float** dl, const std::vector<float>& x, int rows, int cols, int ld) -> int {
+            std::vector<float> hi(x.size()), lo(x.size());
+            for (size_t i = 0; i < x.size(); ++i) {
+                uint32_t b;
+                memcpy(&b, &x[i], 4);
+                b &= 0xFFFFE000u;
+                memcpy(&hi[i], &b, 4);
+                lo[i] = x[i] - hi[i];
+            }
+            if (int r = up(dh, hi.data(), rows, cols, ld)) return r;
+            return up(dl, lo.data(), rows, cols, ld);
+        };
+        {
+            // centre by the centroid mean (double accumulation), |c'|^2 in double
+            std::vector<double> mu(d, 0.0);
+            for (int b = 0; b < B; ++b)
+                for (int j = 0; j < d; ++j) mu[j] += centroids[(size_t)b * d + j];
+            std::vector<float> muf(d), cc((size_t)B * d), cn(B);
+            for (int j = 0; j < d; ++j) muf[j] = (float)(mu[j] / B);
+            for (int b = 0; b < B; ++b) {
+                double s = 0.0;
+                for (int j = 0; j < d; ++j) {
+                    const float v = centroids[(size_t)b * d + j] - muf[j];
+                    cc[(size_t)b * d + j] = v;
+                    s += (double)v * v;
+                }
+                cn[b] = (float)s;
+            }
+            if ((rc = up(&m->mu, muf.data(), 1, d, m->ds))) break;
+            if ((rc = up(&m->cn, cn.data(), 1, B, m->Bp))) break;
+            if ((rc = split_up(&m->cent_h, &m->cent_l, cc, B, d, m->ds))) break;
+            if ((rc = make_tmap(&m->tm_ch, m->cent_h, B, d, m->ds))) break;
+            if ((rc = make_tmap(&m->tm_cl, m->cent_l, B, d, m->ds))) break;
+        }
+        for (int l = 0; l < 6 && !rc; ++l) {
+            std::vector<float> w(weights[2 * l], weights[2 * l] + (size_t)od[l] * id[l]);
+            if ((rc = split_up(&m->W_h[l], &m->W_l[l], w, od[l], id[l], m->in_ld[l]))) break;
+            if ((rc = make_tmap(&m->tm_wh[l], m->W_h[l], od[l], id[l], m->in_ld[l]))) break;
+            rc = make_tmap(&m->tm_wl[l], m->W_l[l], od[l], id[l], m->in_ld[l]);
+        }
     } while (0);
     if (rc) { lira_model_free(m); return rc; }
     *out = m;
+    return 0;
+}
+
+int lira_model_set_use_tensor_cores(lira_model_t* m, int enable) {
+    LIRA_REQUIRE(m, "null model");
+    m->use_tc = enable != 0;
     return 0;
 }
 
@@ -1035,8 +1166,10 @@ int lira_model_free(lira_model_t* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     cudaFree(m->centroids); cudaFree(m->mean); cudaFree(m->scale);
-    for (int l = 0; l < 6; ++l) { cudaFree(m->W[l]); cudaFree(m->bias[l]); }
-    for (DevBuf* b : {&m->feats, &m->h1, &m->cat, &m->h2, &m->h5, &m->scores, &m->q}) b->release();
+    for (int l = 0; l < 6; ++l) { cudaFree(m->W[l]); cudaFree(m->bias[l]); cudaFree(m->W_h[l]); cudaFree(m->W_l[l]); }
+    cudaFree(m->mu); cudaFree(m->cent_h); cudaFree(m->cent_l); cudaFree(m->cn);
+    for (DevBuf* b : {&m->feats, &m->h1, &m->cat, &m->h2, &m->h5, &m->scores, &m->q, &m->qch, &m->qcl, &m->qn, &m->qrh, &m->qrl,
+                      &m->fh, &m->fl, &m->h1h, &m->h1l, &m->cath, &m->catl, &m->h2h, &m->h2l, &m->h5h, &m->h5l}) b->release();
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return 0;
@@ -1089,7 +1222,8 @@ int lira_model_scores(lira_model_t* m, const float* q, int64_t Q, float* scores,
         const long long nq = std::min<long long>(chunk, Q - q0);
         if (int rc = upload_rows(m->q, q + q0 * m->d, nq, m->d, m->ds, st)) return rc;
         if (int rc = m->scores.ensure((size_t)nq * m->Bp * 4)) return rc;
-        if (int rc = model_forward(m, m->q.as<float>(), m->ds, nq, m->scores.as<float>(), m->Bp, nullptr, st)) return rc;
+        if (int rc = m->feats.ensure((size_t)nq * m->Bp * 4)) return rc;
+        if (int rc = model_forward(m, m->q.as<float>(), m->ds, nq, m->scores.as<float>(), m->Bp, m->feats.as<float>(), m->Bp, st)) return rc;
         LIRA_CUDA_OK(cudaMemcpy2DAsync(scores + (size_t)q0 * m->B, (size_t)m->B * 4, m->scores.p, (size_t)m->Bp * 4,
                                        (size_t)m->B * 4, (size_t)nq, cudaMemcpyDeviceToHost, st));
         if (feats)
@@ -1119,7 +1253,7 @@ int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, in
     LIRA_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (int rc = h->ws.scores.ensure((size_t)std::max<int64_t>(Q, 1) * m->Bp * 4)) return rc;
-    if (int rc = model_forward(m, d_q, ldq, Q, h->ws.scores.as<float>(), m->Bp, nullptr, st)) return rc;
+    if (int rc = model_forward(m, d_q, ldq, Q, h->ws.scores.as<float>(), m->Bp, nullptr, 0, st)) return rc;
     return lira_select_search_dev(h, h->ws.scores.as<float>(), m->Bp, d_q, ldq, Q, mode, value, k, dedup, d_D, d_I,
                                   d_nprobe, d_cmp, st);
 }

@@ -278,6 +278,10 @@ class LiraModel:
             ws.append(sd[k + ".bias"].detach().float().cpu().numpy())
         return cls.from_arrays(centroids, scaler_mean, scaler_scale, ws, device)
 
+    def set_use_tensor_cores(self, enable=True):
+        """tcgen05 forward with error-compensated TF32 (default) or the fp32 CUDA-core kernels (False)."""
+        C.check(C.lib().lira_model_set_use_tensor_cores(self._h, int(bool(enable))))
+
     def scores(self, q, return_features=False):
         """all_outputs[Q,B] of model_evaluate / model_infer for raw queries (host arrays)."""
         q = C.f32(q).reshape(-1, self.dim)

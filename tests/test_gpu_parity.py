@@ -349,3 +349,41 @@ def test_tensor_core_query_phase_matches_cuda_cores(L, golden):
         b = index.probe_search(model, q, mode, value, k)
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, error-compensated TF32) forward of the probing model vs the fp32 CUDA-core kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["toy_l2", "toy_ip"])
+def test_model_tensor_core_forward_matches_cuda_cores(L, golden, case):
+    z = golden(case)
+    w = [z[f"mlp_{i}"] for i in range(12)]
+    model = L.LiraModel.from_arrays(z["centroids"], z["scaler_mean"], z["scaler_scale"], w)
+    q = np.tile(z["x_q"], (5, 1))[:301]  # not a multiple of the 128-row tile
+    model.set_use_tensor_cores(True)
+    s_tc, f_tc = model.scores(q, return_features=True)
+    model.set_use_tensor_cores(False)
+    s_cc, f_cc = model.scores(q, return_features=True)
+    # both are fp32-accurate evaluations of the same network: compare with the fp64 arbiter's tolerance
+    np.testing.assert_allclose(f_tc, f_cc, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(s_tc, s_cc, rtol=1e-4, atol=2e-6)
+    _, probs, _ = O.mlp_forward(O.features_cpp(q, z["centroids"], z["scaler_mean"], z["scaler_scale"]), q, w)
+    np.testing.assert_allclose(s_tc, probs, rtol=1e-4, atol=2e-6)
+
+
+def test_model_tensor_core_forward_large_offset_data(L):
+    """SIFT-like data far from the origin: the centred expansion must keep fp32-level feature accuracy."""
+    rng = np.random.RandomState(3)
+    B, d = 40, 128
+    x_d, x_q = synth(6000, d, 257, seed=12, integer=True)   # values 0..255, norms ~1e6
+    cent = x_d[rng.choice(len(x_d), B, replace=False)] + rng.rand(B, d).astype(np.float32)
+    f = O.features_cpp(x_d[:2000], cent)
+    mean, scale = f.mean(0).astype(np.float32), f.std(0).astype(np.float32)
+    shapes = [(128, B), (128,), (64, 128), (64,), (128, d), (128,), (64, 128), (64,), (128, 128), (128,), (B, 128), (B,)]
+    w = [(rng.randn(*s) * (0.02 if len(s) == 2 else 0.1)).astype(np.float32) for s in shapes]
+    model = L.LiraModel.from_arrays(cent, mean, scale, w)
+    s_tc, f_tc = model.scores(x_q, return_features=True)
+    f64 = O.features_py(x_q, cent, mean.astype(np.float64), scale.astype(np.float64))  # fp64 cdist arbiter
+    np.testing.assert_allclose(f_tc, f64, rtol=1e-5, atol=2e-5)
+    _, probs, _ = O.mlp_forward(f64, x_q, w)
+    np.testing.assert_allclose(s_tc, probs, rtol=1e-4, atol=2e-6)
