@@ -26,7 +26,7 @@ enum { TD_EPI_FEATURE = 0, TD_EPI_BIAS_RELU = 1, TD_EPI_BIAS_SIGMOID = 2 };
 static constexpr int TD_THREADS = 192;
 static constexpr int TD_NSTAGE = 3;
 static constexpr int TD_STAGE_BYTES = 4 * B_STAGE_BYTES;   // A_hi, A_lo, B_hi, B_lo: 128 rows x 128 B each
-static constexpr size_t TD_SMEM_BYTES = (size_t)TD_NSTAGE * TD_STAGE_BYTES + 3 * TC_N * 4 + 256;
+static constexpr size_t TD_SMEM_BYTES = (size_t)TD_NSTAGE * TD_STAGE_BYTES + 3 * TC_N * 4 + 4 * 32 * 33 * 4 + 256;
 
 struct TdParams {
     int M, N, K;             // out is M x N, reduction over K (zero-filled past the end by TMA)
@@ -51,7 +51,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* stages = smem_raw;
     float* vec_s = (float*)(stages + (size_t)TD_NSTAGE * TD_STAGE_BYTES);   // [3][128] per-column epilogue vectors
-    uint64_t* full = (uint64_t*)(vec_s + 3 * TC_N);   // [TD_NSTAGE]
+    float* tr_s = vec_s + 3 * TC_N;                   // [4 warps][32][33] transpose tiles of the epilogue
+    uint64_t* full = (uint64_t*)(tr_s + 4 * 32 * 33);   // [TD_NSTAGE]
     uint64_t* empty = full + TD_NSTAGE;               // [TD_NSTAGE]
     uint64_t* t_full = empty + TD_NSTAGE;             // [2]
     uint64_t* t_empty = t_full + 2;                   // [2]
@@ -126,6 +127,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int et = threadIdx.x - 64;   // 0..127
+        float* tr = tr_s + (warp - 2) * 32 * 33;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u;
@@ -145,9 +147,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
             }
             named_bar_sync(2, 128);
             const int m = m0 + row;
-            const bool row_ok = m < p.M;
             float rn = 0.0f;
-            if (EPI == TD_EPI_FEATURE && row_ok) rn = __ldg(p.rown + m);
+            if (EPI == TD_EPI_FEATURE && m < p.M) rn = __ldg(p.rown + m);
             mbar_wait(&t_full[acc], (it >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
@@ -156,46 +157,41 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                 uint32_t r[32];
                 tc_ld32_async(taddr + g * 32, r);
                 tc_ld_wait(r);
-                if (row_ok) {
+                float y[32];
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        float y[4];
+                for (int u = 0; u < 32; ++u) {
+                    const int c = g * 32 + u;
+                    const float a = __uint_as_float(r[u]);
+                    if (EPI == TD_EPI_FEATURE) {
+                        // utils.py:98-118 (Euclidean distance, with sqrt) + StandardScaler.transform (:142-167)
+                        const float d2 = fmaf(-2.0f, a, rn + vec_s[c]);
+                        float v = sqrtf(fmaxf(d2, 0.0f));
+                        if (p.v1) v = (v - vec_s[TC_N + c]) / vec_s[2 * TC_N + c];
+                        y[u] = v;
+                    } else if (EPI == TD_EPI_BIAS_RELU) {
+                        y[u] = fmaxf(a + vec_s[c], 0.0f);
+                    } else {
+                        y[u] = 1.0f / (1.0f + expf(-(a + vec_s[c])));
+                    }
+                }
+                // transpose the warp's 32 x 32 block through shared memory so that every store instruction writes
+                // 128 contiguous bytes of one output row (a thread owns a ROW in TMEM: direct stores would touch
+                // 32 rows per instruction, half a sector each)
+                __syncwarp();
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int c = g * 32 + c4 * 4 + u;
-                            const float a = __uint_as_float(r[c4 * 4 + u]);
-                            if (EPI == TD_EPI_FEATURE) {
-                                // utils.py:98-118 (Euclidean distance, with sqrt) + StandardScaler.transform (:142-167)
-                                float d2 = fmaf(-2.0f, a, rn + vec_s[c]);
-                                float v = sqrtf(fmaxf(d2, 0.0f));
-                                if (p.v1) v = (v - vec_s[TC_N + c]) / vec_s[2 * TC_N + c];
-                                y[u] = v;
-                            } else if (EPI == TD_EPI_BIAS_RELU) {
-                                y[u] = fmaxf(a + vec_s[c], 0.0f);
-                            } else {
-                                y[u] = 1.0f / (1.0f + expf(-(a + vec_s[c])));
-                            }
-                        }
-                        const int n = n0 + g * 32 + c4 * 4;
-                        if (n + 3 < p.N) {
-                            if (p.out) *reinterpret_cast<float4*>(p.out + (size_t)m * p.ldo_f + n) = make_float4(y[0], y[1], y[2], y[3]);
-                            if (p.out_hi) {
-                                float4 h = make_float4(tf32_hi(y[0]), tf32_hi(y[1]), tf32_hi(y[2]), tf32_hi(y[3]));
-                                *reinterpret_cast<float4*>(p.out_hi + (size_t)m * p.ldo + p.col_off + n) = h;
-                                *reinterpret_cast<float4*>(p.out_lo + (size_t)m * p.ldo + p.col_off + n) =
-                                    make_float4(y[0] - h.x, y[1] - h.y, y[2] - h.z, y[3] - h.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (n + u < p.N) {
-                                    if (p.out) p.out[(size_t)m * p.ldo_f + n + u] = y[u];
-                                    if (p.out_hi) {
-                                        const float h = tf32_hi(y[u]);
-                                        p.out_hi[(size_t)m * p.ldo + p.col_off + n + u] = h;
-                                        p.out_lo[(size_t)m * p.ldo + p.col_off + n + u] = y[u] - h;
-                                    }
-                                }
+                for (int u = 0; u < 32; ++u) tr[lane * 33 + u] = y[u];
+                __syncwarp();
+                const int n = n0 + g * 32 + lane;
+                if (n < p.N) {
+                    const int rows = min(32, p.M - (m0 + quad * 32));
+                    for (int rr = 0; rr < rows; ++rr) {
+                        const float v = tr[rr * 33 + lane];
+                        const size_t mm = (size_t)(m0 + quad * 32 + rr);
+                        if (p.out) p.out[mm * p.ldo_f + n] = v;
+                        if (p.out_hi) {
+                            const float h = tf32_hi(v);
+                            p.out_hi[mm * p.ldo + p.col_off + n] = h;
+                            p.out_lo[mm * p.ldo + p.col_off + n] = v - h;
                         }
                     }
                 }
