@@ -164,6 +164,16 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a CONVERGED warp (true for exactly one lane). Single-thread instructions (TMA, tcgen05.mma / commit)
+// are issued under it while the surrounding loop stays warp-uniform: operands computed in uniform code go straight to
+// uniform registers, whereas code under `if (lane == 0)` is divergent to the compiler and every such instruction is
+// then wrapped in a per-thread serialisation loop (measured: 4x on the MMA issue path).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

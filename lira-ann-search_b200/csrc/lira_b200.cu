@@ -77,6 +77,25 @@ static int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols
     return 0;
 }
 
+// rows x 8 fp32 matrix (32-byte rows): box = 128 rows x 8 floats, 32-byte swizzle (the augmented-K blocks).
+static int make_tmap_aug(CUtensorMap* m, const float* base, long long rows) {
+    PFN_encodeTiled enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    LIRA_REQUIRE(((uintptr_t)base & 31) == 0, "tensor map: augmented block must be 32-byte aligned");
+    cuuint64_t dims[2] = {8, (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t strides[1] = {32};
+    cuuint32_t box[2] = {8, (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (augmented block) failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // grow-only device buffers
 // ---------------------------------------------------------------------------------------------
@@ -103,11 +122,11 @@ struct DevBuf {
 
 struct Workspace {
     DevBuf q, sel, nsel, cmp, list_count, cursor, group_offsets, probe_offsets, group_queries, probe_slot, items,
-        n_items, part_key, D, I, scores, probe_ids, nprobe, top1, thr, gq, cand_key, cand_count, qnorm, flags, redo;
+        n_items, part_key, D, I, scores, probe_ids, nprobe, top1, thr, gq, cand_key, cand_count, qnorm, flags, redo, trace;
     void release() {
         for (DevBuf* b : {&q, &sel, &nsel, &cmp, &list_count, &cursor, &group_offsets, &probe_offsets, &group_queries,
                           &probe_slot, &items, &n_items, &part_key, &D, &I, &scores, &probe_ids, &nprobe, &top1, &thr, &gq,
-                          &cand_key, &cand_count, &qnorm, &flags, &redo})
+                          &cand_key, &cand_count, &qnorm, &flags, &redo, &trace})
             b->release();
     }
 };
@@ -129,7 +148,10 @@ struct lira_index {
     cudaStream_t stream = nullptr;
     Workspace ws, ws_seed;
     DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
-    float* vnorm = nullptr;      // |v|^2 / 2 per list entry (tensor-core path)
+    float* vnorm = nullptr;      // |v|^2 per list entry
+    float* vaug = nullptr;       // [E, 8] augmented-K block of every entry: (hi, lo, 0...) with |v|^2 = hi + lo (tensor-core path)
+    float* aaug = nullptr;       // [128, 8] constant augmented-K block of the query side: (-1, -1, 0...)
+    CUtensorMap tmap_vaug, tmap_aaug;
     bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
     bool use_tc = true;
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
@@ -564,7 +586,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
     int one_zero[2] = {1, 0};  // [0] query batch exactly representable, [1] number of overflowed queries
     LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 8, cudaMemcpyHostToDevice, st));
-    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), 1.0f);
+    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), nullptr);
     LIRA_LAUNCH_CHECK();
     long long P = 0;
     const long long* po = nullptr;
@@ -582,6 +604,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     }
     if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
     const int nk = (h->ds + KC - 1) / KC;
+    // L2: the gathered query rows carry the factor 2 of  s = 2 q.v - |v|^2  (exact: integers of <= 11 bits, doubled)
+    const float qscale = h->metric == LIRA_METRIC_IP ? 1.0f : 2.0f;
     Workspace& sw = h->ws_seed;
     if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
@@ -603,7 +627,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
         if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->ds * 4)) return rc;
         gather_group_queries_kernel<<<grid_for(Pseed * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(
-            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<float>());
+            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<float>(), qscale);
         LIRA_LAUNCH_CHECK();
         CUtensorMap tmap_sq;
         if (int rc = make_tmap(&tmap_sq, sw.gq.as<float>(), Pseed, h->ds, h->ds)) return rc;
@@ -615,15 +639,15 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.work_counter = sw.n_items.as<int>() + 1;
         sp.nk = nk;
         sp.max_rows = TC_SEED_ROWS_TC;
-        sp.vnorm = h->vnorm;
         sp.qnorm = ws.qnorm.as<float>();
         sp.thr = ws.thr.as<uint32_t>();
         sp.cand_key = nullptr;
         sp.cand_count = nullptr;
         sp.cap = 0;
+        sp.trace = nullptr;
         sp.k = k;
         sp.is_ip = h->metric == LIRA_METRIC_IP;
-        tc_scan_kernel<true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap, sp);
+        tc_scan_kernel<true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap, h->tmap_vaug, h->tmap_aaug, sp);
         LIRA_LAUNCH_CHECK();
     } else {
         // ---- seed on the CUDA cores (k > 16): exact scan of the first rows of the two best lists ----
@@ -646,7 +670,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // ---- queries in group order (one TMA box per tile) ----
     if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->ds * 4)) return rc;
     gather_group_queries_kernel<<<grid_for(P * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                        ws.group_offsets.as<long long>() + h->B, ws.gq.as<float>());
+                                                                                        ws.group_offsets.as<long long>() + h->B, ws.gq.as<float>(), qscale);
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
     if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
@@ -662,7 +686,6 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.work_counter = ws.n_items.as<int>() + 1;
     tp.nk = nk;
     tp.max_rows = 0;
-    tp.vnorm = h->vnorm;
     tp.qnorm = ws.qnorm.as<float>();
     tp.thr = ws.thr.as<uint32_t>();
     tp.cand_key = ws.cand_key.as<unsigned long long>();
@@ -670,8 +693,15 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.cap = TC_CAPP;
     tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
+    tp.trace = nullptr;
+    const char* trace_path = getenv("LIRA_TC_TRACE");   // debug: per-chunk clock stamps of CTA 0 -> CSV
+    if (trace_path) {
+        if (int rc = ws.trace.ensure((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS * 8)) return rc;
+        LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS * 8, st));
+        tp.trace = ws.trace.as<long long>();
+    }
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    tc_scan_kernel<false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, tp);
+    tc_scan_kernel<false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, h->tmap_vaug, h->tmap_aaug, tp);
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
@@ -683,6 +713,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_LAUNCH_CHECK();
     LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    if (trace_path) {
+        std::vector<long long> tr((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS);
+        cudaMemcpy(tr.data(), ws.trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "chunk,prod_start,mma_acc_free,mma_b0,mma_blast,mma_issued,epi4_ready,epi4_done,epi8_ready,epi8_done\n");
+            for (int c = 0; c < TC_TRACE_CHUNKS; ++c) {
+                fprintf(f, "%d", c);
+                for (int r = 0; r < TC_TRACE_ROLES; ++r) fprintf(f, ",%lld", tr[(size_t)r * TC_TRACE_CHUNKS + c]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (getenv("LIRA_DEBUG")) {
         std::vector<int> cc((size_t)P * 2);
         cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * 2 * 4, cudaMemcpyDeviceToHost);
@@ -790,8 +833,17 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     LIRA_CUDA_OK(cudaMalloc(&d_flag, 4));
     int one = 1;
     LIRA_CUDA_OK(cudaMemcpy(d_flag, &one, 4, cudaMemcpyHostToDevice));
+    LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)std::max<long long>(h->E, 1) * 32));
+    LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
+    {
+        std::vector<float> a(128 * 8, 0.0f);
+        for (int r = 0; r < 128; ++r) a[r * 8] = a[r * 8 + 1] = -1.0f;
+        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
+    if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
     if (h->E > 0) {
-        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, 0.5f);
+        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, h->vaug);
         g_launches.fetch_add(1);
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -929,6 +981,8 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->d_offsets);
     cudaFree(h->d_list_order);
     cudaFree(h->vnorm);
+    cudaFree(h->vaug);
+    cudaFree(h->aaug);
     h->ws.release();
     h->ws_seed.release();
     h->stats.release();

@@ -80,36 +80,40 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     const int nk = (p.K + KC - 1) / KC;
 
     if (warp == 0) {
-        if (lane == 0) {
-            PipeState ps{0, 0};
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m0 = (t / tiles_n) * TC_M, n0 = (t % tiles_n) * TC_N;   // consecutive CTAs share the A rows
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
-                    uint8_t* s = stages + (size_t)ps.stage * TD_STAGE_BYTES;
+        // TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one)
+        PipeState ps{0, 0};
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m0 = (t / tiles_n) * TC_M, n0 = (t % tiles_n) * TC_N;   // consecutive CTAs share the A rows
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
+                uint8_t* s = stages + (size_t)ps.stage * TD_STAGE_BYTES;
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full[ps.stage], TD_STAGE_BYTES);
                     tma_load_2d(s, &tm_ah, kb * KC, m0, &full[ps.stage]);
                     tma_load_2d(s + B_STAGE_BYTES, &tm_al, kb * KC, m0, &full[ps.stage]);
                     tma_load_2d(s + 2 * B_STAGE_BYTES, &tm_bh, kb * KC, n0, &full[ps.stage]);
                     tma_load_2d(s + 3 * B_STAGE_BYTES, &tm_bl, kb * KC, n0, &full[ps.stage]);
-                    ps.advance(TD_NSTAGE);
                 }
+                __syncwarp();
+                ps.advance(TD_NSTAGE);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            PipeState ps{0, 0};
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const uint32_t acc = it & 1u;
-                mbar_wait(&t_empty[acc], ((it >> 1) & 1u) ^ 1u);
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        PipeState ps{0, 0};
+        uint32_t it = 0;
+        const uint32_t stages_u32 = smem_u32(stages);
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u;
+            mbar_wait(&t_empty[acc], ((it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * TC_N;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&full[ps.stage], ps.phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TC_N;
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&full[ps.stage], ps.phase);
-                    tc_fence_after();
-                    const uint32_t s = smem_u32(stages + (size_t)ps.stage * TD_STAGE_BYTES);
-                    const uint32_t ah = s, al = s + B_STAGE_BYTES, bh = s + 2 * B_STAGE_BYTES, bl = s + 3 * B_STAGE_BYTES;
+                const uint32_t s = stages_u32 + (uint32_t)ps.stage * TD_STAGE_BYTES;
+                const uint32_t ah = s, al = s + B_STAGE_BYTES, bh = s + 2 * B_STAGE_BYTES, bl = s + 3 * B_STAGE_BYTES;
+                if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {   // small terms first, then the leading one
                         tc_mma_tf32(d_tmem, tc_smem_desc(al + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC, (kb | j) ? 1u : 0u);
@@ -117,10 +121,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                         tc_mma_tf32(d_tmem, tc_smem_desc(ah + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC, 1u);
                     }
                     tc_commit(&empty[ps.stage]);
-                    ps.advance(TD_NSTAGE);
                 }
-                tc_commit(&t_full[acc]);
+                __syncwarp();
+                ps.advance(TD_NSTAGE);
             }
+            if (elect_one()) tc_commit(&t_full[acc]);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warps 2..5 -> TMEM lane quadrants 2, 3, 0, 1 =====

@@ -25,19 +25,26 @@ namespace lira {
 static constexpr int TC_M = 128;         // queries per tile (UMMA M, TMEM lanes)
 static constexpr int TC_N = 128;         // vectors per chunk (UMMA N, TMEM columns per accumulator)
 static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128 = 512 columns)
-static constexpr int TC_NSTAGE = 6;      // B ring stages (16 KiB each)
+static constexpr int TC_NSLOT = 4;       // B ring slots; a slot = up to TC_SLOT_KB K blocks of one chunk (32 KiB) + its augmented-K box
+static constexpr int TC_SLOT_KB = 2;     //   (one barrier round trip per 8-9 MMAs instead of per 4)
+static constexpr int TC_NABUF = 1;       // A tile buffers (64 KiB each)
 static constexpr int TC_MAX_KB = 4;      // K blocks of 32 floats resident per A tile: d <= 128
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
-static constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc + norm loader, warps 4-11 epilogue
-static constexpr int TC_EPI_WARPS = 8;    // two per TMEM lane quadrant, each takes half of the 128 accumulator columns
+static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 8 floats
+static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * B_STAGE_BYTES + TC_AUG_BYTES;   // 36 KiB
+static constexpr int TC_THREADS = 384;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer, warp 10 TMEM alloc
+static constexpr int TC_W_PROD = 8, TC_W_MMA = 9, TC_W_ALLOC = 10;
+static constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant, each takes half of the 128 accumulator columns
 
 static constexpr int TC_CB = 16;         // a row's best survivors kept in a sorted register chain (k <= 16)
 static constexpr int TC_CAPP = 64;       // candidate slots per (query, list) pair and column half (16 used when k <= 16)
 
-static constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES   // A, double buffered
-                                        + (size_t)TC_NSTAGE * B_STAGE_BYTES     // B ring
-                                        + (size_t)4 * TC_N * 4                  // |v|^2 / 2 per column (TC_NH slots)
-                                        + 512;                                  // barriers, item queue, tmem slot
+static constexpr size_t TC_SMEM_BYTES = (size_t)TC_NABUF * TC_MAX_KB * TC_KBLK_BYTES   // A tile
+                                        + (size_t)TC_NSLOT * TC_SLOT_BYTES              // B ring
+                                        + (size_t)TC_AUG_BYTES                          // the constant augmented-K block of A
+                                        + 512;                                          // barriers, item queue, tmem slot
+
+static constexpr int TC_TRACE_ROLES = 9, TC_TRACE_CHUNKS = 512;
 
 struct TcParams {
     const int* group_queries;        // [P] query id per slot
@@ -47,7 +54,6 @@ struct TcParams {
     int* work_counter;               // zeroed before launch: dynamic item scheduler
     int nk;                          // K blocks (ceil(d / 32)), <= TC_MAX_KB
     int max_rows;                    // > 0: only the first max_rows entries of each list (seed pass)
-    const float* vnorm;              // [E] |v|^2 / 2 (fp32, sequential order)
     const float* qnorm;              // [Q] |q|^2
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
                                      //     seed pass, read AND tightened (atomicMin) by the filter pass
@@ -56,6 +62,7 @@ struct TcParams {
     int cap;
     int k;
     int is_ip;
+    long long* trace;                // debug (LIRA_TC_TRACE): [TC_TRACE_ROLES][TC_TRACE_CHUNKS] SM clock stamps of CTA 0, or null
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------
@@ -74,6 +81,10 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
 // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// K-major, 32-byte swizzle: rows of 32 B (one K = 8 TF32 step), 8-row groups 256 B apart (SBO)
+__device__ __forceinline__ uint64_t tc_smem_desc_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
 // asynchronous TMEM -> register load of 32 consecutive columns of this thread's lane; pair with tc_ld_wait()
 __device__ __forceinline__ void tc_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
@@ -102,10 +113,9 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
 static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / norm loader / epilogue)
-static constexpr int TC_NH = 4;   // |v|^2/2 ring depth
+static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / epilogue)
 static constexpr int TC_G = 64;   // seed pass: group minima per row
-static constexpr int TC_KMAX_TIGHTEN = 16;  // in-kernel threshold tightening (and the tensor-core seed) need k <= 16
+static constexpr int TC_KMAX_TIGHTEN = 16;  // in-kernel bound tightening (and the tensor-core seed) need k <= 16
 
 // ---- small static sorting networks (registers only; every index is a compile-time constant) --------
 __device__ __forceinline__ void tc_sort16(float (&v)[16]) {  // bitonic, ascending
@@ -147,59 +157,54 @@ __device__ __forceinline__ float tc_pick16(const float (&v)[16], int idx) {
     return r;
 }
 
-// t[c] = hv[c] - r[c] for 32 columns of this thread's row, m4[i] = min of columns 4i..4i+3; returns the minimum of
-// all 32 (NaN padding is ignored by fminf).
-//   t = |v|^2/2 - q.v  (L2; score = |q|^2 + 2 t)      t = -q.v (IP; score = t)
-__device__ __forceinline__ float tc_diff32(const uint32_t (&r)[32], const float* hv, float (&t)[32], float (&m4)[8]) {
+// The accumulator holds  s = 2 q.v - |v|^2  (L2; the -|v|^2 term comes from the augmented K block, the factor 2
+// from the gathered query rows) or s = q.v (IP): LARGER is better, and the score is |q|^2 - s resp. -s.
+// m4[i] = max of columns 4i..4i+3; returns the maximum of all 32.
+__device__ __forceinline__ float tc_max32(const uint32_t (&r)[32], float (&m4)[8]) {
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 h = *reinterpret_cast<const float4*>(hv + c4 * 4);
-        t[c4 * 4 + 0] = h.x - __uint_as_float(r[c4 * 4 + 0]);
-        t[c4 * 4 + 1] = h.y - __uint_as_float(r[c4 * 4 + 1]);
-        t[c4 * 4 + 2] = h.z - __uint_as_float(r[c4 * 4 + 2]);
-        t[c4 * 4 + 3] = h.w - __uint_as_float(r[c4 * 4 + 3]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m4[i] = fminf(fminf(t[4 * i], t[4 * i + 1]), fminf(t[4 * i + 2], t[4 * i + 3]));
-    return fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+    for (int i = 0; i < 8; ++i)
+        m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                      fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+    return fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
 }
 
 template <bool SEED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
+               const __grid_constant__ CUtensorMap tmap_vaug, const __grid_constant__ CUtensorMap tmap_aaug, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    uint8_t* sA = smem_raw;                                              // [2][TC_MAX_KB][128 x 128 B]
-    uint8_t* sB = sA + (size_t)2 * TC_MAX_KB * TC_KBLK_BYTES;            // [TC_NSTAGE][128 x 128 B]
-    float* hv_s = (float*)(sB + (size_t)TC_NSTAGE * B_STAGE_BYTES);      // [TC_NH][128]
-    uint64_t* bars = (uint64_t*)(hv_s + TC_NH * TC_N);
+    uint8_t* sA = smem_raw;                                              // [TC_NABUF][TC_MAX_KB][128 x 128 B]
+    uint8_t* sB = sA + (size_t)TC_NABUF * TC_MAX_KB * TC_KBLK_BYTES;     // [TC_NSLOT]{[TC_SLOT_KB][128 x 128 B], [128 x 32 B] aug}
+    uint8_t* sGA = sB + (size_t)TC_NSLOT * TC_SLOT_BYTES;                // [128 x 32 B] constant augmented-K block of A
+    uint64_t* bars = (uint64_t*)(sGA + TC_AUG_BYTES);
     uint64_t* a_full = bars;                        // [2]
     uint64_t* a_empty = a_full + 2;                 // [2]
-    uint64_t* b_full = a_empty + 2;                 // [TC_NSTAGE]
-    uint64_t* b_empty = b_full + TC_NSTAGE;         // [TC_NSTAGE]
-    uint64_t* t_full = b_empty + TC_NSTAGE;         // [TC_NACC]
+    uint64_t* b_full = a_empty + 2;                 // [TC_NSLOT]
+    uint64_t* b_empty = b_full + TC_NSLOT;          // [TC_NSLOT]
+    uint64_t* t_full = b_empty + TC_NSLOT;          // [TC_NACC]
     uint64_t* t_empty = t_full + TC_NACC;           // [TC_NACC]
-    uint64_t* h_full = t_empty + TC_NACC;           // [TC_NH]
-    uint64_t* h_empty = h_full + TC_NH;             // [TC_NH]
-    uint64_t* i_full = h_empty + TC_NH;             // [TC_NQ]
+    uint64_t* i_full = t_empty + TC_NACC;           // [TC_NQ]
     uint64_t* i_empty = i_full + TC_NQ;             // [TC_NQ]
-    ScanItem* iq = (ScanItem*)(i_empty + TC_NQ);    // [TC_NQ]
+    uint64_t* ga_full = i_empty + TC_NQ;            // [1]
+    ScanItem* iq = (ScanItem*)(ga_full + 1);        // [TC_NQ]
     uint32_t* tmem_slot = (uint32_t*)(iq + TC_NQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool aug = !p.is_ip;   // inner product: the accumulator is q.v itself, no augmented block
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SEED ? 4 : TC_EPI_WARPS); }
-        for (int i = 0; i < TC_NH; ++i) { mbar_init(&h_full[i], 32); mbar_init(&h_empty[i], SEED ? 4 : TC_EPI_WARPS); }  // every loader lane arrives
-        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + (SEED ? 4 : TC_EPI_WARPS)); }  // MMA + loader + epilogue warps
+        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 1 + (SEED ? 4 : TC_EPI_WARPS)); }  // MMA + epilogue warps
+        mbar_init(ga_full, 1);
         mbar_fence_init();
     }
-    if (warp == 2) {
+    if (warp == TC_W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x == 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); }
+    if (threadIdx.x == TC_W_PROD * 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_vaug); tma_prefetch_desc(&tmap_aaug); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -213,78 +218,69 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         hi = p.list_offsets[it.list + 1];
         if (p.max_rows > 0 && hi - lo > p.max_rows) hi = lo + p.max_rows;
     };
+    // debug timeline of CTA 0: one clock stamp per (role, chunk)
+    auto stamp = [&](int role, uint32_t chunk) {
+        if (p.trace && blockIdx.x == 0 && chunk < TC_TRACE_CHUNKS && lane == 0) p.trace[role * TC_TRACE_CHUNKS + chunk] = clock64();
+    };
 
-    if (warp == 0) {
-        // ===== scheduler + TMA producer (one elected lane) =====
-        if (lane == 0) {
-            PipeState bs{0, 0};
-            for (int n = 0;; ++n) {
-                const int idx = atomicAdd(p.work_counter, 1);
-                ScanItem it;
-                if (idx < n_items) it = p.items[idx];
-                else { it.list = -1; it.q_begin = 0; it.q_count = 0; it.tm = 0; }
-                const int qs = n % TC_NQ;
-                mbar_wait(&i_empty[qs], ((n / TC_NQ) & 1) ^ 1u);
-                iq[qs] = it;
-                mbar_arrive(&i_full[qs]);
-                if (it.list < 0) break;
-                const int ab = n & 1;
-                mbar_wait(&a_empty[ab], ((n >> 1) & 1) ^ 1u);
+    if (warp == TC_W_PROD) {
+        // ===== scheduler + TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one) =====
+        if (aug) {   // the constant augmented-K block of A: every row is (-1, -1, 0, ..., 0)
+            if (elect_one()) {
+                mbar_arrive_expect_tx(ga_full, TC_AUG_BYTES);
+                tma_load_2d(sGA, &tmap_aaug, 0, 0, ga_full);
+            }
+            __syncwarp();
+        }
+        PipeState bs{0, 0};
+        uint32_t mp = 0;
+        for (int n = 0;; ++n) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(p.work_counter, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            ScanItem it;
+            if (idx < n_items) it = p.items[idx];
+            else { it.list = -1; it.q_begin = 0; it.q_count = 0; it.tm = 0; }
+            const int qs = n % TC_NQ;
+            mbar_wait(&i_empty[qs], ((n / TC_NQ) & 1) ^ 1u);
+            if (lane == 0) { iq[qs] = it; mbar_arrive(&i_full[qs]); }
+            __syncwarp();
+            if (it.list < 0) break;
+            const int ab = n % TC_NABUF;
+            mbar_wait(&a_empty[ab], ((n / TC_NABUF) & 1) ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
                 for (int kb = 0; kb < nk; ++kb)
                     tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * KC, it.q_begin, &a_full[ab]);
-                long long lo, hi;
-                item_rows(it, lo, hi);
-                for (long long row0 = lo; row0 < hi; row0 += TC_N)
-                    for (int kb = 0; kb < nk; ++kb) {
-                        mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
-                        mbar_arrive_expect_tx(&b_full[bs.stage], B_STAGE_BYTES);
-                        tma_load_2d(sB + (size_t)bs.stage * B_STAGE_BYTES, &tmap_v, kb * KC, (int)row0, &b_full[bs.stage]);
-                        bs.advance(TC_NSTAGE);
-                    }
             }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one elected lane) =====
-        if (lane == 0) {
-            PipeState bs{0, 0};
-            uint32_t m = 0;  // running chunk counter -> accumulator slot and phase
-            for (int n = 0;; ++n) {
-                const int qs = n % TC_NQ;
-                mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
-                const ScanItem it = iq[qs];
-                mbar_arrive(&i_empty[qs]);
-                if (it.list < 0) break;
-                const int ab = n & 1;
-                mbar_wait(&a_full[ab], (n >> 1) & 1);
-                tc_fence_after();
-                long long lo, hi;
-                item_rows(it, lo, hi);
-                for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
-                    const uint32_t acc = m & (TC_NACC - 1);
-                    mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * TC_N;
-                    for (int kb = 0; kb < nk; ++kb) {
-                        mbar_wait(&b_full[bs.stage], bs.phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES);
-                        const uint32_t b_addr = smem_u32(sB + (size_t)bs.stage * B_STAGE_BYTES);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)  // 4 x K = 8 tf32 (32 bytes) inside the 128-byte swizzle row
-                            tc_mma_tf32(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC,
-                                        (kb | j) ? 1u : 0u);
-                        tc_commit(&b_empty[bs.stage]);  // frees the B stage when these MMAs have read it
-                        bs.advance(TC_NSTAGE);
+            __syncwarp();
+            long long lo, hi;
+            item_rows(it, lo, hi);
+            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++mp) {
+                stamp(0, mp);
+                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug box with the first)
+                    const int nkb = min(TC_SLOT_KB, nk - kb0);
+                    const bool with_aug = aug && kb0 == 0;
+                    mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
+                    if (elect_one()) {
+                        uint8_t* slot = sB + (size_t)bs.stage * TC_SLOT_BYTES;
+                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nkb * B_STAGE_BYTES + (with_aug ? TC_AUG_BYTES : 0));
+                        for (int j = 0; j < nkb; ++j)
+                            tma_load_2d(slot + (size_t)j * B_STAGE_BYTES, &tmap_v, (kb0 + j) * KC, (int)row0, &b_full[bs.stage]);
+                        if (with_aug) tma_load_2d(slot + TC_SLOT_KB * B_STAGE_BYTES, &tmap_vaug, 0, (int)row0, &b_full[bs.stage]);
                     }
-                    tc_commit(&t_full[acc]);            // accumulator complete -> epilogue
+                    __syncwarp();
+                    bs.advance(TC_NSLOT);
                 }
-                tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
             }
         }
-    } else if (warp == 2) {
-        // ===== |v|^2/2 loader: keeps the epilogue off the global-memory latency path =====
-        uint32_t m = 0;
+    } else if (warp == TC_W_MMA) {
+        // ===== MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====
+        PipeState bs{0, 0};
+        uint32_t m = 0;  // running chunk counter -> accumulator slot and phase
+        if (aug) { mbar_wait(ga_full, 0); tc_fence_after(); }
+        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+        const uint64_t ga_desc = tc_smem_desc_sw32(smem_u32(sGA));
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
             mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
@@ -292,49 +288,67 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&i_empty[qs]);
             if (it.list < 0) break;
+            const int ab = n % TC_NABUF;
+            mbar_wait(&a_full[ab], (n / TC_NABUF) & 1);
+            tc_fence_after();
             long long lo, hi;
             item_rows(it, lo, hi);
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
-                const int hs = m % TC_NH;
-                mbar_wait(&h_empty[hs], ((m / TC_NH) & 1) ^ 1u);
-                float* dst = hv_s + hs * TC_N;
-                if (!p.is_ip && row0 + TC_N <= hi) {
-                    // full chunk: asynchronous copies, the barrier is signalled by the copy engine, and the warp
-                    // moves on to the next chunk at once (TC_NH chunks of norms in flight)
+                const uint32_t acc = m & (TC_NACC - 1);
+                mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
+                tc_fence_after();
+                stamp(1, m);
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {
+                    const int nkb = min(TC_SLOT_KB, nk - kb0);
+                    mbar_wait(&b_full[bs.stage], bs.phase);
+                    tc_fence_after();
+                    if (kb0 == 0) stamp(2, m);
+                    if (kb0 + TC_SLOT_KB >= nk) stamp(3, m);
+                    const uint32_t slot = sB_u32 + (uint32_t)bs.stage * TC_SLOT_BYTES;
+                    if (elect_one()) {
+                        if (aug && kb0 == 0)   // s = -|v|^2 ...
+                            tc_mma_tf32(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * B_STAGE_BYTES), TC_IDESC, 0u);
+                        for (int jb = 0; jb < nkb; ++jb) {   // ... + (2 q) . v
+                            const uint32_t a_addr = sA_u32 + (uint32_t)(ab * TC_MAX_KB + kb0 + jb) * TC_KBLK_BYTES;
+                            const uint32_t b_addr = slot + (uint32_t)jb * B_STAGE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < TC_N / 32; ++j)
-                        cp_async_4(smem_u32(dst + lane + 32 * j), p.vnorm + row0 + lane + 32 * j);
-                    cp_async_mbar_arrive_noinc(&h_full[hs]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < TC_N / 32; ++j) {
-                        const long long e = row0 + lane + 32 * j;
-                        // past the end of the list: NaN, so that neither `t <= tq` (even for tq = +inf) nor fminf picks it
-                        float h = __int_as_float(0x7fc00000);
-                        if (e < hi) h = p.is_ip ? 0.0f : __ldg(p.vnorm + e);
-                        dst[lane + 32 * j] = h;
+                            for (int j = 0; j < 4; ++j)  // 4 x K = 8 tf32 (32 bytes) inside the 128-byte swizzle row
+                                tc_mma_tf32(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC,
+                                            (aug || kb0 || jb || j) ? 1u : 0u);
+                        }
+                        tc_commit(&b_empty[bs.stage]);  // frees the slot when these MMAs have read it
                     }
-                    mbar_arrive(&h_full[hs]);
+                    __syncwarp();
+                    bs.advance(TC_NSLOT);
                 }
+                if (elect_one()) tc_commit(&t_full[acc]);            // accumulator complete -> epilogue
+                __syncwarp();
+                stamp(4, m);
             }
+            if (elect_one()) tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
+            __syncwarp();
         }
-    } else if (warp >= 4 && (!SEED || warp < 8)) {
+    } else if (warp < (SEED ? 4 : TC_EPI_WARPS)) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
         // Two warps per TMEM lane quadrant: a thread owns one query row and one half (64 columns) of every
-        // accumulator of the work item. Filter: the hot loop forms t = |v|^2/2 - q.v and a 3-input-min tree per 32
-        // columns (FADD + FMNMX3, no divergence). About one pair in a thousand survives, i.e. roughly every other
-        // 32-column group of a warp holds one, so the survivor path is straight-line too: a lane picks its first
-        // passing 4-column block with a select tree (no dynamic register indexing) and appends the block's
-        // passing entries to the PRIVATE candidate region of its (query, list, half) -- plain stores, no atomics,
-        // no shared staging. The last 16 survivors' t stay in a register shift chain; every 16th survivor their
-        // k-th smallest TIGHTENS the row's bound and is published (atomicMin) for the query's rows in other lists
-        // and CTAs, so heavy-tailed rows cost O(k log n) survivors, not O(n).
-        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        // accumulator of the work item. With t = -s (t = score - |q|^2 for L2, t = score for IP; smaller is
+        // better) the filter keeps t <= tq. The hot loop is a 3-input-max tree over the raw accumulator values and
+        // ONE compare per 32 columns (FMNMX3 only: the norms are already inside the accumulator). About one pair in
+        // a thousand survives, i.e. a good part of a warp's 32-column groups hold one, so the survivor path is
+        // straight-line too: a lane picks its first passing 4-column block with a select tree (no dynamic
+        // register indexing) and inserts the passing entries into its SORTED 16-entry register chain (the exact
+        // running top-16 of its (query, list, half)); the chain's k-th element tightens the row's bound at once
+        // and is published (atomicMin) for the query's rows in other lists and CTAs, which re-read it every chunk.
+        // At the end of the item the chain goes to the thread's PRIVATE candidate region: plain stores, no
+        // atomics, no shared staging.
         // (the seed pass has no survivor path and one bound per ROW to produce: it runs on 4 warps that take all
         //  128 columns, so the 64 group minima of a row cover all its 1024 seed entries)
-        const int half = SEED ? 0 : (warp - 4) >> 2;   // which 64 of the 128 accumulator columns
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = SEED ? 0 : warp >> 2;     // which 64 of the 128 accumulator columns
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
         constexpr int NG = SEED ? TC_N / 32 : TC_N / 64;   // 32-column groups per thread and chunk
+        constexpr int NCOL = SEED ? TC_N : TC_N / 2;       // columns per thread and chunk
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -363,7 +377,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 if (!p.is_ip) qn = __ldg(p.qnorm + q);
                 if (!SEED) {
                     const float T = ordered_to_f32(*reinterpret_cast<volatile uint32_t*>(p.thr + q));
-                    tq = p.is_ip ? T : 0.5f * (T - qn);   // score <= T  <=>  t <= tq
+                    tq = T - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
                     cand = p.cand_key + ((size_t)(it.q_begin + row) * 2 + half) * p.cap;
                 }
             }
@@ -371,25 +385,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             item_rows(it, lo, hi);
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
-                const int hs = m % TC_NH;
-                const float* hv = hv_s + hs * TC_N + half * 64;
                 // pick up the bound the query's rows in other lists / CTAs have published meanwhile (issued before
-                // the waits so that its latency is hidden behind them)
+                // the wait so that its latency is hidden behind it)
                 uint32_t thr_now = 0xFF800000u;
                 if (!SEED && row_ok) thr_now = *reinterpret_cast<volatile uint32_t*>(p.thr + q);
-                mbar_wait(&h_full[hs], (m / TC_NH) & 1);
                 mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
                 tc_fence_after();
+                if (warp == 0) stamp(5, m);
+                if (warp == 5) stamp(7, m);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N + half * 64;
                 uint32_t ra[32], rb[32];
                 tc_ld32_async(taddr, ra);
                 tc_ld32_async(taddr + 32, rb);
                 tc_ld_wait(ra);   // (waits for both loads)
                 tc_ld_wait(rb);
-                if (!SEED && row_ok) {
-                    const float T = ordered_to_f32(thr_now);
-                    tq = fminf(tq, p.is_ip ? T : 0.5f * (T - qn));
-                }
+                if (!SEED && row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
+                // columns past the end of the list hold other lists' vectors: valid columns of this thread's range
+                const int n_valid = (int)min((long long)NCOL, hi - row0 - half * 64);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     if (SEED && g == 2) {   // second half of the columns (no call is made in the seed pass)
@@ -398,26 +410,33 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         tc_ld_wait(ra);
                         tc_ld_wait(rb);
                     }
-                    float t[32], m4[8];
-                    const float mn = (g & 1) ? tc_diff32(rb, hv + g * 32, t, m4) : tc_diff32(ra, hv + g * 32, t, m4);
+                    uint32_t (&r)[32] = (g & 1) ? rb : ra;
+                    if (n_valid < (g + 1) * 32) {   // partial group (only the last chunk of a list): mask the tail
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (g * 32 + c >= n_valid) r[c] = 0xFF800000u;   // -inf: never the maximum, never passes
+                    }
+                    float m4[8];
+                    const float mx = tc_max32(r, m4);
                     if (SEED) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], t[c]);
-                    } else if (__any_sync(0xffffffffu, mn <= tq)) {
+                        for (int c = 0; c < 32; ++c)
+                            gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], -__uint_as_float(r[c]));
+                    } else if (__any_sync(0xffffffffu, -mx <= tq)) {
                         // (tq = -inf for rows past the end of the tile, so they never pass)
                         uint32_t qm = 0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) qm |= (m4[i] <= tq) ? (1u << i) : 0u;
+                        for (int i = 0; i < 8; ++i) qm |= (-m4[i] <= tq) ? (1u << i) : 0u;
                         do {
                             const int j = __ffs(qm) - 1;   // -1: nothing (left) for this lane
                             qm &= qm - 1;
                             float s4[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float x0 = (j & 1) ? t[4 + u] : t[u], x1 = (j & 1) ? t[12 + u] : t[8 + u];
-                                const float x2 = (j & 1) ? t[20 + u] : t[16 + u], x3 = (j & 1) ? t[28 + u] : t[24 + u];
-                                const float y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
-                                s4[u] = (j & 4) ? y1 : y0;
+                                const uint32_t x0 = (j & 1) ? r[4 + u] : r[u], x1 = (j & 1) ? r[12 + u] : r[8 + u];
+                                const uint32_t x2 = (j & 1) ? r[20 + u] : r[16 + u], x3 = (j & 1) ? r[28 + u] : r[24 + u];
+                                const uint32_t y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
+                                s4[u] = -__uint_as_float((j & 4) ? y1 : y0);
                             }
                             uint32_t pm = 0;
                             if (j >= 0) {
@@ -429,9 +448,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 const int u = __ffs(pm) - 1;
                                 pm &= pm - 1;
                                 const float x = (u & 2) ? ((u & 1) ? s4[3] : s4[2]) : ((u & 1) ? s4[1] : s4[0]);
-                                if (!(x <= tq)) continue;   // the bound may have tightened inside this block
+                                if (!(x <= tq) || !(x < INFINITY)) continue;   // the bound may have tightened inside this block; masked columns
                                 if (!keep_mode) {   // k > 16: every survivor goes to the region (overflow -> exact redo)
-                                    if (cnt < p.cap) cand[cnt] = make_key(p.is_ip ? x : fmaf(2.0f, x, qn), e0 + u);
+                                    if (cnt < p.cap) cand[cnt] = make_key(x + qn, e0 + u);
                                     ++cnt;
                                     continue;
                                 }
@@ -451,22 +470,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 const float tk = tc_pick16(t16, p.k - 1);
                                 if (tk < tq) {
                                     tq = tk;
-                                    atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
+                                    atomicMin(p.thr + q, f32_to_ordered(tk + qn));
                                 }
                                 lost |= (vout <= tq) && (vout < INFINITY);
                             }
                         } while (__any_sync(0xffffffffu, qm != 0));
                     }
                 }
-                // this warp is done with the accumulator and the norm slot
+                // this warp is done with the accumulator
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&h_empty[hs]); }
+                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (warp == 0) stamp(6, m);
+                if (warp == 5) stamp(8, m);
             }
             if (SEED) {
-                // T = k-th smallest of this half's 64 group minima: distinct entries of ONE list, so k real
-                // candidates are at or below it (score = |q|^2 + 2 t for L2, t for IP); the two halves of a row
-                // combine by atomicMin. Needs k <= 16.
+                // T = k-th smallest of the row's 64 group minima of t: distinct entries of ONE list, so k real
+                // candidates are at or below it (score = t + |q|^2 for L2, t for IP). Needs k <= 16.
                 if (row_ok) {
                     float a[16], b[16];
 #pragma unroll
@@ -478,14 +498,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     tc_sort16(b); tc_sort16(c); tc_merge_low16(b, c);
                     tc_merge_low16(a, b);
                     const float tk = tc_pick16(a, p.k - 1);
-                    atomicMin(p.thr + q, f32_to_ordered(p.is_ip ? tk : fmaf(2.0f, tk, qn)));
+                    atomicMin(p.thr + q, f32_to_ordered(tk + qn));
                 }
             } else if (row_ok) {
                 if (keep_mode) {
                     cnt = 0;
 #pragma unroll
                     for (int i = 0; i < TC_CB; ++i)
-                        if (t16[i] <= tq && t16[i] < INFINITY) cand[cnt++] = make_key(p.is_ip ? t16[i] : fmaf(2.0f, t16[i], qn), e16[i]);
+                        if (t16[i] <= tq && t16[i] < INFINITY) cand[cnt++] = make_key(t16[i] + qn, e16[i]);
                     if (lost) cnt = p.cap + 1;
                 }
                 p.cand_count[(size_t)(it.q_begin + row) * 2 + half] = cnt;
@@ -494,7 +514,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == TC_W_ALLOC) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -504,8 +524,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // |x|^2 per row in fp32 (sequential order); *exact_flag is cleared unless every value is an integer of at
 // most 11 bits (exact in TF32) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
 // path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit
+// vaug (may be null): the row's augmented-K block [hi, lo, 0, 0, 0, 0, 0, 0] with |x|^2 = hi + lo, hi a multiple of 2048
+// and lo < 2048, i.e. both exact in TF32 when |x|^2 is an integer below 2^22.
 __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, long long n, float* __restrict__ out,
-                                 int* __restrict__ exact_flag, float out_scale) {
+                                 int* __restrict__ exact_flag, float* __restrict__ vaug) {
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float* r = x + i * ld;
@@ -516,7 +538,12 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
             bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
             bad |= !(fabsf(v.x) <= 2047.f && fabsf(v.y) <= 2047.f && fabsf(v.z) <= 2047.f && fabsf(v.w) <= 2047.f);
         }
-        out[i] = s * out_scale;
+        out[i] = s;
+        if (vaug) {
+            const float hi = floorf(s * (1.0f / 2048.0f)) * 2048.0f;
+            *reinterpret_cast<float4*>(vaug + i * 8) = make_float4(hi, s - hi, 0.f, 0.f);
+            *reinterpret_cast<float4*>(vaug + i * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         bad |= !(s < 4194304.0f);  // |x|^2 < 2^22  =>  |q|^2 + |v|^2 + 2|q.v| < 2^24
     }
     if (bad && exact_flag) *exact_flag = 0;
@@ -526,14 +553,15 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
 // n_slots (device scalar = group_offsets[B]) is the number of valid slots: explicit probe sets may hold invalid
 // (-1) entries, so it can be smaller than the host-side bound P the buffers were sized with.
 __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
-                                            long long P, const long long* __restrict__ n_slots, float* __restrict__ gq) {
+                                            long long P, const long long* __restrict__ n_slots, float* __restrict__ gq, float scale) {
     const int per_row = ds / 4;
     const long long total = (*n_slots < P ? *n_slots : P) * per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long s = i / per_row;
         const int c = (int)(i % per_row) * 4;
-        *reinterpret_cast<float4*>(gq + s * ds + c) =
-            *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+        float4 v = *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        *reinterpret_cast<float4*>(gq + s * ds + c) = v;
     }
 }
 
