@@ -194,25 +194,37 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
         float best = -INFINITY;
         int best_b = 0;
         unsigned long long h1 = KEY_INF, h2 = KEY_INF;  // this lane's two best selected partitions
-        for (int b0 = 0; b0 < p.B; b0 += 32) {
-            const int b = b0 + lane;
-            bool hit = false;
-            if (b < p.B) {
-                const float v = s[b];
-                if (p.mode == SEL_GT) hit = (double)v > p.value;
-                else if (p.mode == SEL_GE_ARGMAX) hit = (double)v >= p.value;
-                else hit = true;
-                if (v > best) { best = v; best_b = b; }  // first maximum per lane (b ascending)
+        for (int base = 0; base < p.B; base += 1024) {
+            // 32 independent coalesced loads in flight per lane (the loop below is compute only)
+            float vv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int b = base + i * 32 + lane;
+                vv[i] = b < p.B ? s[b] : -INFINITY;
             }
-            const uint32_t mm = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                sel[n + __popc(mm & ((1u << lane) - 1u))] = b;
-                atomicAdd(p.list_count + b, 1);
-                cmp += p.list_offsets[b + 1] - p.list_offsets[b];
-                const unsigned long long hk = make_key(-s[b], (uint32_t)b);
-                if (hk < h1) { h2 = h1; h1 = hk; } else if (hk < h2) { h2 = hk; }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int b = base + i * 32 + lane;
+                if (base + i * 32 >= p.B) break;
+                bool hit = false;
+                const float v = vv[i];
+                if (b < p.B) {
+                    if (p.mode == SEL_GT) hit = (double)v > p.value;
+                    else if (p.mode == SEL_GE_ARGMAX) hit = (double)v >= p.value;
+                    else hit = true;
+                    if (v > best) { best = v; best_b = b; }  // first maximum per lane (b ascending)
+                }
+                const uint32_t mm = __ballot_sync(0xffffffffu, hit);
+                if (mm == 0) continue;
+                if (hit) {
+                    sel[n + __popc(mm & ((1u << lane) - 1u))] = b;
+                    atomicAdd(p.list_count + b, 1);
+                    cmp += p.list_offsets[b + 1] - p.list_offsets[b];
+                    const unsigned long long hk = make_key(-v, (uint32_t)b);
+                    if (hk < h1) { h2 = h1; h1 = hk; } else if (hk < h2) { h2 = hk; }
+                }
+                n += __popc(mm);
             }
-            n += __popc(mm);
         }
         // global argmax, first maximum wins (search.cpp:456-466); it is always selected when anything is
 #pragma unroll
@@ -248,17 +260,25 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     }
 }
 
-// exclusive scan of int counts into long long offsets (n+1 entries), single CTA of 1024 threads
+// exclusive scan of int counts into long long offsets (n+1 entries), single CTA of 1024 threads, 8 elements per
+// thread and round
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* in, long long* out, int n) {
     __shared__ long long warp_sum[32];
     __shared__ long long carry_s;
+    constexpr int PER = 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const long long v = i < n ? (long long)in[i] : 0;
-        long long x = v;
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int i0 = base + threadIdx.x * PER;
+        int v[PER];
+        long long tsum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+            tsum += v[j];
+        }
+        long long x = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const long long y = __shfl_up_sync(0xffffffffu, x, o);
@@ -277,8 +297,12 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* in, lon
         }
         __syncthreads();
         const long long carry = carry_s;
-        const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + (x - v);
-        if (i < n) out[i] = before;
+        long long before = carry + (warp ? warp_sum[warp - 1] : 0) + (x - tsum);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (i0 + j < n) out[i0 + j] = before;
+            before += v[j];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = carry + warp_sum[31];
         __syncthreads();

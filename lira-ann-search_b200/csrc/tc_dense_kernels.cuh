@@ -14,7 +14,7 @@
 // cancel catastrophically for SIFT-like data (norms 1e5-1e6, squared distances 1e4).
 //
 // One persistent CTA per SM; warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue (one TMEM
-// lane quadrant each). 128 x 128 output tiles, K blocks of 32 floats, 3-stage ring of {A_hi, A_lo, B_hi, B_lo}
+// lane quadrant and half of the columns each, eight warps). 128 x 128 output tiles, K blocks of 32 floats, 3-stage ring of {A_hi, A_lo, B_hi, B_lo}
 // boxes (64 KiB per stage), two TMEM accumulators so the epilogue of a tile overlaps the MMAs of the next.
 #pragma once
 #include "tc_scan_kernels.cuh"
@@ -23,10 +23,11 @@ namespace lira {
 
 enum { TD_EPI_FEATURE = 0, TD_EPI_BIAS_RELU = 1, TD_EPI_BIAS_SIGMOID = 2 };
 
-static constexpr int TD_THREADS = 192;
+static constexpr int TD_THREADS = 320;   // warp 0 TMA, warp 1 TMEM + MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+static constexpr int TD_EPI_WARPS = 8;
 static constexpr int TD_NSTAGE = 3;
 static constexpr int TD_STAGE_BYTES = 4 * B_STAGE_BYTES;   // A_hi, A_lo, B_hi, B_lo: 128 rows x 128 B each
-static constexpr size_t TD_SMEM_BYTES = (size_t)TD_NSTAGE * TD_STAGE_BYTES + 3 * TC_N * 4 + 4 * 32 * 33 * 4 + 256;
+static constexpr size_t TD_SMEM_BYTES = (size_t)TD_NSTAGE * TD_STAGE_BYTES + 3 * TC_N * 4 + TD_EPI_WARPS * 32 * 33 * 4 + 256;
 
 struct TdParams {
     int M, N, K;             // out is M x N, reduction over K (zero-filled past the end by TMA)
@@ -41,6 +42,12 @@ struct TdParams {
     const float* rown;       // FEATURE: |q'|^2 [M]
 };
 
+// MUFU.SQRT: max relative error 2^-22 (the reference's own two feature paths differ by more: fp64 cdist vs fp32 loop)
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 template <int EPI>
@@ -51,8 +58,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* stages = smem_raw;
     float* vec_s = (float*)(stages + (size_t)TD_NSTAGE * TD_STAGE_BYTES);   // [3][128] per-column epilogue vectors
-    float* tr_s = vec_s + 3 * TC_N;                   // [4 warps][32][33] transpose tiles of the epilogue
-    uint64_t* full = (uint64_t*)(tr_s + 4 * 32 * 33);   // [TD_NSTAGE]
+    float* tr_s = vec_s + 3 * TC_N;                   // [8 warps][32][33] transpose tiles of the epilogue
+    uint64_t* full = (uint64_t*)(tr_s + TD_EPI_WARPS * 32 * 33);   // [TD_NSTAGE]
     uint64_t* empty = full + TD_NSTAGE;               // [TD_NSTAGE]
     uint64_t* t_full = empty + TD_NSTAGE;             // [2]
     uint64_t* t_empty = t_full + 2;                   // [2]
@@ -61,7 +68,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < TD_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TD_EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -129,18 +136,19 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
             __syncwarp();
         }
     } else {
-        // ===== epilogue: warps 2..5 -> TMEM lane quadrants 2, 3, 0, 1 =====
+        // ===== epilogue: warps 2..9 -> TMEM lane quadrants 2, 3, 0, 1, 2, 3, 0, 1; warps 2-5 take columns 0-63, 6-9 columns 64-127 =====
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;   // 0..127
+        const int et = threadIdx.x - 64;   // 0..255
+        const int half = (warp - 2) >> 2;
         float* tr = tr_s + (warp - 2) * 32 * 33;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u;
             const int m0 = (t / tiles_n) * TC_M, n0 = (t % tiles_n) * TC_N;
             // per-column vectors of this tile -> shared (previous tile's readers are past their last read: bar below)
-            named_bar_sync(2, 128);
-            {
+            named_bar_sync(2, TD_EPI_WARPS * 32);
+            if (et < TC_N) {
                 const int n = n0 + et;
                 const bool ok = n < p.N;
                 vec_s[et] = (ok && p.v0) ? __ldg(p.v0 + n) : 0.0f;
@@ -148,10 +156,10 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                     vec_s[TC_N + et] = (ok && p.v1) ? __ldg(p.v1 + n) : 0.0f;
                     float sc = (ok && p.v2) ? __ldg(p.v2 + n) : 1.0f;
                     if (sc == 0.0f) sc = 1.0f;   // search.cpp:246
-                    vec_s[2 * TC_N + et] = sc;
+                    vec_s[2 * TC_N + et] = 1.0f / sc;   // the epilogue multiplies (1 ulp from the reference's division)
                 }
             }
-            named_bar_sync(2, 128);
+            named_bar_sync(2, TD_EPI_WARPS * 32);
             const int m = m0 + row;
             float rn = 0.0f;
             if (EPI == TD_EPI_FEATURE && m < p.M) rn = __ldg(p.rown + m);
@@ -159,7 +167,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
 #pragma unroll 1
-            for (int g = 0; g < TC_N / 32; ++g) {
+            for (int g = half * 2; g < half * 2 + 2; ++g) {
                 uint32_t r[32];
                 tc_ld32_async(taddr + g * 32, r);
                 tc_ld_wait(r);
@@ -171,13 +179,13 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                     if (EPI == TD_EPI_FEATURE) {
                         // utils.py:98-118 (Euclidean distance, with sqrt) + StandardScaler.transform (:142-167)
                         const float d2 = fmaf(-2.0f, a, rn + vec_s[c]);
-                        float v = sqrtf(fmaxf(d2, 0.0f));
-                        if (p.v1) v = (v - vec_s[TC_N + c]) / vec_s[2 * TC_N + c];
+                        float v = fast_sqrt(fmaxf(d2, 0.0f));
+                        if (p.v1) v = (v - vec_s[TC_N + c]) * vec_s[2 * TC_N + c];
                         y[u] = v;
                     } else if (EPI == TD_EPI_BIAS_RELU) {
                         y[u] = fmaxf(a + vec_s[c], 0.0f);
                     } else {
-                        y[u] = 1.0f / (1.0f + expf(-(a + vec_s[c])));
+                        y[u] = __fdividef(1.0f, 1.0f + __expf(-(a + vec_s[c])));   // sigmoid, ~2 ulp
                     }
                 }
                 // transpose the warp's 32 x 32 block through shared memory so that every store instruction writes

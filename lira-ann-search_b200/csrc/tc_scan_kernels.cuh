@@ -646,25 +646,26 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
             }
         }
         overflow |= cnt > p.cap;
-        uint32_t live = __ballot_sync(0xffffffffu, cnt > 0);
-        while (live) {
-            const int src = __ffs(live) - 1;
-            live &= live - 1;
-            int n = __shfl_sync(0xffffffffu, cnt, src);
-            n = n < p.cap ? n : p.cap;
-            const unsigned long long* srcp = p.cand_key + (size_t)__shfl_sync(0xffffffffu, region, src) * p.cap;
-            for (int e0 = 0; e0 < n; e0 += 32) {
-                const int e = e0 + lane;
-                unsigned long long x = KEY_INF;
-                if (e < n) {
-                    const unsigned long long c = srcp[e];
-                    x = (c & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(c));  // entry -> global id
-                }
-                uint32_t mm = __ballot_sync(0xffffffffu, x < kth);
+        cnt = cnt < p.cap ? cnt : p.cap;
+        const unsigned long long* srcp = p.cand_key + (size_t)(region < 0 ? 0 : region) * p.cap;
+        const int max_cnt = __reduce_max_sync(0xffffffffu, cnt);
+        for (int r0 = 0; r0 < max_cnt; r0 += 16) {
+            // every lane pulls up to 16 entries of ITS region: all key loads, then all id loads, are in flight together
+            // (two dependent round trips per block instead of two per region)
+            unsigned long long x[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = (r0 + r < cnt) ? srcp[r0 + r] : KEY_INF;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (x[r] != KEY_INF) x[r] = (x[r] & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(x[r]));  // entry -> global id
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                if (r0 + r >= max_cnt) break;
+                uint32_t mm = __ballot_sync(0xffffffffu, x[r] < kth);
                 while (mm) {
                     const int sl = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    const unsigned long long y = shfl_u64(x, sl);
+                    const unsigned long long y = shfl_u64(x[r], sl);
                     if (!(y < kth)) continue;
                     bool dup = false;
                     if (p.dedup) {
