@@ -578,7 +578,10 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                      cudaStream_t st) {
     *done = false;
     *n_redo = 0;
-    if (!h->tc_ok || h->ds > TC_MAX_KB * KC || Q < 256 || ps.kind == 2) return 0;
+    if (!h->tc_ok || h->ds > TC_MAX_KB * KC || Q < 256) return 0;
+    // exhaustive probe sets (exact kNN over base segments): only with the in-kernel bound tightening (k <= 16); a
+    // static seed bound alone would let a large share of a million-row base through
+    if (ps.kind == 2 && k > TC_KMAX_TIGHTEN) return 0;
     LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
     Workspace& ws = h->ws;
     if (int rc = ws.qnorm.ensure((size_t)Q * 4)) return rc;
@@ -596,6 +599,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = save_stats(h, ws, st)) return rc;
     if (ps.kind == 1) {
         first_probes_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, (int)Q, ws.top1.as<int>());
+        LIRA_LAUNCH_CHECK();
+    } else if (ps.kind == 2) {   // every query probes every list: seed with the first (two)
+        seed_first_lists_kernel<<<grid_for(Q, 256), 256, 0, st>>>((int)Q, h->B, ws.top1.as<int>());
         LIRA_LAUNCH_CHECK();
     }
     if (d_nprobe) {
@@ -676,7 +682,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
     // ---- filter on the tensor cores ----
     // one private candidate region per (pair, column half); every valid pair's owner writes its count
-    if (int rc = ws.cand_key.ensure((size_t)P * 2 * TC_CAPP * 8)) return rc;
+    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CB : TC_CAPP;   // chain mode stores at most TC_CB entries per region
+    if (int rc = ws.cand_key.ensure((size_t)P * 2 * cap * 8)) return rc;
     if (int rc = ws.cand_count.ensure((size_t)P * 2 * 4)) return rc;
     TcParams tp;
     tp.group_queries = ws.group_queries.as<int>();
@@ -690,7 +697,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.thr = ws.thr.as<uint32_t>();
     tp.cand_key = ws.cand_key.as<unsigned long long>();
     tp.cand_count = ws.cand_count.as<int>();
-    tp.cap = TC_CAPP;
+    tp.cap = cap;
     tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
     tp.trace = nullptr;
@@ -705,7 +712,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
-    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), TC_CAPP, po, ws.probe_slot.as<int>(), h->ids, k,
+    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), cap, po, ws.probe_slot.as<int>(), h->ids, k,
                     (int)Q, dedup, h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1};
     const int warps = 8;
     if (k <= 32) refine_topk_kernel<1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);

@@ -606,6 +606,14 @@ __global__ void first_probes_kernel(const long long* probe_offsets, const int* p
     }
 }
 
+// exhaustive probe sets: seed every query with lists 0 and 1
+__global__ void seed_first_lists_kernel(int Q, int B, int* seed_ids) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
+        seed_ids[2 * q + 0] = 0;
+        seed_ids[2 * q + 1] = B > 1 ? 1 : -1;
+    }
+}
+
 // refine: the candidate regions (score, list entry) of a query's probed (list, half) pairs -> exact top-k over
 // distinct ids. One warp per query.
 struct RefineParams {

@@ -387,3 +387,16 @@ def test_model_tensor_core_forward_large_offset_data(L):
     np.testing.assert_allclose(f_tc, f64, rtol=1e-5, atol=2e-5)
     _, probs, _ = O.mlp_forward(f64, x_q, w)
     np.testing.assert_allclose(s_tc, probs, rtol=1e-4, atol=2e-6)
+
+
+def test_knn_tensor_core_path_matches_oracle(L):
+    """Exact kNN over base segments on the tensor-core scan (integer data, >= 256 queries, k <= 16)."""
+    x_d, x_q = synth(40000, 64, 300, seed=77, integer=True)
+    k = 11  # compute_knn's k + 1 for k = 10 (compute_knn.cpp:237)
+    D, I = L.knn(x_d, x_q, k, O.L2)
+    D_ref, I_ref = O.knn(x_d, x_q, k, O.L2, O.F64)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref.astype(np.float32))
+    # self-kNN shape: the query itself comes first
+    D2, I2 = L.knn(x_d, x_d[:512], k, O.L2)
+    D2_ref, I2_ref = O.knn(x_d, x_d[:512], k, O.L2, O.F64)
+    assert np.array_equal(I2, I2_ref) and np.array_equal(D2, D2_ref.astype(np.float32))
