@@ -47,19 +47,32 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def _gxx():
+    # the image exports CC/CXX wrappers that lack libgomp.spec; use the distro g++ like oracle/Makefile
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+
+
 def build_binaries(force=False):
-    """compute_knn and search command-line programs (reference argv) -> bin/."""
+    """compute_knn and search command-line programs (reference argv) -> bin/.
+    compute_knn is plain C++ over the C ABI; search additionally links LibTorch (from the installed torch wheel),
+    used only to read the TorchScript checkpoint written by the reference's index.py."""
     os.makedirs(BIN, exist_ok=True)
     built = []
-    for name in ("compute_knn", "search"):
-        src = os.path.join(CSRC, name + "_main.cpp")
-        if not os.path.exists(src):
-            continue
-        out = os.path.join(BIN, name)
-        if force or _newer(out, [src, LIB] + _sources()):
-            subprocess.check_call([_nvcc(), "-std=c++17", "-O2", "-x", "cu", "-gencode",
-                                   "arch=compute_100a,code=sm_100a", "-o", out, src,
-                                   "-I" + os.path.join(ROOT, "include"), "-L" + HERE, "-llira_b200",
-                                   "-Xlinker", "-rpath," + HERE, "-Xlinker", "-rpath,$ORIGIN/../lira-ann-search_b200"])
-        built.append(out)
+    inc = "-I" + os.path.join(ROOT, "include")
+    link = ["-L" + HERE, "-llira_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../lira-ann-search_b200"]
+    src = os.path.join(CSRC, "compute_knn_main.cpp")
+    out = os.path.join(BIN, "compute_knn")
+    if force or _newer(out, [src, LIB]):
+        subprocess.check_call([_gxx(), "-std=c++17", "-O2", "-o", out, src, inc] + link)
+    built.append(out)
+    src = os.path.join(CSRC, "search_main.cpp")
+    out = os.path.join(BIN, "search")
+    if force or _newer(out, [src, LIB]):
+        import torch
+        tdir = os.path.dirname(torch.__file__)
+        subprocess.check_call([_gxx(), "-std=gnu++17", "-O2", "-o", out, src, inc,
+                               "-I" + os.path.join(tdir, "include"), "-I" + os.path.join(tdir, "include/torch/csrc/api/include"),
+                               "-L" + os.path.join(tdir, "lib"), "-Wl,-rpath," + os.path.join(tdir, "lib"),
+                               "-lc10", "-ltorch", "-ltorch_cpu"] + link)
+    built.append(out)
     return built

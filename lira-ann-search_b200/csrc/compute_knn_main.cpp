@@ -1,0 +1,141 @@
+// compute_knn: self-kNN ground truth of a dataset, the command line and file formats of the reference's
+// compute_knn.cpp (argv :100-104, input :111-137, exact branch :208-259, outputs :262-290), with the brute-force
+// search on the GPU through liblira_b200 (lira_knn) instead of faiss::IndexFlatL2.
+//
+//   compute_knn <dataset> <data_path> <k> [nprobe] [n_threads]
+//
+// reads  {data_path}/{dataset}/{dataset}_base.fvecs (or .bvecs)
+// writes {data_path}/{dataset}/knn_cache/{dataset}-data_self_knn{k}-n{n}.bin   (raw int32 [n, k]) and .bin.meta
+//
+// The reference's IVF branch (nprobe != 0) trades accuracy for CPU time; the GPU search is exact at any size, so
+// every nprobe value produces the exact result (method: flat_exact, no _ivf_nprobe suffix). n_threads is accepted
+// and ignored.
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "lira_b200.h"
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::high_resolution_clock::now().time_since_epoch()).count();
+}
+
+// .fvecs / .bvecs: per vector a little-endian int32 dimension followed by `dim` elements
+template <class T>
+bool read_vecs(const std::string& path, std::vector<float>& out, int64_t& n, int& dim) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    int32_t d = 0;
+    if (std::fread(&d, 4, 1, f) != 1 || d <= 0) { std::fclose(f); return false; }
+    std::fseek(f, 0, SEEK_END);
+    const long long bytes = std::ftell(f);
+    const long long rec = 4 + (long long)d * sizeof(T);
+    if (bytes % rec != 0) { std::fclose(f); std::cerr << "Error: " << path << " is not a whole number of records" << std::endl; return false; }
+    n = bytes / rec;
+    dim = d;
+    std::fseek(f, 0, SEEK_SET);
+    out.resize((size_t)n * d);
+    std::vector<unsigned char> buf(rec);
+    for (int64_t i = 0; i < n; ++i) {
+        if (std::fread(buf.data(), 1, rec, f) != (size_t)rec) { std::fclose(f); return false; }
+        const T* src = reinterpret_cast<const T*>(buf.data() + 4);
+        for (int j = 0; j < d; ++j) out[(size_t)i * d + j] = (float)src[j];
+    }
+    std::fclose(f);
+    return true;
+}
+
+bool exists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 4) {
+        std::cout << "Usage: " << argv[0] << " <dataset> <data_path> <k> [nprobe] [n_threads]" << std::endl;
+        std::cout << "  exact brute-force self-kNN on the GPU (any nprobe gives the exact result)" << std::endl;
+        return 1;
+    }
+    const std::string dataset = argv[1], data_path = argv[2];
+    const int k = std::atoi(argv[3]);
+    if (k < 1 || k > 127) { std::cerr << "Error: k must be in [1, 127]" << std::endl; return 1; }
+
+    std::cout << "=== GPU KNN Computation (liblira_b200) ===" << std::endl;
+    std::cout << "Dataset: " << dataset << std::endl;
+    std::cout << "K: " << k << std::endl;
+
+    const std::string dir = data_path + "/" + dataset;
+    std::string base_file = dir + "/" + dataset + "_base.fvecs";
+    bool bvecs = false;
+    if (!exists(base_file)) {
+        base_file = dir + "/" + dataset + "_base.bvecs";
+        bvecs = true;
+        if (!exists(base_file)) {
+            std::cerr << "Error: Cannot find base file for dataset " << dataset << std::endl;
+            return 1;
+        }
+    }
+    int64_t n = 0;
+    int dim = 0;
+    std::vector<float> data;
+    const double t0 = now_s();
+    std::cout << "Reading " << (bvecs ? ".bvecs" : ".fvecs") << " file..." << std::endl;
+    const bool ok = bvecs ? read_vecs<uint8_t>(base_file, data, n, dim) : read_vecs<float>(base_file, data, n, dim);
+    if (!ok) { std::cerr << "Error: Cannot open file " << base_file << std::endl; return 1; }
+    const double read_time = now_s() - t0;
+    std::cout << "Loaded " << n << " vectors of dimension " << dim << std::endl;
+    std::cout << "Read time: " << read_time << "s" << std::endl;
+
+    // k + 1 neighbours of every base vector, column 0 (the vector itself) dropped: compute_knn.cpp:237, 254-259
+    std::vector<float> D((size_t)n * (k + 1));
+    std::vector<int64_t> I((size_t)n * (k + 1));
+    const double t1 = now_s();
+    if (lira_knn(data.data(), n, data.data(), n, dim, k + 1, LIRA_METRIC_L2, 0, D.data(), I.data()) != 0) {
+        std::cerr << "Error: " << lira_last_error() << std::endl;
+        return 1;
+    }
+    const double search_time = now_s() - t1;
+    std::cout << "Search time: " << search_time << "s" << std::endl;
+
+    std::vector<int32_t> knn((size_t)n * k);
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < k; ++j) knn[(size_t)i * k + j] = (int32_t)I[(size_t)i * (k + 1) + j + 1];
+
+    const std::string cache_dir = dir + "/knn_cache";
+    mkdir(cache_dir.c_str(), 0755);
+    const std::string out = cache_dir + "/" + dataset + "-data_self_knn" + std::to_string(k) + "-n" + std::to_string(n) + ".bin";
+    {
+        std::ofstream f(out, std::ios::binary);
+        if (!f) { std::cerr << "Error: Cannot write " << out << std::endl; return 1; }
+        f.write(reinterpret_cast<const char*>(knn.data()), (std::streamsize)(knn.size() * sizeof(int32_t)));
+    }
+    {
+        std::ofstream meta(out + ".meta");
+        meta << "dataset: " << dataset << std::endl;
+        meta << "n: " << n << std::endl;
+        meta << "dim: " << dim << std::endl;
+        meta << "k: " << k << std::endl;
+        meta << "method: flat_exact" << std::endl;
+        meta << "read_time: " << read_time << "s" << std::endl;
+        meta << "build_time: " << 0.0 << "s" << std::endl;
+        meta << "search_time: " << search_time << "s" << std::endl;
+        meta << "total_time: " << (read_time + search_time) << "s" << std::endl;
+    }
+    std::cout << std::endl << "=== Summary ===" << std::endl;
+    std::cout << "Total time: " << (read_time + search_time) << "s" << std::endl;
+    std::cout << "Output file: " << out << std::endl;
+    std::cout << "To load in Python:" << std::endl;
+    std::cout << "  knn_data = np.fromfile('" << out << "', dtype=np.int32).reshape(" << n << ", " << k << ")" << std::endl;
+    return 0;
+}
