@@ -166,38 +166,62 @@ def recall_at(ids, gt, k):
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML (the library behind nvidia-smi's clocks.sm /
+    clocks_event_reasons.* fields) from a polling thread: the timed region of this bench is a few milliseconds,
+    shorter than one `nvidia-smi -lms` period, so the samples are taken in-process every ~0.5 ms. mark() brackets
+    the timed region; the summary is over the samples inside it."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu=0):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.stop_flag, self.thread, self.h = gpu, [], False, None, None
+        self.t0 = self.t1 = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception as e:  # no NVML: the line then says so
+            print(f"[bench] clocks: NVML unavailable ({e})", file=sys.stderr)
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        scope = "timed region"
+        if not inside:  # (should not happen: the poll period is far below one step)
+            inside, scope = self.rows, "warm-up + timed region"
+        sm = [r[1] for r in inside]
+        reasons = sorted({name for r in inside for name, bit in self.REASONS if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sm), "scope": scope, "source": "NVML, polled in-process every ~0.5 ms"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -379,6 +403,9 @@ def main():
         out = index.probe_search_dev(model, d_q, L.SELECT_GT, thr, k, True, out=out)
         return gather_merge(out[0], out[1])
 
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         flush.zero_()
         step()
@@ -387,11 +414,9 @@ def main():
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     scan_ms, scan_bytes, scan_pairs = [], [], []
+    clocks.mark_begin()
     t_wall = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
@@ -405,6 +430,7 @@ def main():
     if dist is not None:
         dist.barrier()
     wall = time.perf_counter() - t_wall
+    clocks.mark_end()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     launches = L.launch_count() - launches0

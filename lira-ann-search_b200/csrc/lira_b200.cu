@@ -77,16 +77,35 @@ static int make_tmap(CUtensorMap* m, const float* base, long long rows, int cols
     return 0;
 }
 
-// rows x 8 fp32 matrix (32-byte rows): box = 128 rows x 8 floats, 32-byte swizzle (the augmented-K blocks).
-static int make_tmap_aug(CUtensorMap* m, const float* base, long long rows) {
+// rows x cols fp16 matrix with row stride ld (halves); box = 128 rows x 64 halves, 128-byte swizzle (tensor-core scan).
+static int make_tmap_f16(CUtensorMap* m, const void* base, long long rows, int cols, long long ld) {
+    PFN_encodeTiled enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    LIRA_REQUIRE(((uintptr_t)base & 15) == 0 && (ld % 8) == 0, "tensor map: base must be 16-byte aligned, ld % 8 == 0");
+    cuuint64_t dims[2] = {(cuuint64_t)std::max(cols, 1), (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KH, (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp16) failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
+// rows x 16 fp16 matrix (32-byte rows): box = 128 rows x 16 halves, 32-byte swizzle (the augmented-K blocks).
+static int make_tmap_aug(CUtensorMap* m, const void* base, long long rows) {
     PFN_encodeTiled enc;
     if (int rc = get_encode_fn(&enc)) return rc;
     LIRA_REQUIRE(((uintptr_t)base & 31) == 0, "tensor map: augmented block must be 32-byte aligned");
-    cuuint64_t dims[2] = {8, (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t dims[2] = {16, (cuuint64_t)std::max<long long>(rows, 1)};
     cuuint64_t strides[1] = {32};
-    cuuint32_t box[2] = {8, (cuuint32_t)TN};
+    cuuint32_t box[2] = {16, (cuuint32_t)TN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -149,8 +168,11 @@ struct lira_index {
     Workspace ws, ws_seed;
     DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
     float* vnorm = nullptr;      // |v|^2 per list entry
-    float* vaug = nullptr;       // [E, 8] augmented-K block of every entry: (hi, lo, 0...) with |v|^2 = hi + lo (tensor-core path)
-    float* aaug = nullptr;       // [128, 8] constant augmented-K block of the query side: (-1, -1, 0...)
+    __half* vaug = nullptr;      // [E, 16] fp16 augmented-K block of every entry: (hi, lo, 0...) with |v|^2 = 2048 hi + lo (tensor-core path)
+    __half* vecs16 = nullptr;    // [E, d16] fp16 shadow copy of vecs (exact when tc_ok): the tensor-core scan streams this
+    int d16 = 0;                 // round_up(d, 8)
+    CUtensorMap tmap16;
+    __half* aaug = nullptr;      // [128, 16] constant fp16 augmented-K block of the query side: (-2048, -1, 0...)
     CUtensorMap tmap_vaug, tmap_aaug;
     bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
     bool use_tc = true;
@@ -203,8 +225,9 @@ static int init_kernels(int device) {
     rc |= set_smem(scan_lists_kernel<OP_DOT, 1>, scan_smem_bytes<1>());
     rc |= set_smem(scan_lists_kernel<OP_L2, 4>, scan_smem_bytes<4>());
     rc |= set_smem(scan_lists_kernel<OP_DOT, 4>, scan_smem_bytes<4>());
-    rc |= set_smem(tc_scan_kernel<false>, TC_SMEM_BYTES);
-    rc |= set_smem(tc_scan_kernel<true>, TC_SMEM_BYTES);
+    rc |= set_smem(tc_scan_kernel<false, false>, TC_SMEM_BYTES);
+    rc |= set_smem(tc_scan_kernel<false, true>, TC_SMEM_BYTES);
+    rc |= set_smem(tc_scan_kernel<true, false>, TC_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
@@ -578,7 +601,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                      cudaStream_t st) {
     *done = false;
     *n_redo = 0;
-    if (!h->tc_ok || h->ds > TC_MAX_KB * KC || Q < 256) return 0;
+    if (!h->tc_ok || Q < 256) return 0;
     // exhaustive probe sets (exact kNN over base segments): only with the in-kernel bound tightening (k <= 16); a
     // static seed bound alone would let a large share of a million-row base through
     if (ps.kind == 2 && k > TC_KMAX_TIGHTEN) return 0;
@@ -589,7 +612,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
     int one_zero[2] = {1, 0};  // [0] query batch exactly representable, [1] number of overflowed queries
     LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 8, cudaMemcpyHostToDevice, st));
-    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), nullptr);
+    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), nullptr, nullptr, 0);
     LIRA_LAUNCH_CHECK();
     long long P = 0;
     const long long* po = nullptr;
@@ -609,8 +632,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         LIRA_LAUNCH_CHECK();
     }
     if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
-    const int nk = (h->ds + KC - 1) / KC;
-    // L2: the gathered query rows carry the factor 2 of  s = 2 q.v - |v|^2  (exact: integers of <= 11 bits, doubled)
+    const int nk = (h->d16 + TC_KH - 1) / TC_KH;
+    // L2: the gathered fp16 query rows carry the factor 2 of  s = 2 q.v - |v|^2  (exact: integers of <= 11 bits, doubled)
     const float qscale = h->metric == LIRA_METRIC_IP ? 1.0f : 2.0f;
     Workspace& sw = h->ws_seed;
     if (k <= TC_KMAX_TIGHTEN) {
@@ -631,12 +654,12 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         long long Pseed = 0;
         const long long* po_seed = nullptr;
         if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
-        if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->ds * 4)) return rc;
-        gather_group_queries_kernel<<<grid_for(Pseed * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(
-            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<float>(), qscale);
+        if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->d16 * 2)) return rc;
+        gather_group_queries_kernel<<<grid_for(Pseed * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(
+            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<__half>(), h->d16, qscale);
         LIRA_LAUNCH_CHECK();
         CUtensorMap tmap_sq;
-        if (int rc = make_tmap(&tmap_sq, sw.gq.as<float>(), Pseed, h->ds, h->ds)) return rc;
+        if (int rc = make_tmap_f16(&tmap_sq, sw.gq.as<__half>(), Pseed, h->d16, h->d16)) return rc;
         TcParams sp;
         sp.group_queries = sw.group_queries.as<int>();
         sp.list_offsets = h->d_offsets;
@@ -644,7 +667,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.n_items = sw.n_items.as<int>();
         sp.work_counter = sw.n_items.as<int>() + 1;
         sp.nk = nk;
-        sp.max_rows = TC_SEED_ROWS_TC;
+        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_TC;
+        sp.exp = 0;
         sp.qnorm = ws.qnorm.as<float>();
         sp.thr = ws.thr.as<uint32_t>();
         sp.cand_key = nullptr;
@@ -653,8 +677,11 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.trace = nullptr;
         sp.k = k;
         sp.is_ip = h->metric == LIRA_METRIC_IP;
-        tc_scan_kernel<true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap, h->tmap_vaug, h->tmap_aaug, sp);
-        LIRA_LAUNCH_CHECK();
+        // (LIRA_TC_NO_SEED, tests only: every bound starts at +inf, so the in-kernel region compaction does all the work)
+        if (!getenv("LIRA_TC_NO_SEED")) {
+            tc_scan_kernel<true, false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
+            LIRA_LAUNCH_CHECK();
+        }
     } else {
         // ---- seed on the CUDA cores (k > 16): exact scan of the first rows of the two best lists ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
@@ -674,15 +701,15 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         LIRA_LAUNCH_CHECK();
     }
     // ---- queries in group order (one TMA box per tile) ----
-    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->ds * 4)) return rc;
-    gather_group_queries_kernel<<<grid_for(P * (h->ds / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                        ws.group_offsets.as<long long>() + h->B, ws.gq.as<float>(), qscale);
+    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
+    gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
+                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale);
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
-    if (int rc = make_tmap(&tmap_q, ws.gq.as<float>(), P, h->ds, h->ds)) return rc;
+    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
     // ---- filter on the tensor cores ----
     // one private candidate region per (pair, column half); every valid pair's owner writes its count
-    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CB : TC_CAPP;   // chain mode stores at most TC_CB entries per region
+    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
     if (int rc = ws.cand_key.ensure((size_t)P * 2 * cap * 8)) return rc;
     if (int rc = ws.cand_count.ensure((size_t)P * 2 * 4)) return rc;
     TcParams tp;
@@ -701,6 +728,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
     tp.trace = nullptr;
+    tp.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) : 0;
     const char* trace_path = getenv("LIRA_TC_TRACE");   // debug: per-chunk clock stamps of CTA 0 -> CSV
     if (trace_path) {
         if (int rc = ws.trace.ensure((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS * 8)) return rc;
@@ -708,7 +736,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         tp.trace = ws.trace.as<long long>();
     }
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    tc_scan_kernel<false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap, h->tmap_vaug, h->tmap_aaug, tp);
+    if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    else tc_scan_kernel<false, false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
@@ -843,20 +872,31 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)std::max<long long>(h->E, 1) * 32));
     LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
     {
-        std::vector<float> a(128 * 8, 0.0f);
-        for (int r = 0; r < 128; ++r) a[r * 8] = a[r * 8 + 1] = -1.0f;
-        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<__half> a(128 * 16, __float2half(0.0f));
+        for (int r = 0; r < 128; ++r) { a[r * 16] = __float2half(-2048.0f); a[r * 16 + 1] = __float2half(-1.0f); }
+        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
     }
+    h->d16 = (h->ds + 7) / 8 * 8;
+    // fp16 shadow copy of the rows for the tensor-core scan (dropped again below when the data is not exact in fp16)
+    const bool want16 = h->d16 <= TC_MAX_KB * TC_KH;
+    if (want16) LIRA_CUDA_OK(cudaMalloc(&h->vecs16, (size_t)std::max<long long>(h->E, 1) * h->d16 * 2));
     if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
     if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
     if (h->E > 0) {
-        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, h->vaug);
+        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, h->vaug,
+                                                                              h->vecs16, h->d16);
         g_launches.fetch_add(1);
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
     LIRA_CUDA_OK(cudaMemcpy(&one, d_flag, 4, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
-    h->tc_ok = (one == 1) && h->E > 0;
+    h->tc_ok = (one == 1) && h->E > 0 && want16;
+    if (!h->tc_ok) {   // the CUDA-core scan never reads these
+        cudaFree(h->vecs16); h->vecs16 = nullptr;
+        cudaFree(h->vaug); h->vaug = nullptr;
+    } else {
+        if (int rc = make_tmap_f16(&h->tmap16, h->vecs16, h->E, h->d16, h->d16)) return rc;
+    }
     cudaDeviceProp prop;
     LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
     h->num_sms = prop.multiProcessorCount;
@@ -989,6 +1029,7 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->d_list_order);
     cudaFree(h->vnorm);
     cudaFree(h->vaug);
+    cudaFree(h->vecs16);
     cudaFree(h->aaug);
     h->ws.release();
     h->ws_seed.release();
@@ -1015,7 +1056,7 @@ int lira_index_set_use_tensor_cores(lira_index_t* h, int enable) {
 }
 int lira_index_last_path(const lira_index_t* h) { return h ? h->last_path : -1; }
 int lira_index_last_redo(const lira_index_t* h) { return h ? h->last_redo : -1; }
-int lira_index_tensor_core_eligible(const lira_index_t* h) { return h ? (h->tc_ok && h->ds <= TC_MAX_KB * KC ? 1 : 0) : -1; }
+int lira_index_tensor_core_eligible(const lira_index_t* h) { return h ? (h->tc_ok ? 1 : 0) : -1; }
 
 int lira_index_set_timing(lira_index_t* h, int enable) {
     LIRA_REQUIRE(h, "null index");

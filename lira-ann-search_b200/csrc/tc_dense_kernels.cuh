@@ -123,9 +123,9 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {   // small terms first, then the leading one
-                        tc_mma_tf32(d_tmem, tc_smem_desc(al + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC, (kb | j) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, tc_smem_desc(ah + j * 32), tc_smem_desc(bl + j * 32), TC_IDESC, 1u);
-                        tc_mma_tf32(d_tmem, tc_smem_desc(ah + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC, 1u);
+                        tc_mma_tf32(d_tmem, tc_smem_desc(al + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC_TF32, (kb | j) ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, tc_smem_desc(ah + j * 32), tc_smem_desc(bl + j * 32), TC_IDESC_TF32, 1u);
+                        tc_mma_tf32(d_tmem, tc_smem_desc(ah + j * 32), tc_smem_desc(bh + j * 32), TC_IDESC_TF32, 1u);
                     }
                     tc_commit(&empty[ps.stage]);
                 }

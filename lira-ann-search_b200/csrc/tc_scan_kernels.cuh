@@ -5,19 +5,22 @@
 //            probed list gives T[q], a valid upper bound of the final k-th best score (any k real
 //            candidates bound it).
 //   filter   this file: for a tile of 128 queries x one inverted list, D = Q_tile . V^T is computed by
-//            tcgen05.mma kind::tf32 straight from the fp32 rows that TMA staged in shared memory
+//            tcgen05.mma kind::f16 from the fp16 shadow copy of the list rows (exact for this data, see below; half
+//            the HBM / shared-memory bytes and twice the MMA rate of TF32) that TMA staged in shared memory
 //            (128-byte swizzle, K-major), accumulators in TMEM (4 x 128 columns, so the epilogue of one
 //            chunk overlaps the MMAs of the next three). Epilogue warps read their query row with
 //            tcgen05.ld and keep only the candidates with  |q|^2 + |v|^2 - 2 q.v <= T[q]
 //            (one FADD + compare per pair); survivors are appended to the query's candidate buffer.
 //   refine   per query: candidates -> exact top-k with id de-duplication.
 //
-// Exactness: this path is taken only when every stored vector and every query of the batch is exactly
-// representable in TF32 (e.g. SIFT / BigANN-style small integers). Then every product and partial sum
-// is an integer below 2^24, the tensor-core result equals the fp32 direct-difference result bit for
-// bit, and ids and distances are identical to the CUDA-core path. Other data keeps the exact
-// CUDA-core scan (scan_kernels.cuh).
+// Exactness: this path is taken only when every stored value and every query value of the batch is an
+// integer of at most 11 bits (exactly representable in fp16, e.g. SIFT / BigANN-style data) and
+// |x|^2 < 2^22. Then every product and partial sum is an integer below 2^24, the tensor-core result
+// (fp16 operands, fp32 accumulation) equals the fp32 direct-difference result bit for bit, and ids and
+// distances are identical to the CUDA-core path. Other data keeps the exact CUDA-core scan
+// (scan_kernels.cuh).
 #pragma once
+#include <cuda_fp16.h>
 #include "scan_kernels.cuh"
 
 namespace lira {
@@ -28,16 +31,18 @@ static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128
 static constexpr int TC_NSLOT = 4;       // B ring slots; a slot = up to TC_SLOT_KB K blocks of one chunk (32 KiB) + its augmented-K box
 static constexpr int TC_SLOT_KB = 2;     //   (one barrier round trip per 8-9 MMAs instead of per 4)
 static constexpr int TC_NABUF = 1;       // A tile buffers (64 KiB each)
-static constexpr int TC_MAX_KB = 4;      // K blocks of 32 floats resident per A tile: d <= 128
+static constexpr int TC_KH = 64;         // fp16 values per K block (one 128-byte swizzle row)
+static constexpr int TC_MAX_KB = 4;      // K blocks of 64 halves resident per A tile: d <= 256
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
-static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 8 floats
+static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 16 halves
 static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * B_STAGE_BYTES + TC_AUG_BYTES;   // 36 KiB
 static constexpr int TC_THREADS = 384;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer, warp 10 TMEM alloc
 static constexpr int TC_W_PROD = 8, TC_W_MMA = 9, TC_W_ALLOC = 10;
 static constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant, each takes half of the 128 accumulator columns
 
-static constexpr int TC_CB = 16;         // a row's best survivors kept in a sorted register chain (k <= 16)
-static constexpr int TC_CAPP = 64;       // candidate slots per (query, list) pair and column half (16 used when k <= 16)
+static constexpr int TC_CAPK = 32;       // k <= 16: candidate slots per (query, list, column half) region; a full region is
+                                         //          compacted in place to its k best by the whole warp (one key per lane)
+static constexpr int TC_CAPP = 64;       // k > 16: slots per region, no compaction (overflow -> the query is redone exactly)
 
 static constexpr size_t TC_SMEM_BYTES = (size_t)TC_NABUF * TC_MAX_KB * TC_KBLK_BYTES   // A tile
                                         + (size_t)TC_NSLOT * TC_SLOT_BYTES              // B ring
@@ -52,7 +57,7 @@ struct TcParams {
     const ScanItem* items;           // tiles of up to 128 queries, most expensive first
     const int* n_items;
     int* work_counter;               // zeroed before launch: dynamic item scheduler
-    int nk;                          // K blocks (ceil(d / 32)), <= TC_MAX_KB
+    int nk;                          // K blocks (ceil(d / 64)), <= TC_MAX_KB
     int max_rows;                    // > 0: only the first max_rows entries of each list (seed pass)
     const float* qnorm;              // [Q] |q|^2
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
@@ -62,6 +67,7 @@ struct TcParams {
     int cap;
     int k;
     int is_ip;
+    int exp;                         // experiments (LIRA_TC_EXP): bit 0 = skip the survivor path (wrong results, timing only)
     long long* trace;                // debug (LIRA_TC_TRACE): [TC_TRACE_ROLES][TC_TRACE_CHUNKS] SM clock stamps of CTA 0, or null
 };
 
@@ -78,11 +84,18 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// K-major, 32-byte swizzle: rows of 32 B (one K = 8 TF32 step), 8-row groups 256 B apart (SBO)
+// K-major, 32-byte swizzle: rows of 32 B (one K = 16 fp16 step), 8-row groups 256 B apart (SBO)
 __device__ __forceinline__ uint64_t tc_smem_desc_sw32(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
@@ -110,8 +123,9 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// instruction descriptors: D = F32, A = B = F16 (format 0) resp. TF32 (format 2), both K-major, N = 128, M = 128
+static constexpr uint32_t TC_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+static constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / epilogue)
 static constexpr int TC_G = 64;   // seed pass: group minima per row
@@ -168,7 +182,7 @@ __device__ __forceinline__ float tc_max32(const uint32_t (&r)[32], float (&m4)[8
     return fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
 }
 
-template <bool SEED>
+template <bool SEED, bool TRACE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
                const __grid_constant__ CUtensorMap tmap_vaug, const __grid_constant__ CUtensorMap tmap_aaug, const TcParams p) {
@@ -220,12 +234,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     };
     // debug timeline of CTA 0: one clock stamp per (role, chunk)
     auto stamp = [&](int role, uint32_t chunk) {
-        if (p.trace && blockIdx.x == 0 && chunk < TC_TRACE_CHUNKS && lane == 0) p.trace[role * TC_TRACE_CHUNKS + chunk] = clock64();
+        if constexpr (TRACE) {
+            if (p.trace && blockIdx.x == 0 && chunk < TC_TRACE_CHUNKS && lane == 0) p.trace[role * TC_TRACE_CHUNKS + chunk] = clock64();
+        }
     };
 
     if (warp == TC_W_PROD) {
         // ===== scheduler + TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one) =====
-        if (aug) {   // the constant augmented-K block of A: every row is (-1, -1, 0, ..., 0)
+        if (aug) {   // the constant augmented-K block of A: every row is (-2048, -1, 0, ..., 0)
             if (elect_one()) {
                 mbar_arrive_expect_tx(ga_full, TC_AUG_BYTES);
                 tma_load_2d(sGA, &tmap_aaug, 0, 0, ga_full);
@@ -251,7 +267,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
                 for (int kb = 0; kb < nk; ++kb)
-                    tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * KC, it.q_begin, &a_full[ab]);
+                    tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * TC_KH, it.q_begin, &a_full[ab]);
             }
             __syncwarp();
             long long lo, hi;
@@ -266,7 +282,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         uint8_t* slot = sB + (size_t)bs.stage * TC_SLOT_BYTES;
                         mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nkb * B_STAGE_BYTES + (with_aug ? TC_AUG_BYTES : 0));
                         for (int j = 0; j < nkb; ++j)
-                            tma_load_2d(slot + (size_t)j * B_STAGE_BYTES, &tmap_v, (kb0 + j) * KC, (int)row0, &b_full[bs.stage]);
+                            tma_load_2d(slot + (size_t)j * B_STAGE_BYTES, &tmap_v, (kb0 + j) * TC_KH, (int)row0, &b_full[bs.stage]);
                         if (with_aug) tma_load_2d(slot + TC_SLOT_KB * B_STAGE_BYTES, &tmap_vaug, 0, (int)row0, &b_full[bs.stage]);
                     }
                     __syncwarp();
@@ -308,13 +324,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const uint32_t slot = sB_u32 + (uint32_t)bs.stage * TC_SLOT_BYTES;
                     if (elect_one()) {
                         if (aug && kb0 == 0)   // s = -|v|^2 ...
-                            tc_mma_tf32(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * B_STAGE_BYTES), TC_IDESC, 0u);
+                            tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * B_STAGE_BYTES), TC_IDESC_F16, 0u);
                         for (int jb = 0; jb < nkb; ++jb) {   // ... + (2 q) . v
                             const uint32_t a_addr = sA_u32 + (uint32_t)(ab * TC_MAX_KB + kb0 + jb) * TC_KBLK_BYTES;
                             const uint32_t b_addr = slot + (uint32_t)jb * B_STAGE_BYTES;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)  // 4 x K = 8 tf32 (32 bytes) inside the 128-byte swizzle row
-                                tc_mma_tf32(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC,
+                            for (int j = 0; j < 4; ++j)  // 4 x K = 16 fp16 (32 bytes) inside the 128-byte swizzle row
+                                tc_mma_f16(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC_F16,
                                             (aug || kb0 || jb || j) ? 1u : 0u);
                         }
                         tc_commit(&b_empty[bs.stage]);  // frees the slot when these MMAs have read it
@@ -335,13 +351,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // accumulator of the work item. With t = -s (t = score - |q|^2 for L2, t = score for IP; smaller is
         // better) the filter keeps t <= tq. The hot loop is a 3-input-max tree over the raw accumulator values and
         // ONE compare per 32 columns (FMNMX3 only: the norms are already inside the accumulator). About one pair in
-        // a thousand survives, i.e. a good part of a warp's 32-column groups hold one, so the survivor path is
-        // straight-line too: a lane picks its first passing 4-column block with a select tree (no dynamic
-        // register indexing) and inserts the passing entries into its SORTED 16-entry register chain (the exact
-        // running top-16 of its (query, list, half)); the chain's k-th element tightens the row's bound at once
-        // and is published (atomicMin) for the query's rows in other lists and CTAs, which re-read it every chunk.
-        // At the end of the item the chain goes to the thread's PRIVATE candidate region: plain stores, no
-        // atomics, no shared staging.
+        // a thousand survives, i.e. a good part of a warp's 32-column groups hold one, but a thread sees only one
+        // or two survivors per list. So the survivor path is kept short and warp-uniform: a lane picks its next
+        // passing 4-column block with a select tree (no dynamic register indexing) and APPENDS the passing entries
+        // to its PRIVATE candidate region in global memory (plain stores, no atomics, no shared staging, nothing
+        // kept in registers). Only a region that fills up (k <= 16: 32 slots) is compacted, by the whole warp, to
+        // its k best entries in sorted order; its k-th score is then an exact bound for the row and is published
+        // (atomicMin) for the query's rows in other lists and CTAs, which re-read it every chunk.
         // (the seed pass has no survivor path and one bound per ROW to produce: it runs on 4 warps that take all
         //  128 columns, so the 64 group minima of a row cover all its 1024 seed entries)
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -349,6 +365,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
         constexpr int NG = SEED ? TC_N / 32 : TC_N / 64;   // 32-column groups per thread and chunk
         constexpr int NCOL = SEED ? TC_N : TC_N / 2;       // columns per thread and chunk
+        const bool keep_mode = p.k <= TC_KMAX_TIGHTEN;
+        const int cap = p.cap;
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -363,32 +381,28 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             float gmin[SEED ? TC_G : 1];
 #pragma unroll
             for (int g = 0; g < (SEED ? TC_G : 1); ++g) gmin[g] = INFINITY;
-            // k <= 16: the row's 16 best survivors so far, ascending in t (exact running top-16 of this thread's
-            // (query, list, half)); t16[k-1] is then an exact bound and is folded into tq after every insertion
-            float t16[TC_CB];
-            uint32_t e16[TC_CB];
-#pragma unroll
-            for (int j = 0; j < TC_CB; ++j) { t16[j] = INFINITY; e16[j] = 0; }
-            bool lost = false;     // an entry that still passed the bound fell off the chain: redo the query exactly
-            const bool keep_mode = p.k <= TC_KMAX_TIGHTEN;
+            bool lost = false;     // a tie at the bound fell out of a compacted region: redo the query exactly
             unsigned long long* cand = nullptr;
+            const volatile uint32_t* thr_q = p.thr;   // (rows past the end of the tile read thr[0]; their tq stays -inf)
+            uint32_t thr_pref = 0xFF800000u;
             if (row_ok) {
                 q = __ldg(p.group_queries + it.q_begin + row);
                 if (!p.is_ip) qn = __ldg(p.qnorm + q);
                 if (!SEED) {
-                    const float T = ordered_to_f32(*reinterpret_cast<volatile uint32_t*>(p.thr + q));
-                    tq = T - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
-                    cand = p.cand_key + ((size_t)(it.q_begin + row) * 2 + half) * p.cap;
+                    thr_q = p.thr + q;
+                    thr_pref = *thr_q;
+                    tq = ordered_to_f32(thr_pref) - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
+                    cand = p.cand_key + ((size_t)(it.q_begin + row) * 2 + half) * cap;
                 }
             }
             long long lo, hi;
             item_rows(it, lo, hi);
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
-                // pick up the bound the query's rows in other lists / CTAs have published meanwhile (issued before
-                // the wait so that its latency is hidden behind it)
-                uint32_t thr_now = 0xFF800000u;
-                if (!SEED && row_ok) thr_now = *reinterpret_cast<volatile uint32_t*>(p.thr + q);
+                // the bound the query's rows in other lists / CTAs have published meanwhile: the value loaded one
+                // chunk ago is used now and the next one is requested, so the load latency is never waited for
+                const uint32_t thr_now = thr_pref;
+                if (!SEED) thr_pref = *thr_q;
                 mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
                 tc_fence_after();
                 if (warp == 0) stamp(5, m);
@@ -399,7 +413,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_ld32_async(taddr + 32, rb);
                 tc_ld_wait(ra);   // (waits for both loads)
                 tc_ld_wait(rb);
-                if (!SEED && row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
+                if (!SEED) {
+                    // the thread's 64 columns are in registers: hand the accumulator back to the MMA warp at once
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[acc]);
+                    if (row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
+                }
                 // columns past the end of the list hold other lists' vectors: valid columns of this thread's range
                 const int n_valid = (int)min((long long)NCOL, hi - row0 - half * 64);
 #pragma unroll
@@ -422,65 +442,75 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             gmin[(g * 32 + c) & (TC_G - 1)] = fminf(gmin[(g * 32 + c) & (TC_G - 1)], -__uint_as_float(r[c]));
-                    } else if (__any_sync(0xffffffffu, -mx <= tq)) {
+                    } else if (__any_sync(0xffffffffu, -mx <= tq) && !(p.exp & 1)) {
                         // (tq = -inf for rows past the end of the tile, so they never pass)
-                        uint32_t qm = 0;
+                        uint32_t qm = 0;   // passing 4-column blocks of this lane still to look at
 #pragma unroll
                         for (int i = 0; i < 8; ++i) qm |= (-m4[i] <= tq) ? (1u << i) : 0u;
-                        do {
-                            const int j = __ffs(qm) - 1;   // -1: nothing (left) for this lane
-                            qm &= qm - 1;
-                            float s4[4];
+                        uint32_t pm = 0;   // passing entries of the current block still to append
+                        uint32_t e0 = 0;
+                        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                        do {   // one round = at most one new block and one appended entry per lane; the warp stays converged
+                            const int j = (pm == 0) ? __ffs(qm) - 1 : -1;   // -1: no new block for this lane in this round
+                            if (pm == 0) qm &= qm - 1;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const uint32_t x0 = (j & 1) ? r[4 + u] : r[u], x1 = (j & 1) ? r[12 + u] : r[8 + u];
                                 const uint32_t x2 = (j & 1) ? r[20 + u] : r[16 + u], x3 = (j & 1) ? r[28 + u] : r[24 + u];
                                 const uint32_t y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
-                                s4[u] = -__uint_as_float((j & 4) ? y1 : y0);
+                                const float v = -__uint_as_float((j & 4) ? y1 : y0);
+                                s4[u] = (j >= 0) ? v : s4[u];
+                                pm |= (j >= 0 && v <= tq) ? (1u << u) : 0u;
                             }
-                            uint32_t pm = 0;
-                            if (j >= 0) {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) pm |= (s4[u] <= tq) ? (1u << u) : 0u;
-                            }
-                            const uint32_t e0 = (uint32_t)(row0 + half * 64 + g * 32 + j * 4);
-                            while (pm) {
+                            e0 = (j >= 0) ? (uint32_t)(row0 + half * 64 + g * 32 + j * 4) : e0;
+                            if (pm) {
                                 const int u = __ffs(pm) - 1;
                                 pm &= pm - 1;
                                 const float x = (u & 2) ? ((u & 1) ? s4[3] : s4[2]) : ((u & 1) ? s4[1] : s4[0]);
-                                if (!(x <= tq) || !(x < INFINITY)) continue;   // the bound may have tightened inside this block; masked columns
-                                if (!keep_mode) {   // k > 16: every survivor goes to the region (overflow -> exact redo)
-                                    if (cnt < p.cap) cand[cnt] = make_key(x + qn, e0 + u);
-                                    ++cnt;
-                                    continue;
+                                // (the bound may have tightened since the block was looked at; masked columns are +inf)
+                                if (x <= tq && x < INFINITY) {
+                                    if (cnt < cap) cand[cnt] = make_key(x + qn, e0 + u);
+                                    ++cnt;   // k > 16: may run past cap -> the query is redone exactly
                                 }
-                                const uint32_t e = e0 + u;
-                                const float vout = fmaxf(x, t16[TC_CB - 1]);   // what leaves (or never enters) the chain
-#pragma unroll
-                                for (int i = TC_CB - 1; i > 0; --i) {
-                                    const bool sh = x < t16[i - 1], in = x < t16[i];
-                                    e16[i] = sh ? e16[i - 1] : (in ? e : e16[i]);
-                                    t16[i] = sh ? t16[i - 1] : (in ? x : t16[i]);
-                                }
-                                {
-                                    const bool in = x < t16[0];
-                                    e16[0] = in ? e : e16[0];
-                                    t16[0] = in ? x : t16[0];
-                                }
-                                const float tk = tc_pick16(t16, p.k - 1);
-                                if (tk < tq) {
-                                    tq = tk;
-                                    atomicMin(p.thr + q, f32_to_ordered(tk + qn));
-                                }
-                                lost |= (vout <= tq) && (vout < INFINITY);
                             }
-                        } while (__any_sync(0xffffffffu, qm != 0));
+                            if (keep_mode) {
+                                // a full region (32 keys, one per lane) -> its k best, in sorted order, by the whole warp
+                                uint32_t fm = __ballot_sync(0xffffffffu, cnt >= TC_CAPK);
+                                while (fm) {
+                                    const int L = __ffs(fm) - 1;
+                                    fm &= fm - 1;
+                                    __syncwarp();   // lane L's stores are visible to the warp
+                                    unsigned long long* reg = (unsigned long long*)shfl_u64((unsigned long long)cand, L);
+                                    const unsigned long long key = __ldcg(reg + lane);
+                                    int rank = 0;   // keys of one region are distinct (distinct list entries)
+#pragma unroll 8
+                                    for (int i = 0; i < 32; ++i) rank += (shfl_u64(key, i) < key) ? 1 : 0;
+                                    __syncwarp();   // every lane holds its key before the region is rewritten
+                                    const uint32_t sc = (uint32_t)(key >> 32);   // ordered score bits
+                                    const uint32_t mk = __ballot_sync(0xffffffffu, rank == p.k - 1);
+                                    const uint32_t sk = __shfl_sync(0xffffffffu, sc, __ffs(mk) - 1);     // k-th best score
+                                    // kept: everything at or below the k-th score (ties stay, their id order is settled by
+                                    // the refine pass); ranks are the sorted order, so the kept keys are ranks 0 .. n_keep-1
+                                    const bool keep = sc <= sk;
+                                    if (keep) reg[rank] = key;
+                                    const int n_keep = __popc(__ballot_sync(0xffffffffu, keep));
+                                    if (lane == L) {
+                                        cnt = n_keep;
+                                        if (n_keep >= TC_CAPK - 4) { lost = true; cnt = p.k; }   // (nearly) all ties: give the query up
+                                        tq = fminf(tq, ordered_to_f32(sk) - qn);
+                                        atomicMin(p.thr + q, sk);
+                                    }
+                                    __syncwarp();
+                                }
+                            }
+                        } while (__any_sync(0xffffffffu, (qm | pm) != 0));
                     }
                 }
-                // this warp is done with the accumulator
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (SEED) {   // this warp is done with the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[acc]);
+                }
                 if (warp == 0) stamp(6, m);
                 if (warp == 5) stamp(8, m);
             }
@@ -501,14 +531,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     atomicMin(p.thr + q, f32_to_ordered(tk + qn));
                 }
             } else if (row_ok) {
-                if (keep_mode) {
-                    cnt = 0;
-#pragma unroll
-                    for (int i = 0; i < TC_CB; ++i)
-                        if (t16[i] <= tq && t16[i] < INFINITY) cand[cnt++] = make_key(t16[i] + qn, e16[i]);
-                    if (lost) cnt = p.cap + 1;
-                }
-                p.cand_count[(size_t)(it.q_begin + row) * 2 + half] = cnt;
+                p.cand_count[(size_t)(it.q_begin + row) * 2 + half] = lost ? cap + 1 : cnt;
             }
         }
     }
@@ -522,12 +545,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 // ---- helpers around the filter --------------------------------------------------------------------
 // |x|^2 per row in fp32 (sequential order); *exact_flag is cleared unless every value is an integer of at
-// most 11 bits (exact in TF32) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
-// path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit
-// vaug (may be null): the row's augmented-K block [hi, lo, 0, 0, 0, 0, 0, 0] with |x|^2 = hi + lo, hi a multiple of 2048
-// and lo < 2048, i.e. both exact in TF32 when |x|^2 is an integer below 2^22.
+// most 11 bits (exact in fp16) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
+// path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit.
+// vaug (may be null): the row's augmented-K block [hi, lo, 0 x 14] in fp16 with |x|^2 = 2048 hi + lo, hi and lo
+// integers below 2048 (exact in fp16) when |x|^2 is an integer below 2^22; the A side holds (-2048, -1, 0 ...).
+// x16 (may be null): the fp16 shadow copy of the rows, [n, d16] with zero padding (d16 % 8 == 0).
 __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, long long n, float* __restrict__ out,
-                                 int* __restrict__ exact_flag, float* __restrict__ vaug) {
+                                 int* __restrict__ exact_flag, __half* __restrict__ vaug, __half* __restrict__ x16, int d16) {
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float* r = x + i * ld;
@@ -537,31 +561,47 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
             s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
             bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
             bad |= !(fabsf(v.x) <= 2047.f && fabsf(v.y) <= 2047.f && fabsf(v.z) <= 2047.f && fabsf(v.w) <= 2047.f);
+            if (x16) {
+                __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(x16 + i * d16 + j) = pk;
+            }
         }
+        if (x16)
+            for (int j = d; j < d16; j += 4) *reinterpret_cast<uint2*>(x16 + i * d16 + j) = make_uint2(0u, 0u);
         out[i] = s;
         if (vaug) {
-            const float hi = floorf(s * (1.0f / 2048.0f)) * 2048.0f;
-            *reinterpret_cast<float4*>(vaug + i * 8) = make_float4(hi, s - hi, 0.f, 0.f);
-            *reinterpret_cast<float4*>(vaug + i * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float hi = floorf(s * (1.0f / 2048.0f));
+            __half2 h = __floats2half2_rn(hi, s - hi * 2048.0f);
+            uint4 w = make_uint4(*reinterpret_cast<uint32_t*>(&h), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(vaug + i * 16) = w;
+            *reinterpret_cast<uint4*>(vaug + i * 16 + 8) = make_uint4(0u, 0u, 0u, 0u);
         }
         bad |= !(s < 4194304.0f);  // |x|^2 < 2^22  =>  |q|^2 + |v|^2 + 2|q.v| < 2^24
     }
     if (bad && exact_flag) *exact_flag = 0;
 }
 
-// gq[slot, :] = q[group_queries[slot], :]  (queries in group order, so a tile of a group is one TMA box)
-// n_slots (device scalar = group_offsets[B]) is the number of valid slots: explicit probe sets may hold invalid
-// (-1) entries, so it can be smaller than the host-side bound P the buffers were sized with.
+// gq[slot, :] = fp16(scale * q[group_queries[slot], :])  (queries in group order, so a tile of a group is one TMA box;
+// zero padded to d16 columns). n_slots (device scalar = group_offsets[B]) is the number of valid slots: explicit probe
+// sets may hold invalid (-1) entries, so it can be smaller than the host-side bound P the buffers were sized with.
 __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
-                                            long long P, const long long* __restrict__ n_slots, float* __restrict__ gq, float scale) {
-    const int per_row = ds / 4;
+                                            long long P, const long long* __restrict__ n_slots, __half* __restrict__ gq, int d16,
+                                            float scale) {
+    const int per_row = d16 / 4;
     const long long total = (*n_slots < P ? *n_slots : P) * per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long s = i / per_row;
         const int c = (int)(i % per_row) * 4;
-        float4 v = *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
-        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-        *reinterpret_cast<float4*>(gq + s * ds + c) = v;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ds) v = *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+        __half2 h0 = __floats2half2_rn(v.x * scale, v.y * scale), h1 = __floats2half2_rn(v.z * scale, v.w * scale);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(gq + s * d16 + c) = pk;
     }
 }
 

@@ -313,6 +313,29 @@ def test_tensor_core_scan_is_bit_identical(L, metric, k, d):
     assert np.array_equal(I0, I0_ref) and np.array_equal(D0, D0_ref)
 
 
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("k", [1, 10, 16])
+def test_tensor_core_region_compaction_without_seed(L, metric, k, monkeypatch):
+    """Every bound starts at +inf (seed pass skipped): each (query, list, half) region fills up and is compacted in the
+    kernel again and again, duplicated vectors put ties at the bound (-> exact redo). Results must not change."""
+    monkeypatch.setenv("LIRA_TC_NO_SEED", "1")
+    rng = np.random.RandomState(5 + k)
+    x_d, x_q = synth(20000, 64, 600, seed=77, integer=True)
+    x_d[1000:1400] = x_d[600:1000]  # exact duplicates under different ids: ties everywhere
+    B = 6
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(x_d, cl)
+    nprobe = rng.randint(1, 5, len(x_q))
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    pids = np.concatenate([rng.choice(B, n, replace=False) for n in nprobe]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    D, I, cmp_ = index.search(x_q, poff, pids, k)
+    assert index.last_path == "tensor-core"
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
+
+
 def test_tensor_core_path_is_not_taken_for_inexact_data(L):
     x_d, x_q = synth(8000, 32, 300, seed=8, integer=False)  # real-valued: not exact in TF32
     cl = random_lists(len(x_d), 8, np.random.RandomState(1))
