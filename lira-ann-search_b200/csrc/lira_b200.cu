@@ -679,7 +679,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.is_ip = h->metric == LIRA_METRIC_IP;
         // (LIRA_TC_NO_SEED, tests only: every bound starts at +inf, so the in-kernel region compaction does all the work)
         if (!getenv("LIRA_TC_NO_SEED")) {
-            tc_scan_kernel<true, false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
+            tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(tmap_sq, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
             LIRA_LAUNCH_CHECK();
         }
     } else {
@@ -708,10 +708,10 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     CUtensorMap tmap_q;
     if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
     // ---- filter on the tensor cores ----
-    // one private candidate region per (pair, column half); every valid pair's owner writes its count
+    // one private candidate region per (pair, column part); every valid pair's owner writes its count
     const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
-    if (int rc = ws.cand_key.ensure((size_t)P * 2 * cap * 8)) return rc;
-    if (int rc = ws.cand_count.ensure((size_t)P * 2 * 4)) return rc;
+    if (int rc = ws.cand_key.ensure((size_t)P * TC_PARTS * cap * 8)) return rc;
+    if (int rc = ws.cand_count.ensure((size_t)P * TC_PARTS * 4)) return rc;
     TcParams tp;
     tp.group_queries = ws.group_queries.as<int>();
     tp.list_offsets = h->d_offsets;
@@ -736,8 +736,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         tp.trace = ws.trace.as<long long>();
     }
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
-    else tc_scan_kernel<false, false><<<h->num_sms, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
@@ -763,14 +763,14 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         }
     }
     if (getenv("LIRA_DEBUG")) {
-        std::vector<int> cc((size_t)P * 2);
-        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * 2 * 4, cudaMemcpyDeviceToHost);
+        std::vector<int> cc((size_t)P * TC_PARTS);
+        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * TC_PARTS * 4, cudaMemcpyDeviceToHost);
         std::vector<int> sorted(cc);
         std::sort(sorted.begin(), sorted.end());
         long long tot = 0;
         for (int c : cc) tot += c;
-        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, half) p50 %d p99 %d max %d; redo %d\n",
-                Q, P, (double)tot / Q, sorted[P], sorted[(size_t)(P * 2 * 0.99)], sorted[P * 2 - 1], *n_redo);
+        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, part) p50 %d p99 %d max %d; redo %d\n",
+                Q, P, (double)tot / Q, sorted[P * TC_PARTS / 2], sorted[(size_t)(P * TC_PARTS * 0.99)], sorted[P * TC_PARTS - 1], *n_redo);
     }
     h->last_path = 1;
     h->last_redo = *n_redo;

@@ -30,26 +30,36 @@ static constexpr int TC_N = 128;         // vectors per chunk (UMMA N, TMEM colu
 static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128 = 512 columns)
 static constexpr int TC_NSLOT = 4;       // B ring slots; a slot = up to TC_SLOT_KB K blocks of one chunk (32 KiB) + its augmented-K box
 static constexpr int TC_SLOT_KB = 2;     //   (one barrier round trip per 8-9 MMAs instead of per 4)
-static constexpr int TC_NABUF = 1;       // A tile buffers (64 KiB each)
+static constexpr int TC_A_KB = 4;        // K blocks of A storage: one tile of d <= 256, or two tiles (double buffered) of d <= 128
 static constexpr int TC_KH = 64;         // fp16 values per K block (one 128-byte swizzle row)
 static constexpr int TC_MAX_KB = 4;      // K blocks of 64 halves resident per A tile: d <= 256
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
 static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 16 halves
 static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * B_STAGE_BYTES + TC_AUG_BYTES;   // 36 KiB
-static constexpr int TC_THREADS = 384;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer, warp 10 TMEM alloc
-static constexpr int TC_W_PROD = 8, TC_W_MMA = 9, TC_W_ALLOC = 10;
-static constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant, each takes half of the 128 accumulator columns
+static constexpr int TC_PARTS = 4;       // filter pass: column parts per accumulator = epilogue warps per TMEM lane quadrant
+static constexpr int TC_EPI_WARPS = 4 * TC_PARTS;   // filter pass: each epilogue warp takes 128 / TC_PARTS accumulator columns
+static constexpr int TC_SEED_EPI_WARPS = 4;         // seed pass: one warp per quadrant takes all 128 columns
+// warp roles: epilogue warps first (a warp may only touch the TMEM lanes 32 (w % 4) .. +31), then the TMA producer,
+// the MMA issuer and the TMEM allocator
+__host__ __device__ constexpr int tc_w_prod(bool seed) { return seed ? 8 : TC_EPI_WARPS; }
+__host__ __device__ constexpr int tc_threads(bool seed) { return (tc_w_prod(seed) + 3) * 32; }
 
-static constexpr int TC_CAPK = 32;       // k <= 16: candidate slots per (query, list, column half) region; a full region is
+static constexpr int TC_CAPK = 32;       // k <= 16: candidate slots per (query, list, column part) region; a full region is
                                          //          compacted in place to its k best by the whole warp (one key per lane)
 static constexpr int TC_CAPP = 64;       // k > 16: slots per region, no compaction (overflow -> the query is redone exactly)
 
-static constexpr size_t TC_SMEM_BYTES = (size_t)TC_NABUF * TC_MAX_KB * TC_KBLK_BYTES   // A tile
+static constexpr size_t TC_SMEM_BYTES = (size_t)TC_A_KB * TC_KBLK_BYTES                  // A tile(s)
                                         + (size_t)TC_NSLOT * TC_SLOT_BYTES              // B ring
                                         + (size_t)TC_AUG_BYTES                          // the constant augmented-K block of A
                                         + 512;                                          // barriers, item queue, tmem slot
 
 static constexpr int TC_TRACE_ROLES = 9, TC_TRACE_CHUNKS = 512;
+
+// work-item queue entry (scheduler -> MMA / epilogue warps): the tile and its row range of the list
+struct TcQItem {
+    int list, q_begin, q_count, pad;
+    long long lo, hi;
+};
 
 struct TcParams {
     const int* group_queries;        // [P] query id per slot
@@ -62,8 +72,8 @@ struct TcParams {
     const float* qnorm;              // [Q] |q|^2
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score, as f32_to_ordered(T): written by the
                                      //     seed pass, read AND tightened (atomicMin) by the filter pass
-    unsigned long long* cand_key;    // [2 P, cap] (score, list entry) keys: one private region per (pair, column half)
-    int* cand_count;                 // [2 P] survivors of the region's owner (may exceed cap: the query is then redone)
+    unsigned long long* cand_key;    // [TC_PARTS P, cap] (score, list entry) keys: one private region per (pair, column part)
+    int* cand_count;                 // [TC_PARTS P] survivors of the region's owner (may exceed cap: the query is then redone)
     int cap;
     int k;
     int is_ip;
@@ -183,13 +193,13 @@ __device__ __forceinline__ float tc_max32(const uint32_t (&r)[32], float (&m4)[8
 }
 
 template <bool SEED, bool TRACE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(SEED), 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
                const __grid_constant__ CUtensorMap tmap_vaug, const __grid_constant__ CUtensorMap tmap_aaug, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    uint8_t* sA = smem_raw;                                              // [TC_NABUF][TC_MAX_KB][128 x 128 B]
-    uint8_t* sB = sA + (size_t)TC_NABUF * TC_MAX_KB * TC_KBLK_BYTES;     // [TC_NSLOT]{[TC_SLOT_KB][128 x 128 B], [128 x 32 B] aug}
+    uint8_t* sA = smem_raw;                                              // [nabuf][TC_A_KB / nabuf][128 x 128 B]
+    uint8_t* sB = sA + (size_t)TC_A_KB * TC_KBLK_BYTES;     // [TC_NSLOT]{[TC_SLOT_KB][128 x 128 B], [128 x 32 B] aug}
     uint8_t* sGA = sB + (size_t)TC_NSLOT * TC_SLOT_BYTES;                // [128 x 32 B] constant augmented-K block of A
     uint64_t* bars = (uint64_t*)(sGA + TC_AUG_BYTES);
     uint64_t* a_full = bars;                        // [2]
@@ -201,16 +211,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint64_t* i_full = t_empty + TC_NACC;           // [TC_NQ]
     uint64_t* i_empty = i_full + TC_NQ;             // [TC_NQ]
     uint64_t* ga_full = i_empty + TC_NQ;            // [1]
-    ScanItem* iq = (ScanItem*)(ga_full + 1);        // [TC_NQ]
+    TcQItem* iq = (TcQItem*)(ga_full + 1);          // [TC_NQ]
     uint32_t* tmem_slot = (uint32_t*)(iq + TC_NQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TC_W_PROD = tc_w_prod(SEED), TC_W_MMA = TC_W_PROD + 1, TC_W_ALLOC = TC_W_PROD + 2;
+    constexpr int N_EPI = SEED ? TC_SEED_EPI_WARPS : TC_EPI_WARPS;
     const bool aug = !p.is_ip;   // inner product: the accumulator is q.v itself, no augmented block
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], SEED ? 4 : TC_EPI_WARPS); }
-        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 1 + (SEED ? 4 : TC_EPI_WARPS)); }  // MMA + epilogue warps
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], N_EPI); }
+        for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 1 + N_EPI); }  // MMA + epilogue warps
         mbar_init(ga_full, 1);
         mbar_fence_init();
     }
@@ -225,13 +237,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     const int n_items = *p.n_items;
     const int nk = p.nk;
+    // A tiles: with d <= 128 (nk <= 2) two query tiles fit, so the next work item's queries load while this item's MMAs run
+    const int nabuf = nk <= TC_A_KB / 2 ? 2 : 1;
+    const int a_kb = TC_A_KB / nabuf;
 
-    // list range of an item, clipped for the seed pass
-    auto item_rows = [&](const ScanItem& it, long long& lo, long long& hi) {
-        lo = p.list_offsets[it.list];
-        hi = p.list_offsets[it.list + 1];
-        if (p.max_rows > 0 && hi - lo > p.max_rows) hi = lo + p.max_rows;
-    };
     // debug timeline of CTA 0: one clock stamp per (role, chunk)
     auto stamp = [&](int role, uint32_t chunk) {
         if constexpr (TRACE) {
@@ -250,30 +259,58 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         PipeState bs{0, 0};
         uint32_t mp = 0;
+        // Dynamic scheduler, ONE work item ahead (more would hurt the balance at the tail: an item is ~10 % of a
+        // CTA's share). The three dependent global round trips that describe the next item -- ticket (atomicAdd),
+        // descriptor, list range -- are issued at chunks 0, 2 and 4 of the current item, each consuming the result
+        // of the previous one, so none of them is ever waited for between two items.
+        auto ticket = [&]() { return lane == 0 ? atomicAdd(p.work_counter, 1) : 0; };
+        auto descriptor = [&](int t) {
+            const int idx = __shfl_sync(0xffffffffu, t, 0);
+            ScanItem d;
+            if (idx < n_items) d = p.items[idx];
+            else { d.list = -1; d.q_begin = 0; d.q_count = 0; d.tm = 0; }
+            return d;
+        };
+        auto with_rows = [&](const ScanItem& d) {
+            TcQItem o;
+            o.list = d.list; o.q_begin = d.q_begin; o.q_count = d.q_count; o.pad = 0;
+            o.lo = 0; o.hi = 0;
+            if (d.list >= 0) {
+                o.lo = p.list_offsets[d.list];
+                o.hi = p.list_offsets[d.list + 1];
+                if (p.max_rows > 0 && o.hi - o.lo > p.max_rows) o.hi = o.lo + p.max_rows;   // seed pass
+            }
+            return o;
+        };
+        TcQItem cur = with_rows(descriptor(ticket()));
         for (int n = 0;; ++n) {
-            int idx = 0;
-            if (lane == 0) idx = atomicAdd(p.work_counter, 1);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
-            ScanItem it;
-            if (idx < n_items) it = p.items[idx];
-            else { it.list = -1; it.q_begin = 0; it.q_count = 0; it.tm = 0; }
+            const TcQItem it = cur;
             const int qs = n % TC_NQ;
             mbar_wait(&i_empty[qs], ((n / TC_NQ) & 1) ^ 1u);
             if (lane == 0) { iq[qs] = it; mbar_arrive(&i_full[qs]); }
             __syncwarp();
             if (it.list < 0) break;
-            const int ab = n % TC_NABUF;
-            mbar_wait(&a_empty[ab], ((n / TC_NABUF) & 1) ^ 1u);
+            int t_next = 0, stage = 0;     // next item: 0 nothing yet, 1 ticket requested, 2 descriptor requested, 3 complete
+            ScanItem d_next;
+            d_next.list = -1; d_next.q_begin = 0; d_next.q_count = 0; d_next.tm = 0;
+            auto advance_prefetch = [&]() {
+                if (stage == 0) t_next = ticket();
+                else if (stage == 1) d_next = descriptor(t_next);
+                else if (stage == 2) cur = with_rows(d_next);
+                ++stage;
+            };
+            const int ab = n % nabuf;
+            mbar_wait(&a_empty[ab], ((n / nabuf) & 1) ^ 1u);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
                 for (int kb = 0; kb < nk; ++kb)
-                    tma_load_2d(sA + (size_t)(ab * TC_MAX_KB + kb) * TC_KBLK_BYTES, &tmap_q, kb * TC_KH, it.q_begin, &a_full[ab]);
+                    tma_load_2d(sA + (size_t)(ab * a_kb + kb) * TC_KBLK_BYTES, &tmap_q, kb * TC_KH, it.q_begin, &a_full[ab]);
             }
             __syncwarp();
-            long long lo, hi;
-            item_rows(it, lo, hi);
+            const long long lo = it.lo, hi = it.hi;
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++mp) {
                 stamp(0, mp);
+                if (stage < 3 && (((row0 - lo) / TC_N) & 1) == 0) advance_prefetch();
                 for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug box with the first)
                     const int nkb = min(TC_SLOT_KB, nk - kb0);
                     const bool with_aug = aug && kb0 == 0;
@@ -289,6 +326,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     bs.advance(TC_NSLOT);
                 }
             }
+            while (stage < 3) advance_prefetch();   // short list: the rest of the look-ahead (waited for)
         }
     } else if (warp == TC_W_MMA) {
         // ===== MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====
@@ -300,15 +338,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
             mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
-            const ScanItem it = iq[qs];
+            const TcQItem it = iq[qs];
             __syncwarp();
             if (lane == 0) mbar_arrive(&i_empty[qs]);
             if (it.list < 0) break;
-            const int ab = n % TC_NABUF;
-            mbar_wait(&a_full[ab], (n / TC_NABUF) & 1);
+            const int ab = n % nabuf;
+            mbar_wait(&a_full[ab], (n / nabuf) & 1);
             tc_fence_after();
-            long long lo, hi;
-            item_rows(it, lo, hi);
+            const long long lo = it.lo, hi = it.hi;
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
                 mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
@@ -326,7 +363,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         if (aug && kb0 == 0)   // s = -|v|^2 ...
                             tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * B_STAGE_BYTES), TC_IDESC_F16, 0u);
                         for (int jb = 0; jb < nkb; ++jb) {   // ... + (2 q) . v
-                            const uint32_t a_addr = sA_u32 + (uint32_t)(ab * TC_MAX_KB + kb0 + jb) * TC_KBLK_BYTES;
+                            const uint32_t a_addr = sA_u32 + (uint32_t)(ab * a_kb + kb0 + jb) * TC_KBLK_BYTES;
                             const uint32_t b_addr = slot + (uint32_t)jb * B_STAGE_BYTES;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)  // 4 x K = 16 fp16 (32 bytes) inside the 128-byte swizzle row
@@ -345,10 +382,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (elect_one()) tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
             __syncwarp();
         }
-    } else if (warp < (SEED ? 4 : TC_EPI_WARPS)) {
+    } else if (warp < N_EPI) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
-        // Two warps per TMEM lane quadrant: a thread owns one query row and one half (64 columns) of every
-        // accumulator of the work item. With t = -s (t = score - |q|^2 for L2, t = score for IP; smaller is
+        // TC_PARTS warps per TMEM lane quadrant: a thread owns one query row and one part (128 / TC_PARTS columns) of
+        // every accumulator of the work item (many warps with little work each: the survivor path is a chain of
+        // dependent selects, votes and stores, and only other warps can hide its latency). With t = -s (t = score - |q|^2 for L2, t = score for IP; smaller is
         // better) the filter keeps t <= tq. The hot loop is a 3-input-max tree over the raw accumulator values and
         // ONE compare per 32 columns (FMNMX3 only: the norms are already inside the accumulator). About one pair in
         // a thousand survives, i.e. a good part of a warp's 32-column groups hold one, but a thread sees only one
@@ -361,17 +399,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // (the seed pass has no survivor path and one bound per ROW to produce: it runs on 4 warps that take all
         //  128 columns, so the 64 group minima of a row cover all its 1024 seed entries)
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = SEED ? 0 : warp >> 2;     // which 64 of the 128 accumulator columns
+        const int part = SEED ? 0 : warp >> 2;     // which part of the 128 accumulator columns
         const int row = quad * 32 + lane;          // query row of this thread inside the tile
-        constexpr int NG = SEED ? TC_N / 32 : TC_N / 64;   // 32-column groups per thread and chunk
-        constexpr int NCOL = SEED ? TC_N : TC_N / 2;       // columns per thread and chunk
+        constexpr int NCOL = SEED ? TC_N : TC_N / TC_PARTS;   // columns per thread and chunk
+        constexpr int NG = NCOL / 32;                         // 32-column groups per thread and chunk
         const bool keep_mode = p.k <= TC_KMAX_TIGHTEN;
         const int cap = p.cap;
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
             mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
-            const ScanItem it = iq[qs];
+            const TcQItem it = iq[qs];
             __syncwarp();
             if (lane == 0) mbar_arrive(&i_empty[qs]);
             if (it.list < 0) break;
@@ -392,12 +430,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     thr_q = p.thr + q;
                     thr_pref = *thr_q;
                     tq = ordered_to_f32(thr_pref) - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
-                    cand = p.cand_key + ((size_t)(it.q_begin + row) * 2 + half) * cap;
+                    cand = p.cand_key + ((size_t)(it.q_begin + row) * TC_PARTS + part) * cap;
                 }
             }
-            long long lo, hi;
-            item_rows(it, lo, hi);
-            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
+            // 32-bit chunk bookkeeping (an index holds fewer than 2^31 entries): first entry of this thread's columns in
+            // the current chunk, and how many entries of the list are left from there
+            uint32_t ebase = (uint32_t)it.lo + part * NCOL;
+            int left = (int)(it.hi - it.lo) - part * NCOL;
+            for (int rows_left = (int)(it.hi - it.lo); rows_left > 0; rows_left -= TC_N, ebase += TC_N, left -= TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
                 // the bound the query's rows in other lists / CTAs have published meanwhile: the value loaded one
                 // chunk ago is used now and the next one is requested, so the load latency is never waited for
@@ -407,30 +447,32 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_fence_after();
                 if (warp == 0) stamp(5, m);
                 if (warp == 5) stamp(7, m);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N + half * 64;
-                uint32_t ra[32], rb[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N + part * NCOL;
+                uint32_t ra[32], rb[NG > 1 ? 32 : 1];
                 tc_ld32_async(taddr, ra);
-                tc_ld32_async(taddr + 32, rb);
+                if constexpr (NG > 1) tc_ld32_async(taddr + 32, rb);
                 tc_ld_wait(ra);   // (waits for both loads)
-                tc_ld_wait(rb);
+                if constexpr (NG > 1) tc_ld_wait(rb);
                 if (!SEED) {
-                    // the thread's 64 columns are in registers: hand the accumulator back to the MMA warp at once
+                    // the thread's columns are in registers: hand the accumulator back to the MMA warp at once
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[acc]);
                     if (row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
                 }
                 // columns past the end of the list hold other lists' vectors: valid columns of this thread's range
-                const int n_valid = (int)min((long long)NCOL, hi - row0 - half * 64);
+                const int n_valid = min(NCOL, left);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (SEED && g == 2) {   // second half of the columns (no call is made in the seed pass)
-                        tc_ld32_async(taddr + 64, ra);
-                        tc_ld32_async(taddr + 96, rb);
-                        tc_ld_wait(ra);
-                        tc_ld_wait(rb);
+                    if constexpr (SEED) {
+                        if (g == 2) {   // second half of the columns (no call is made in the seed pass)
+                            tc_ld32_async(taddr + 64, ra);
+                            tc_ld32_async(taddr + 96, rb);
+                            tc_ld_wait(ra);
+                            tc_ld_wait(rb);
+                        }
                     }
-                    uint32_t (&r)[32] = (g & 1) ? rb : ra;
+                    uint32_t (&r)[32] = (NG > 1 && (g & 1)) ? reinterpret_cast<uint32_t (&)[32]>(rb) : ra;
                     if (n_valid < (g + 1) * 32) {   // partial group (only the last chunk of a list): mask the tail
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
@@ -454,7 +496,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                             const int j = (pm == 0) ? __ffs(qm) - 1 : -1;   // -1: no new block for this lane in this round
                             if (pm == 0) qm &= qm - 1;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
+                            for (int u = 0; u < 4; ++u) {   // select tree: no dynamic register indexing
                                 const uint32_t x0 = (j & 1) ? r[4 + u] : r[u], x1 = (j & 1) ? r[12 + u] : r[8 + u];
                                 const uint32_t x2 = (j & 1) ? r[20 + u] : r[16 + u], x3 = (j & 1) ? r[28 + u] : r[24 + u];
                                 const uint32_t y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
@@ -462,7 +504,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 s4[u] = (j >= 0) ? v : s4[u];
                                 pm |= (j >= 0 && v <= tq) ? (1u << u) : 0u;
                             }
-                            e0 = (j >= 0) ? (uint32_t)(row0 + half * 64 + g * 32 + j * 4) : e0;
+                            e0 = (j >= 0) ? ebase + (uint32_t)(g * 32 + j * 4) : e0;
                             if (pm) {
                                 const int u = __ffs(pm) - 1;
                                 pm &= pm - 1;
@@ -531,7 +573,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     atomicMin(p.thr + q, f32_to_ordered(tk + qn));
                 }
             } else if (row_ok) {
-                p.cand_count[(size_t)(it.q_begin + row) * 2 + half] = lost ? cap + 1 : cnt;
+                p.cand_count[(size_t)(it.q_begin + row) * TC_PARTS + part] = lost ? cap + 1 : cnt;
             }
         }
     }
@@ -654,11 +696,11 @@ __global__ void seed_first_lists_kernel(int Q, int B, int* seed_ids) {
     }
 }
 
-// refine: the candidate regions (score, list entry) of a query's probed (list, half) pairs -> exact top-k over
+// refine: the candidate regions (score, list entry) of a query's probed (list, column part) pairs -> exact top-k over
 // distinct ids. One warp per query.
 struct RefineParams {
-    const unsigned long long* cand_key;   // [2 P, cap]
-    const int* cand_count;                // [2 P]
+    const unsigned long long* cand_key;   // [TC_PARTS P, cap]
+    const int* cand_count;                // [TC_PARTS P]
     int cap;
     const long long* probe_offsets;       // [Q+1]
     const int* probe_slot;                // [P] slot of the j-th probe of a query (-1: invalid probe)
@@ -682,14 +724,15 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
     unsigned long long kth = KEY_INF;
     bool overflow = false;
     const long long lo = p.probe_offsets[q], hi = p.probe_offsets[q + 1];
-    for (long long j0 = lo; j0 < hi; j0 += 16) {
-        // 16 probes = 32 regions per pass: lane l looks at region (probe j0 + l/2, half l&1)
-        const long long j = j0 + (lane >> 1);
+    constexpr int PPP = 32 / TC_PARTS;   // probes per pass
+    for (long long j0 = lo; j0 < hi; j0 += PPP) {
+        // PPP probes = 32 regions per pass: lane l looks at region (probe j0 + l / TC_PARTS, part l % TC_PARTS)
+        const long long j = j0 + (lane / TC_PARTS);
         int region = -1, cnt = 0;
         if (j < hi) {
             const int slot = p.probe_slot[j];
             if (slot >= 0) {
-                region = slot * 2 + (lane & 1);
+                region = slot * TC_PARTS + (lane % TC_PARTS);
                 cnt = p.cand_count[region];
             }
         }
