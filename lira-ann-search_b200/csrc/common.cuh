@@ -119,8 +119,13 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
+// same, on a precomputed shared-window address (hot loops: the generic -> shared conversion is not free)
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
     uint32_t done = 0;
     uint64_t t0 = 0;
 #pragma unroll 1

@@ -640,17 +640,22 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
         if (int rc = sw.probe_ids.ensure((size_t)(Q + 1) * 4)) return rc;
-        iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, 1);
+        // seed lists per query: the best one, or (LIRA_TC_SEED_LISTS=2) the two best -- every list alone yields k real
+        // candidates, so the smaller of the per-list bounds (atomicMin in the kernel) is valid
+        const int seed_lists = getenv("LIRA_TC_SEED_LISTS") ? std::max(1, std::min(2, atoi(getenv("LIRA_TC_SEED_LISTS")))) : 2;
+        iota_offsets_kernel<<<grid_for(Q + 1, 256), 256, 0, st>>>(sw.probe_offsets.as<long long>(), Q, seed_lists);
         LIRA_LAUNCH_CHECK();
-        first_of_pairs_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.top1.as<int>(), (int)Q, sw.probe_ids.as<int>());
-        LIRA_LAUNCH_CHECK();
+        if (seed_lists == 1) {
+            first_of_pairs_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.top1.as<int>(), (int)Q, sw.probe_ids.as<int>());
+            LIRA_LAUNCH_CHECK();
+        }
         fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u /* f32_to_ordered(+inf) */);
         LIRA_LAUNCH_CHECK();
         ProbeSpec seed;
         seed.kind = 1;
         seed.d_probe_offsets = sw.probe_offsets.as<long long>();
-        seed.d_probe_ids = sw.probe_ids.as<int>();
-        seed.P = Q;
+        seed.d_probe_ids = seed_lists == 1 ? sw.probe_ids.as<int>() : ws.top1.as<int>();
+        seed.P = Q * seed_lists;
         long long Pseed = 0;
         const long long* po_seed = nullptr;
         if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
@@ -731,8 +736,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) : 0;
     const char* trace_path = getenv("LIRA_TC_TRACE");   // debug: per-chunk clock stamps of CTA 0 -> CSV
     if (trace_path) {
-        if (int rc = ws.trace.ensure((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS * 8)) return rc;
-        LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS * 8, st));
+        if (int rc = ws.trace.ensure(((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8)) return rc;
+        LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, ((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8, st));
         tp.trace = ws.trace.as<long long>();
     }
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
@@ -750,7 +755,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     if (trace_path) {
-        std::vector<long long> tr((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS);
+        std::vector<long long> tr((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4);
         cudaMemcpy(tr.data(), ws.trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
         if (FILE* f = fopen(trace_path, "w")) {
             fprintf(f, "chunk,prod_start,mma_acc_free,mma_b0,mma_blast,mma_issued,epi4_ready,epi4_done,epi8_ready,epi8_done\n");
@@ -761,8 +766,30 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
             }
             fclose(f);
         }
+        if (FILE* f = fopen((std::string(trace_path) + ".ctas").c_str(), "w")) {   // per-CTA span and work (load balance)
+            fprintf(f, "cta,start_ns,end_ns,chunks,items\n");
+            const long long* c = tr.data() + (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS;
+            for (int b = 0; b < std::min(h->num_sms, TC_TRACE_CTAS); ++b)
+                fprintf(f, "%d,%lld,%lld,%lld,%lld\n", b, c[b * 4], c[b * 4 + 1], c[b * 4 + 2], c[b * 4 + 3]);
+            fclose(f);
+        }
+        if (FILE* f = fopen((std::string(trace_path) + ".items").c_str(), "w")) {   // per-CTA item timeline
+            fprintf(f, "cta,n,start_ns,list,rows,queries\n");
+            const long long* c = tr.data() + (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4;
+            for (int b = 0; b < std::min(h->num_sms, TC_TRACE_CTAS); ++b)
+                for (int n = 0; n < TC_TRACE_ITEMS; ++n) {
+                    const long long* e = c + ((size_t)b * TC_TRACE_ITEMS + n) * 4;
+                    if (e[0]) fprintf(f, "%d,%d,%lld,%lld,%lld,%lld\n", b, n, e[0], e[1], e[2], e[3]);
+                }
+            fclose(f);
+        }
     }
     if (getenv("LIRA_DEBUG")) {
+        std::vector<uint32_t> th((size_t)Q);
+        cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+        long long n_inf = 0;
+        for (uint32_t t : th) n_inf += (t == 0xFF800000u);
+        fprintf(stderr, "[lira] tc batch: final bound still +inf for %lld queries\n", n_inf);
         std::vector<int> cc((size_t)P * TC_PARTS);
         cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * TC_PARTS * 4, cudaMemcpyDeviceToHost);
         std::vector<int> sorted(cc);

@@ -53,7 +53,7 @@ static constexpr size_t TC_SMEM_BYTES = (size_t)TC_A_KB * TC_KBLK_BYTES         
                                         + (size_t)TC_AUG_BYTES                          // the constant augmented-K block of A
                                         + 512;                                          // barriers, item queue, tmem slot
 
-static constexpr int TC_TRACE_ROLES = 9, TC_TRACE_CHUNKS = 512;
+static constexpr int TC_TRACE_ROLES = 9, TC_TRACE_CHUNKS = 512, TC_TRACE_CTAS = 256, TC_TRACE_ITEMS = 24;   // + per CTA: {start ns, end ns, chunks, items}; + per CTA and item: {start ns, list, rows, queries}
 
 // work-item queue entry (scheduler -> MMA / epilogue warps): the tile and its row range of the list
 struct TcQItem {
@@ -332,6 +332,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // ===== MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====
         PipeState bs{0, 0};
         uint32_t m = 0;  // running chunk counter -> accumulator slot and phase
+        long long cta_t0 = 0;
+        int cta_items = 0;
+        if constexpr (TRACE) cta_t0 = (long long)global_timer_ns();
         if (aug) { mbar_wait(ga_full, 0); tc_fence_after(); }
         const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
         const uint64_t ga_desc = tc_smem_desc_sw32(smem_u32(sGA));
@@ -346,6 +349,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             mbar_wait(&a_full[ab], (n / nabuf) & 1);
             tc_fence_after();
             const long long lo = it.lo, hi = it.hi;
+            if constexpr (TRACE) {
+                if (p.trace && lane == 0 && blockIdx.x < TC_TRACE_CTAS && n < TC_TRACE_ITEMS) {
+                    long long* c = p.trace + (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + ((size_t)blockIdx.x * TC_TRACE_ITEMS + n) * 4;
+                    c[0] = (long long)global_timer_ns(); c[1] = it.list; c[2] = hi - lo; c[3] = it.q_count;
+                }
+            }
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
                 mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
@@ -381,6 +390,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             if (elect_one()) tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
             __syncwarp();
+            ++cta_items;
+        }
+        if constexpr (TRACE) {
+            if (p.trace && lane == 0 && blockIdx.x < TC_TRACE_CTAS) {
+                long long* c = p.trace + (size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + blockIdx.x * 4;
+                c[0] = cta_t0; c[1] = (long long)global_timer_ns(); c[2] = m; c[3] = cta_items;
+            }
         }
     } else if (warp < N_EPI) {
         // ===== epilogue: TMEM -> registers -> (seed: group minima | filter: survivors) =====
@@ -405,6 +421,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         constexpr int NG = NCOL / 32;                         // 32-column groups per thread and chunk
         const bool keep_mode = p.k <= TC_KMAX_TIGHTEN;
         const int cap = p.cap;
+        const uint32_t t_full_u32 = smem_u32(t_full), t_empty_u32 = smem_u32(t_empty);
         uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -443,7 +460,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 // chunk ago is used now and the next one is requested, so the load latency is never waited for
                 const uint32_t thr_now = thr_pref;
                 if (!SEED) thr_pref = *thr_q;
-                mbar_wait(&t_full[acc], (m / TC_NACC) & 1);
+                mbar_wait_addr(t_full_u32 + acc * 8, (m / TC_NACC) & 1);
                 tc_fence_after();
                 if (warp == 0) stamp(5, m);
                 if (warp == 5) stamp(7, m);
@@ -457,7 +474,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     // the thread's columns are in registers: hand the accumulator back to the MMA warp at once
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[acc]);
+                    if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
                     if (row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
                 }
                 // columns past the end of the list hold other lists' vectors: valid columns of this thread's range

@@ -14,8 +14,6 @@ except Exception as e:
 PY
   grep "tc batch" gpurun_out/bench_${tag}_$name.err | tail -1
 }
-run base LIRA_X=0
-run trace LIRA_TC_TRACE=gpurun_out/trace_${tag}.csv
 for v in "$@"; do
   name=${v%%:*}; envs=${v#*:}
   run $name $envs
