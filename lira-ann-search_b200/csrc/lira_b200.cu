@@ -1442,7 +1442,7 @@ int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d,
         if (int r2 = lira_index_create_dev(dbase.as<float>(), ds, d, off.data(), dids.as<int>(), nseg, metric, device, &h)) return r2;
         cudaStream_t st = h->stream;
         Workspace& ws = h->ws;
-        const long long max_pairs = 16ll << 20;
+        const long long max_pairs = 4ll << 20;   // (query, segment) pairs per batch: bounds the per-pair workspaces (1 KiB each on the tensor-core path)
         const long long qb = std::max<long long>(1, std::min<long long>(std::max<int64_t>(Q, 1), max_pairs / nseg));
         for (long long q0 = 0; q0 < Q; q0 += qb) {
             const long long nq = std::min<long long>(qb, Q - q0);

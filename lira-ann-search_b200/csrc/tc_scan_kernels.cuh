@@ -48,10 +48,12 @@ static constexpr int TC_CAPK = 32;       // k <= 16: candidate slots per (query,
                                          //          compacted in place to its k best by the whole warp (one key per lane)
 static constexpr int TC_CAPP = 64;       // k > 16: slots per region, no compaction (overflow -> the query is redone exactly)
 
+static constexpr int TC_NQ_ = 4;         // work-item queue depth (scheduler -> MMA / epilogue)
 static constexpr size_t TC_SMEM_BYTES = (size_t)TC_A_KB * TC_KBLK_BYTES                  // A tile(s)
                                         + (size_t)TC_NSLOT * TC_SLOT_BYTES              // B ring
                                         + (size_t)TC_AUG_BYTES                          // the constant augmented-K block of A
-                                        + 512;                                          // barriers, item queue, tmem slot
+                                        + 512                                           // barriers, item queue, tmem slot
+                                        + (size_t)TC_NQ_ * TC_M * 12;                   // per queued item and row: query id, |q|^2, bound
 
 static constexpr int TC_TRACE_ROLES = 9, TC_TRACE_CHUNKS = 512, TC_TRACE_CTAS = 256, TC_TRACE_ITEMS = 24;   // + per CTA: {start ns, end ns, chunks, items}; + per CTA and item: {start ns, list, rows, queries}
 
@@ -137,7 +139,7 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
 static constexpr uint32_t TC_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 static constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-static constexpr int TC_NQ = 4;   // work-item queue depth (scheduler -> MMA / epilogue)
+static constexpr int TC_NQ = TC_NQ_;
 static constexpr int TC_G = 64;   // seed pass: group minima per row
 static constexpr int TC_KMAX_TIGHTEN = 16;  // in-kernel bound tightening (and the tensor-core seed) need k <= 16
 
@@ -213,6 +215,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint64_t* ga_full = i_empty + TC_NQ;            // [1]
     TcQItem* iq = (TcQItem*)(ga_full + 1);          // [TC_NQ]
     uint32_t* tmem_slot = (uint32_t*)(iq + TC_NQ);
+    // per queued item and tile row, staged by the scheduler warp so that an epilogue warp starts an item without any
+    // global round trip: query id, |q|^2 and the query's bound (a snapshot: bounds only ever decrease, so a stale one is
+    // merely looser)
+    int* s_q = (int*)((uint8_t*)bars + 512);               // [TC_NQ][TC_M]
+    float* s_qn = (float*)(s_q + TC_NQ * TC_M);            // [TC_NQ][TC_M]
+    uint32_t* s_thr = (uint32_t*)(s_qn + TC_NQ * TC_M);    // [TC_NQ][TC_M]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int TC_W_PROD = tc_w_prod(SEED), TC_W_MMA = TC_W_PROD + 1, TC_W_ALLOC = TC_W_PROD + 2;
@@ -260,9 +268,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         PipeState bs{0, 0};
         uint32_t mp = 0;
         // Dynamic scheduler, ONE work item ahead (more would hurt the balance at the tail: an item is ~10 % of a
-        // CTA's share). The three dependent global round trips that describe the next item -- ticket (atomicAdd),
-        // descriptor, list range -- are issued at chunks 0, 2 and 4 of the current item, each consuming the result
-        // of the previous one, so none of them is ever waited for between two items.
+        // CTA's share). The dependent global round trips that describe the next item -- ticket (atomicAdd),
+        // descriptor, list range + row ids, per-row |q|^2 and bound -- are issued one per chunk of the current item,
+        // each consuming the result of the previous one, so none of them is waited for between two items.
         auto ticket = [&]() { return lane == 0 ? atomicAdd(p.work_counter, 1) : 0; };
         auto descriptor = [&](int t) {
             const int idx = __shfl_sync(0xffffffffu, t, 0);
@@ -282,21 +290,52 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             return o;
         };
-        TcQItem cur = with_rows(descriptor(ticket()));
+        // per-row data of an item, 4 rows per lane (row = lane + 32 j)
+        int rq[4];
+        float rqn[4];
+        uint32_t rthr[4];
+        auto row_ids = [&](const ScanItem& d) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rq[j] = (d.list >= 0 && lane + 32 * j < d.q_count) ? __ldg(p.group_queries + d.q_begin + lane + 32 * j) : -1;
+        };
+        auto row_data = [&]() {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rqn[j] = (rq[j] >= 0 && !p.is_ip) ? __ldg(p.qnorm + rq[j]) : 0.f;
+                rthr[j] = (rq[j] >= 0 && !SEED) ? *reinterpret_cast<const volatile uint32_t*>(p.thr + rq[j]) : 0xFF800000u;
+            }
+        };
+        TcQItem cur;
+        {
+            const ScanItem d0 = descriptor(ticket());
+            cur = with_rows(d0);
+            row_ids(d0);
+            row_data();
+        }
+        constexpr int N_STAGES = 5;
         for (int n = 0;; ++n) {
             const TcQItem it = cur;
             const int qs = n % TC_NQ;
             mbar_wait(&i_empty[qs], ((n / TC_NQ) & 1) ^ 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_q[qs * TC_M + lane + 32 * j] = rq[j];
+                s_qn[qs * TC_M + lane + 32 * j] = rqn[j];
+                s_thr[qs * TC_M + lane + 32 * j] = rthr[j];
+            }
+            __syncwarp();   // every lane's rows are written before lane 0 publishes the item (arrive = release)
             if (lane == 0) { iq[qs] = it; mbar_arrive(&i_full[qs]); }
             __syncwarp();
             if (it.list < 0) break;
-            int t_next = 0, stage = 0;     // next item: 0 nothing yet, 1 ticket requested, 2 descriptor requested, 3 complete
+            // next item: ticket -> descriptor -> list range and row ids -> per-row data, one stage per chunk
+            int t_next = 0, stage = 0;
             ScanItem d_next;
             d_next.list = -1; d_next.q_begin = 0; d_next.q_count = 0; d_next.tm = 0;
             auto advance_prefetch = [&]() {
                 if (stage == 0) t_next = ticket();
                 else if (stage == 1) d_next = descriptor(t_next);
-                else if (stage == 2) cur = with_rows(d_next);
+                else if (stage == 2) { cur = with_rows(d_next); row_ids(d_next); }
+                else if (stage == 3) row_data();
                 ++stage;
             };
             const int ab = n % nabuf;
@@ -310,7 +349,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const long long lo = it.lo, hi = it.hi;
             for (long long row0 = lo; row0 < hi; row0 += TC_N, ++mp) {
                 stamp(0, mp);
-                if (stage < 3 && (((row0 - lo) / TC_N) & 1) == 0) advance_prefetch();
+                if (stage < N_STAGES) advance_prefetch();
                 for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug box with the first)
                     const int nkb = min(TC_SLOT_KB, nk - kb0);
                     const bool with_aug = aug && kb0 == 0;
@@ -326,7 +365,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     bs.advance(TC_NSLOT);
                 }
             }
-            while (stage < 3) advance_prefetch();   // short list: the rest of the look-ahead (waited for)
+            while (stage < N_STAGES) advance_prefetch();   // short list: the rest of the look-ahead (waited for)
         }
     } else if (warp == TC_W_MMA) {
         // ===== MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====
@@ -427,6 +466,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const int qs = n % TC_NQ;
             mbar_wait(&i_full[qs], (n / TC_NQ) & 1);
             const TcQItem it = iq[qs];
+            const int q_s = s_q[qs * TC_M + row];
+            const float qn_s = s_qn[qs * TC_M + row];
+            const uint32_t thr_s = s_thr[qs * TC_M + row];
             __syncwarp();
             if (lane == 0) mbar_arrive(&i_empty[qs]);
             if (it.list < 0) break;
@@ -441,11 +483,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const volatile uint32_t* thr_q = p.thr;   // (rows past the end of the tile read thr[0]; their tq stays -inf)
             uint32_t thr_pref = 0xFF800000u;
             if (row_ok) {
-                q = __ldg(p.group_queries + it.q_begin + row);
-                if (!p.is_ip) qn = __ldg(p.qnorm + q);
+                q = q_s;
+                qn = qn_s;
                 if (!SEED) {
                     thr_q = p.thr + q;
-                    thr_pref = *thr_q;
+                    thr_pref = thr_s;
                     tq = ordered_to_f32(thr_pref) - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
                     cand = p.cand_key + ((size_t)(it.q_begin + row) * TC_PARTS + part) * cap;
                 }
@@ -454,8 +496,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             // the current chunk, and how many entries of the list are left from there
             uint32_t ebase = (uint32_t)it.lo + part * NCOL;
             int left = (int)(it.hi - it.lo) - part * NCOL;
+            // a warp whose 32 tile rows are all padding (tile of fewer queries) only keeps the accumulator handshake going
+            const bool warp_idle = !SEED && quad * 32 >= it.q_count;
             for (int rows_left = (int)(it.hi - it.lo); rows_left > 0; rows_left -= TC_N, ebase += TC_N, left -= TC_N, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
+                if (warp_idle) {
+                    mbar_wait_addr(t_full_u32 + acc * 8, (m / TC_NACC) & 1);
+                    if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
+                    __syncwarp();
+                    continue;
+                }
                 // the bound the query's rows in other lists / CTAs have published meanwhile: the value loaded one
                 // chunk ago is used now and the next one is requested, so the load latency is never waited for
                 const uint32_t thr_now = thr_pref;
