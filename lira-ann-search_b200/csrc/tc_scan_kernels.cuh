@@ -26,16 +26,20 @@
 namespace lira {
 
 static constexpr int TC_M = 128;         // queries per tile (UMMA M, TMEM lanes)
-static constexpr int TC_N = 128;         // vectors per chunk (UMMA N, TMEM columns per accumulator)
-static constexpr int TC_NACC = 4;        // TMEM accumulators in flight (4 x 128 = 512 columns)
-static constexpr int TC_NSLOT = 4;       // B ring slots; a slot = up to TC_SLOT_KB K blocks of one chunk (32 KiB) + its augmented-K box
+static constexpr int TC_N = 128;         // vectors per TMA box / per half of a chunk
+static constexpr int TC_NS = 256;        // vectors per chunk (UMMA N, TMEM columns per accumulator): with N = 256 an MMA reads 12 KiB of
+                                         //   shared memory per 128 tensor-pipe cycles instead of 8 KiB per 64 (N = 128 is bound by it)
+static constexpr int TC_NH = TC_NS / TC_N;   // halves (TMA boxes of 128 rows) per chunk
+static constexpr int TC_NACC = 2;        // TMEM accumulators in flight (2 x 256 = 512 columns)
+static constexpr int TC_NSLOT = 2;       // B ring slots; a slot = up to TC_SLOT_KB K blocks of one chunk (2 x 32 KiB) + its augmented-K boxes
 static constexpr int TC_SLOT_KB = 2;     //   (one barrier round trip per 8-9 MMAs instead of per 4)
 static constexpr int TC_A_KB = 4;        // K blocks of A storage: one tile of d <= 256, or two tiles (double buffered) of d <= 128
 static constexpr int TC_KH = 64;         // fp16 values per K block (one 128-byte swizzle row)
 static constexpr int TC_MAX_KB = 4;      // K blocks of 64 halves resident per A tile: d <= 256
 static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 128 B
 static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 16 halves
-static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * B_STAGE_BYTES + TC_AUG_BYTES;   // 36 KiB
+static constexpr int TC_SKB_BYTES = TC_NH * B_STAGE_BYTES;                        // 32 KiB: one K block of a chunk (256 rows x 128 B)
+static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * TC_SKB_BYTES + TC_NH * TC_AUG_BYTES;   // 72 KiB
 static constexpr int TC_PARTS = 4;       // filter pass: column parts per accumulator = epilogue warps per TMEM lane quadrant
 static constexpr int TC_EPI_WARPS = 4 * TC_PARTS;   // filter pass: each epilogue warp takes 128 / TC_PARTS accumulator columns
 static constexpr int TC_SEED_EPI_WARPS = 4;         // seed pass: one warp per quadrant takes all 128 columns
@@ -135,8 +139,9 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// instruction descriptors: D = F32, A = B = F16 (format 0) resp. TF32 (format 2), both K-major, N = 128, M = 128
-static constexpr uint32_t TC_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// instruction descriptors: D = F32, A = B = F16 (format 0) resp. TF32 (format 2), both K-major, M = 128, N = 256 / 128
+static constexpr uint32_t TC_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_NS >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+static constexpr uint32_t TC_IDESC_F16_N128 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 static constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 static constexpr int TC_NQ = TC_NQ_;
@@ -347,19 +352,25 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             __syncwarp();
             const long long lo = it.lo, hi = it.hi;
-            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++mp) {
+            for (long long row0 = lo; row0 < hi; row0 += TC_NS, ++mp) {
                 stamp(0, mp);
                 if (stage < N_STAGES) advance_prefetch();
-                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug box with the first)
+                const int nh = hi - row0 > TC_N ? TC_NH : 1;   // boxes of 128 rows in this chunk (the tail of a list may need one only)
+                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug boxes with the first)
                     const int nkb = min(TC_SLOT_KB, nk - kb0);
                     const bool with_aug = aug && kb0 == 0;
                     mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
                     if (elect_one()) {
                         uint8_t* slot = sB + (size_t)bs.stage * TC_SLOT_BYTES;
-                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nkb * B_STAGE_BYTES + (with_aug ? TC_AUG_BYTES : 0));
+                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)(nkb * nh) * B_STAGE_BYTES + (with_aug ? nh * TC_AUG_BYTES : 0));
                         for (int j = 0; j < nkb; ++j)
-                            tma_load_2d(slot + (size_t)j * B_STAGE_BYTES, &tmap_v, (kb0 + j) * TC_KH, (int)row0, &b_full[bs.stage]);
-                        if (with_aug) tma_load_2d(slot + TC_SLOT_KB * B_STAGE_BYTES, &tmap_vaug, 0, (int)row0, &b_full[bs.stage]);
+                            for (int x = 0; x < nh; ++x)
+                                tma_load_2d(slot + (size_t)j * TC_SKB_BYTES + (size_t)x * B_STAGE_BYTES, &tmap_v, (kb0 + j) * TC_KH,
+                                            (int)row0 + x * TC_N, &b_full[bs.stage]);
+                        if (with_aug)
+                            for (int x = 0; x < nh; ++x)
+                                tma_load_2d(slot + TC_SLOT_KB * TC_SKB_BYTES + (size_t)x * TC_AUG_BYTES, &tmap_vaug, 0, (int)row0 + x * TC_N,
+                                            &b_full[bs.stage]);
                     }
                     __syncwarp();
                     bs.advance(TC_NSLOT);
@@ -394,12 +405,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     c[0] = (long long)global_timer_ns(); c[1] = it.list; c[2] = hi - lo; c[3] = it.q_count;
                 }
             }
-            for (long long row0 = lo; row0 < hi; row0 += TC_N, ++m) {
+            for (long long row0 = lo; row0 < hi; row0 += TC_NS, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
                 mbar_wait(&t_empty[acc], ((m / TC_NACC) & 1) ^ 1u);
                 tc_fence_after();
                 stamp(1, m);
-                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                const uint32_t d_tmem = tmem_base + acc * TC_NS;
+                const uint32_t idesc = hi - row0 > TC_N ? TC_IDESC_F16 : TC_IDESC_F16_N128;   // (the tail of a list: N = 128)
                 for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {
                     const int nkb = min(TC_SLOT_KB, nk - kb0);
                     mbar_wait(&b_full[bs.stage], bs.phase);
@@ -409,13 +421,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const uint32_t slot = sB_u32 + (uint32_t)bs.stage * TC_SLOT_BYTES;
                     if (elect_one()) {
                         if (aug && kb0 == 0)   // s = -|v|^2 ...
-                            tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * B_STAGE_BYTES), TC_IDESC_F16, 0u);
+                            tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * TC_SKB_BYTES), idesc, 0u);
                         for (int jb = 0; jb < nkb; ++jb) {   // ... + (2 q) . v
                             const uint32_t a_addr = sA_u32 + (uint32_t)(ab * a_kb + kb0 + jb) * TC_KBLK_BYTES;
-                            const uint32_t b_addr = slot + (uint32_t)jb * B_STAGE_BYTES;
+                            const uint32_t b_addr = slot + (uint32_t)jb * TC_SKB_BYTES;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)  // 4 x K = 16 fp16 (32 bytes) inside the 128-byte swizzle row
-                                tc_mma_f16(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), TC_IDESC_F16,
+                                tc_mma_f16(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), idesc,
                                             (aug || kb0 || jb || j) ? 1u : 0u);
                         }
                         tc_commit(&b_empty[bs.stage]);  // frees the slot when these MMAs have read it
@@ -498,8 +510,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             int left = (int)(it.hi - it.lo) - part * NCOL;
             // a warp whose 32 tile rows are all padding (tile of fewer queries) only keeps the accumulator handshake going
             const bool warp_idle = !SEED && quad * 32 >= it.q_count;
-            for (int rows_left = (int)(it.hi - it.lo); rows_left > 0; rows_left -= TC_N, ebase += TC_N, left -= TC_N, ++m) {
+            for (int rows_left = (int)(it.hi - it.lo); rows_left > 0; rows_left -= TC_NS, ebase += TC_NS, left -= TC_NS, ++m) {
                 const uint32_t acc = m & (TC_NACC - 1);
+                const int nh = rows_left > TC_N ? TC_NH : 1;   // halves of 128 columns the MMA warp filled (tail of a list: one)
                 if (warp_idle) {
                     mbar_wait_addr(t_full_u32 + acc * 8, (m / TC_NACC) & 1);
                     if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
@@ -514,21 +527,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_fence_after();
                 if (warp == 0) stamp(5, m);
                 if (warp == 5) stamp(7, m);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N + part * NCOL;
+                if (!SEED && row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
+                for (int h = 0; h < nh; ++h) {   // the two 128-column halves of the accumulator, one after the other
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_NS + h * TC_N + part * NCOL;
                 uint32_t ra[32], rb[NG > 1 ? 32 : 1];
                 tc_ld32_async(taddr, ra);
                 if constexpr (NG > 1) tc_ld32_async(taddr + 32, rb);
                 tc_ld_wait(ra);   // (waits for both loads)
                 if constexpr (NG > 1) tc_ld_wait(rb);
-                if (!SEED) {
-                    // the thread's columns are in registers: hand the accumulator back to the MMA warp at once
+                if (!SEED && h == nh - 1) {
+                    // the thread's last columns are in registers: hand the accumulator back to the MMA warp at once
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
-                    if (row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
                 }
                 // columns past the end of the list hold other lists' vectors: valid columns of this thread's range
-                const int n_valid = min(NCOL, left);
+                const int n_valid = min(NCOL, left - h * TC_N);
+                const uint32_t ebase_h = ebase + h * TC_N;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     if constexpr (SEED) {
@@ -571,7 +586,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 s4[u] = (j >= 0) ? v : s4[u];
                                 pm |= (j >= 0 && v <= tq) ? (1u << u) : 0u;
                             }
-                            e0 = (j >= 0) ? ebase + (uint32_t)(g * 32 + j * 4) : e0;
+                            e0 = (j >= 0) ? ebase_h + (uint32_t)(g * 32 + j * 4) : e0;
                             if (pm) {
                                 const int u = __ffs(pm) - 1;
                                 pm &= pm - 1;
@@ -615,6 +630,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         } while (__any_sync(0xffffffffu, (qm | pm) != 0));
                     }
                 }
+                }   // h
                 if (SEED) {   // this warp is done with the accumulator
                     tc_fence_before();
                     __syncwarp();
