@@ -590,7 +590,8 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
 }
 
 static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows of each of the two best probed lists
-static constexpr int TC_SEED_ROWS_TC = 1024;  // tensor-core seed (k <= 16): rows of the best probed list
+static constexpr int TC_SEED_ROWS_TC = 0;     // tensor-core seed (k <= 16): rows of each of the two best probed lists (0 = all: the pass streams
+                                              // (nearly) every list once anyway, and whole lists halve the survivors of the filter pass)
 
 // The online query path on the tensor cores (tc_scan_kernels.cuh). *done = true when results were produced
 // for every query whose ws.redo flag is 0; *n_redo counts the queries (flag 1) whose candidate buffer
@@ -672,7 +673,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.n_items = sw.n_items.as<int>();
         sp.work_counter = sw.n_items.as<int>() + 1;
         sp.nk = nk;
-        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_TC;
+        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_TC;   // 0: whole lists
         sp.exp = 0;
         sp.qnorm = ws.qnorm.as<float>();
         sp.thr = ws.thr.as<uint32_t>();
