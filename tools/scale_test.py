@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""One GPU's share of config 5 (BigANN-100M shape sharded over 8 GPUs): N = 12.5 M base vectors x 128, full 2x
+redundancy (every vector in its two nearest partitions, LIRA_largescale.py:320-329) = 25 M list entries, B = 1024,
+10 000 queries, k = 10. Everything is generated and indexed on the device (plain torch, untimed plumbing); the timed
+part is the library's grouped list scan with explicit probe sets (nprobe nearest centroids, the paper's IVF baseline).
+Checks the ids of a query sample against a brute-force scan of the probed entries and prints one JSON line.
+
+    python tools/scale_test.py [--N 12500000] [--Q 10000] [--B 1024] [--nprobe 16] [--steps 5]
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import lira_ann_search_b200 as L
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--N", type=int, default=12_500_000)
+ap.add_argument("--d", type=int, default=128)
+ap.add_argument("--Q", type=int, default=10_000)
+ap.add_argument("--B", type=int, default=1024)
+ap.add_argument("--nprobe", type=int, default=16)
+ap.add_argument("--k", type=int, default=10)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--check", type=int, default=64)
+args = ap.parse_args()
+L._cabi.require_gpu()
+dev = torch.device("cuda:0")
+N, d, Q, B, k = args.N, args.d, args.Q, args.B, args.k
+t0 = time.time()
+g = torch.Generator(device=dev).manual_seed(43)
+ncomp = 4096
+centres = torch.randn(ncomp, d, device=dev, generator=g)
+logw = 0.5 * torch.randn(ncomp, device=dev, generator=g)
+w = torch.softmax(logw, 0)
+
+
+def gen(n, seed):
+    gg = torch.Generator(device=dev).manual_seed(seed)
+    comp = torch.multinomial(w, n, replacement=True, generator=gg)
+    x = centres[comp] + 0.35 * torch.randn(n, d, device=dev, generator=gg)
+    return torch.clamp(torch.round(32 * x + 64), 0, 255)   # integer valued, like SIFT / BigANN
+
+
+CH = 1_000_000
+x_d = torch.empty((N, d), dtype=torch.float32, device=dev)
+for c, s in enumerate(range(0, N, CH)):
+    x_d[s:s + CH] = gen(min(CH, N - s), 43 * 1_000_003 + c)
+x_q = gen(Q, 50)
+# centroids: a few Lloyd iterations on a sample (plumbing)
+samp = x_d[torch.randperm(N, device=dev, generator=g)[:262_144]]
+cent = samp[:B].clone()
+for _ in range(8):
+    a = torch.cdist(samp, cent).argmin(1)
+    s = torch.zeros_like(cent).index_add_(0, a, samp)
+    n = torch.bincount(a, minlength=B).clamp(min=1).unsqueeze(1)
+    cent = s / n
+# two nearest partitions per vector
+b2 = torch.empty((N, 2), dtype=torch.int64, device=dev)
+for s in range(0, N, CH):
+    b2[s:s + CH] = torch.cdist(x_d[s:s + CH], cent).topk(2, dim=1, largest=False).indices
+ids = torch.arange(N, device=dev).repeat_interleave(2)
+key = b2.reshape(-1) * N + ids
+order = torch.argsort(key)
+ids = ids[order].to(torch.int32)
+sizes = torch.bincount(b2.reshape(-1), minlength=B)
+off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+off[1:] = torch.cumsum(sizes, 0)
+del key, order, b2
+E = int(off[-1])
+vecs = torch.empty((E, d), dtype=torch.float32, device=dev)
+for s in range(0, E, 4 * CH):
+    vecs[s:s + 4 * CH] = x_d[ids[s:s + 4 * CH].long()]
+del x_d
+torch.cuda.synchronize()
+print(f"[scale] data + lists on the device: {time.time() - t0:.1f}s; E = {E} entries, list sizes {int(sizes.min())}..{int(sizes.max())}",
+      file=sys.stderr, flush=True)
+index = L.LiraIndex.from_device(vecs, ids, off.cpu().numpy(), d, "L2")
+assert index.tensor_core_eligible
+# probe sets: nprobe nearest centroids
+pids = torch.cdist(x_q, cent).topk(args.nprobe, dim=1, largest=False).indices.to(torch.int32).reshape(-1).contiguous()
+poff = (torch.arange(Q + 1, device=dev, dtype=torch.int64) * args.nprobe).contiguous()
+index.set_timing(True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(3):
+    D, I, cmp_ = index.search_dev(x_q, poff, pids, k)
+torch.cuda.synchronize()
+assert index.last_path == "tensor-core"
+ms, scan_ms, scan_bytes, scan_pairs = [], [], [], []
+for _ in range(args.steps):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    D, I, cmp_ = index.search_dev(x_q, poff, pids, k)
+    e1.record()
+    e1.synchronize()
+    ms.append(e0.elapsed_time(e1))
+    tm = index.last_timing()
+    scan_ms.append(tm["scan_ms"]); scan_bytes.append(tm["scan_bytes"]); scan_pairs.append(tm["scan_pairs"])
+# check a sample against a brute-force scan of the probed entries (distinct ids, ties by id)
+Ih, Dh = I.cpu().numpy(), D.cpu().numpy()
+offh = off.cpu().numpy()
+bad = 0
+for qi in range(min(args.check, Q)):
+    lists = pids[qi * args.nprobe:(qi + 1) * args.nprobe].cpu().numpy()
+    rows = torch.cat([torch.arange(offh[b], offh[b + 1], device=dev) for b in lists])
+    dist = ((vecs[rows] - x_q[qi]) ** 2).sum(1)
+    gid = ids[rows].long()
+    o = torch.argsort(dist.double() * 4294967296.0 + gid.double())   # by (distance, id): exact, both are small integers
+    gid_s, dist_s = gid[o].cpu().numpy(), dist[o].cpu().numpy()
+    _, first = np.unique(gid_s, return_index=True)
+    keep = np.sort(first)[:k]
+    if not (np.array_equal(gid_s[keep], Ih[qi]) and np.array_equal(dist_s[keep], Dh[qi])):
+        bad += 1
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+s_ms = float(np.mean(scan_ms))
+print(json.dumps({"workload": "config 5 shard (1/8 of BigANN-100M shape, full 2x redundancy)", "N": N, "entries": E, "Q": Q, "B": B,
+                  "nprobe": args.nprobe, "k": k, "ms_per_batch": float(np.mean(ms)), "qps": Q / (float(np.mean(ms)) * 1e-3),
+                  "scan_kernel_ms": s_ms, "scan_algorithmic_bytes": float(np.mean(scan_bytes)),
+                  "scan_gbs_algorithmic": float(np.mean(scan_bytes)) / (s_ms * 1e-3) / 1e9,
+                  "roofline_frac_of_measured_hbm": float(np.mean(scan_bytes)) / (s_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                  "scan_tflops_algorithmic": 2.0 * d * float(np.mean(scan_pairs)) / (s_ms * 1e-3) / 1e12,
+                  "tensor_frac_of_measured_bf16_sustained": 2.0 * d * float(np.mean(scan_pairs)) / (s_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                  "mean_entries_scanned_per_query": float(cmp_.double().mean()),
+                  "checked_queries": min(args.check, Q), "mismatches": bad, "redo": index.last_redo}), flush=True)
