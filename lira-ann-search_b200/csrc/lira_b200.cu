@@ -174,6 +174,8 @@ struct lira_index {
     CUtensorMap tmap16;
     __half* aaug = nullptr;      // [128, 16] constant fp16 augmented-K block of the query side: (-2048, -1, 0...)
     CUtensorMap tmap_vaug, tmap_aaug;
+    int nprobe_cap = 64;         // threshold selection without a host round trip keeps at most this many lists per query (adaptive)
+    bool tc_force_sync = false;  // next tensor-core attempt uses the exact pair count (after a truncated / inexact optimistic run)
     bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
     bool use_tc = true;
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
@@ -456,7 +458,7 @@ static int launch_merge(const MergeParams& mp, cudaStream_t st) {
 // of (query, list) pairs. `probe_offsets_out` is the CSR the merge must use.
 static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const ProbeSpec& ps, int tile, long long* d_cmp,
                           long long* P_out, const long long** probe_offsets_out, int* extra_flag_host,
-                          const int* d_extra_flag, const int* d_mask, cudaStream_t st) {
+                          const int* d_extra_flag, const int* d_mask, cudaStream_t st, int* d_trunc_flag = nullptr) {
     LIRA_REQUIRE(Q >= 0 && Q < (1ll << 31), "Q out of range");
     const int B = h->B;
     const int warps = 8;
@@ -479,8 +481,16 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
         LIRA_REQUIRE(ps.mode >= 0 && ps.mode <= 2, "unknown selection mode");
         if (ps.mode == LIRA_SELECT_TOPN) LIRA_REQUIRE(ps.value >= 1 && ps.value <= 128, "top-nprobe must be in [1, 128]");
         if (int rc = ws.sel.ensure((size_t)Q * B * 4)) return rc;
+        // no host round trip when the caller asked for it (d_trunc_flag) and the bound Q * cap is affordable
+        int per_q_cap = 0;
+        if (d_trunc_flag) {
+            per_q_cap = ps.mode == LIRA_SELECT_TOPN ? std::max(1, std::min({(int)ps.value, B, 128})) : std::min(B, h->nprobe_cap);
+            if (Q * (long long)per_q_cap > (4ll << 20)) per_q_cap = 0;
+        }
+        const bool nosync = per_q_cap > 0;
         SelectParams sp{ps.d_scores, ps.lds, (int)Q, B, ps.mode, ps.value, h->d_offsets, ws.sel.as<int>(),
-                        ws.nsel.as<int>(), d_cmp, ws.list_count.as<int>(), ws.top1.as<int>(), d_mask};
+                        ws.nsel.as<int>(), d_cmp, ws.list_count.as<int>(), ws.top1.as<int>(), d_mask,
+                        (nosync && ps.mode != LIRA_SELECT_TOPN) ? per_q_cap : 0, d_trunc_flag};
         select_kernel<4><<<qgrid, warps * 32, 0, st>>>(sp);
         LIRA_LAUNCH_CHECK();
         exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.nsel.as<int>(), ws.probe_offsets.as<long long>(), (int)Q);
@@ -488,10 +498,18 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
         exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
         LIRA_LAUNCH_CHECK();
         // the one host round trip of the query phase: P sizes the partial-result buffers
-        LIRA_CUDA_OK(cudaMemcpyAsync(&P, ws.probe_offsets.as<long long>() + Q, 8, cudaMemcpyDeviceToHost, st));
-        if (extra_flag_host && d_extra_flag)
-            LIRA_CUDA_OK(cudaMemcpyAsync(extra_flag_host, d_extra_flag, 4, cudaMemcpyDeviceToHost, st));
-        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        if (nosync) {
+            // upper bound instead of the round trip: top-nprobe selects exactly `want` per query, the threshold modes keep at
+            // most h->nprobe_cap per query (select_kernel raises flags[2] when a query had more; the caller checks it --
+            // and flags[0], the exactness of the query batch -- at its own final synchronisation and reruns if needed)
+            P = Q * (long long)per_q_cap;
+            if (extra_flag_host) *extra_flag_host = 1;
+        } else {
+            LIRA_CUDA_OK(cudaMemcpyAsync(&P, ws.probe_offsets.as<long long>() + Q, 8, cudaMemcpyDeviceToHost, st));
+            if (extra_flag_host && d_extra_flag)
+                LIRA_CUDA_OK(cudaMemcpyAsync(extra_flag_host, d_extra_flag, 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
     } else if (ps.kind == 1) {
         P = ps.P;
         int* bad = ws.n_items.as<int>() + 8;
@@ -598,10 +616,11 @@ static constexpr int TC_SEED_ROWS_TC = 0;     // tensor-core seed (k <= 16): row
 // overflowed and that the caller must answer with the exact CUDA-core path. *done = false (no error) when
 // the batch does not qualify at all.
 static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k, int dedup,
-                     float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, bool* done, int* n_redo,
+                     float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, bool* done, int* n_redo, bool* retry,
                      cudaStream_t st) {
     *done = false;
     *n_redo = 0;
+    *retry = false;
     if (!h->tc_ok || Q < 256) return 0;
     // exhaustive probe sets (exact kNN over base segments): only with the in-kernel bound tightening (k <= 16); a
     // static seed bound alone would let a large share of a million-row base through
@@ -611,15 +630,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.qnorm.ensure((size_t)Q * 4)) return rc;
     if (int rc = ws.flags.ensure(64)) return rc;
     if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
-    int one_zero[2] = {1, 0};  // [0] query batch exactly representable, [1] number of overflowed queries
-    LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 8, cudaMemcpyHostToDevice, st));
+    // [0] query batch exactly representable, [1] number of overflowed queries, [2] a query's probe set was truncated
+    static const int one_zero[3] = {1, 0, 0};
+    LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 12, cudaMemcpyHostToDevice, st));
+    const bool optimistic = ps.kind == 0 && !h->tc_force_sync;   // no host round trip before the scan (checked at the end)
+    h->tc_force_sync = false;
     row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), nullptr, nullptr, 0);
     LIRA_LAUNCH_CHECK();
     long long P = 0;
     const long long* po = nullptr;
     int q_exact = 1;
-    if (int rc = prepare_groups(h, ws, Q, ps, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st)) return rc;
-    if (!q_exact || P == 0) return 0;  // not exact in TF32 (or nothing probed): exact CUDA-core path
+    if (int rc = prepare_groups(h, ws, Q, ps, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st,
+                                optimistic ? ws.flags.as<int>() + 2 : nullptr)) return rc;
+    if (!q_exact || P == 0) return 0;  // not exact in fp16 (or nothing probed): exact CUDA-core path
     if (int rc = save_stats(h, ws, st)) return rc;
     if (ps.kind == 1) {
         first_probes_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, (int)Q, ws.top1.as<int>());
@@ -753,8 +776,18 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (k <= 32) refine_topk_kernel<1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else refine_topk_kernel<4><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     LIRA_LAUNCH_CHECK();
-    LIRA_CUDA_OK(cudaMemcpyAsync(n_redo, ws.flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
+    int fl[3] = {1, 0, 0};
+    LIRA_CUDA_OK(cudaMemcpyAsync(fl, ws.flags.p, 12, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    *n_redo = fl[1];
+    if (optimistic && (fl[0] == 0 || fl[2] != 0)) {
+        // the optimistic run is void: the batch is not exact in fp16 (-> the caller's CUDA-core path), or a probe set was
+        // truncated (-> once more with the exact pair count and a larger cap from now on)
+        if (fl[2] != 0) { h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4); *retry = fl[0] != 0; }
+        h->tc_force_sync = true;
+        *n_redo = 0;
+        return 0;
+    }
     if (trace_path) {
         std::vector<long long> tr((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4);
         cudaMemcpy(tr.data(), ws.trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
@@ -816,7 +849,10 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
     bool done = false;
     int n_redo = 0;
     if (h->use_tc) {
-        if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, st)) return rc;
+        bool retry = false;
+        if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st)) return rc;
+        if (!done && retry)
+            if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st)) return rc;
     }
     if (!done || n_redo > 0) {
         // exact CUDA-core path: the whole batch, or only the queries the tensor-core pass flagged

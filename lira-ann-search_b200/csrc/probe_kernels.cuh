@@ -115,6 +115,8 @@ struct SelectParams {
     int* list_count;      // [B] histogram (atomic)
     int* seed_ids;        // [Q, 2] the two best-scoring selected partitions (-1 padded); may be null
     const int* mask;      // optional [Q]: queries with mask[q] == 0 select nothing
+    int cap;              // > 0 (threshold modes): at most `cap` partitions per query are kept, so that Q * cap bounds the
+    int* trunc_flag;      //   number of pairs without a host round trip; *trunc_flag = 1 when a query had more (caller reruns)
 };
 
 // the two smallest keys of a warp's per-lane (k1 <= k2) pairs, broadcast to all lanes
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
                 }
                 const uint32_t mm = __ballot_sync(0xffffffffu, hit);
                 if (mm == 0) continue;
-                if (hit) {
+                if (hit && (p.cap <= 0 || n + __popc(mm & ((1u << lane) - 1u)) < p.cap)) {
                     sel[n + __popc(mm & ((1u << lane) - 1u))] = b;
                     atomicAdd(p.list_count + b, 1);
                     cmp += p.list_offsets[b + 1] - p.list_offsets[b];
@@ -225,6 +227,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
                 }
                 n += __popc(mm);
             }
+        }
+        if (p.cap > 0 && n > p.cap) {
+            n = p.cap;
+            if (lane == 0 && p.trunc_flag) *p.trunc_flag = 1;
         }
         // global argmax, first maximum wins (search.cpp:456-466); it is always selected when anything is
 #pragma unroll

@@ -374,6 +374,46 @@ def test_tensor_core_query_phase_matches_cuda_cores(L, golden):
             assert np.array_equal(x, y)
 
 
+def test_select_without_round_trip_truncation_and_inexact_batches(L):
+    """Threshold selection on the tensor-core path sizes its buffers with an upper bound (64 lists per query) instead of a
+    host round trip. Queries that select more lists than that, and batches that turn out not to be exact in fp16, must be
+    answered again transparently: same results as the CUDA-core path, which always takes the round trip."""
+    import torch
+    rng = np.random.RandomState(3)
+    x_d, x_q = synth(40000, 64, 512, seed=5, integer=True)
+    B = 100
+    cl = random_lists(len(x_d), B, rng, redundancy=0.2)
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    scores = rng.rand(len(x_q), B).astype(np.float32)   # threshold 0.25 -> ~75 lists per query (> 64)
+    dev = torch.device("cuda:0")
+    d_s, d_q = torch.as_tensor(scores, device=dev), torch.as_tensor(x_q, device=dev)
+    for thr in (0.25, 0.9, 0.25):   # truncated (cap grows), small probe sets, large again (now below the cap)
+        index.set_use_tensor_cores(True)
+        a = [t.cpu().numpy() for t in index.select_search_dev(d_s, d_q, L.SELECT_GT, thr, 10)]
+        assert index.last_path == "tensor-core"
+        index.set_use_tensor_cores(False)
+        b = [t.cpu().numpy() for t in index.select_search_dev(d_s, d_q, L.SELECT_GT, thr, 10)]
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        poff = np.zeros(len(x_q) + 1, np.int64)
+        np.cumsum((scores > thr).sum(1), out=poff[1:])
+        pids = np.nonzero(scores > thr)[1].astype(np.int32)
+        I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
+        assert np.array_equal(a[1], I_ref) and np.array_equal(a[0], D_ref) and np.array_equal(a[3], cmp_ref)
+    # a real-valued query batch on an integer index: the optimistic tensor-core attempt is void, CUDA cores answer
+    index.set_use_tensor_cores(True)
+    xq_f = (x_q + 0.25).astype(np.float32)
+    d_qf = torch.as_tensor(xq_f, device=dev)
+    a = [t.cpu().numpy() for t in index.select_search_dev(d_s, d_qf, L.SELECT_GT, 0.9, 10)]
+    assert index.last_path == "cuda-core"
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum((scores > 0.9).sum(1), out=poff[1:])
+    pids = np.nonzero(scores > 0.9)[1].astype(np.int32)
+    I_ref, D_ref, _ = O.search(off, ids, vecs, xq_f, poff, pids, 10, O.L2, O.F64, 1)
+    assert_topk_equiv(a[0], a[1], D_ref, I_ref, xq_f, x_d, O.L2)
+
+
 # ---------------------------------------------------------------------------------------------
 # tensor-core (tcgen05, error-compensated TF32) forward of the probing model vs the fp32 CUDA-core kernels
 # ---------------------------------------------------------------------------------------------
