@@ -457,13 +457,15 @@ def main():
     pin_q.copy_(torch.as_tensor(wl["x_q"]))
     q_host = pin_q.numpy()
     e2e_t = []
+    host_out = None   # result arrays of the first call are reused (filled in place) by the later ones
     for i in range(3 + min(args.steps, 10)):
         flush.zero_()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        Dh, Ih, nph, cmph = index.probe_search(model, q_host, L.SELECT_GT, thr, k, True)
+        host_out = index.probe_search(model, q_host, L.SELECT_GT, thr, k, True, out=host_out)
+        Dh, Ih, nph, cmph = host_out
         if shard_lists:
             Dg, Ig = gather_merge(torch.as_tensor(Dh, device=dev), torch.as_tensor(Ih, device=dev))
             Ih = Ig.cpu().numpy()

@@ -166,6 +166,8 @@ struct lira_index {
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
     Workspace ws, ws_seed;
+    void* h_stage = nullptr;     // pinned host staging for results (D2H into pageable user buffers is staged by the driver otherwise,
+    size_t h_stage_cap = 0;      //   synchronously and in small pieces)
     DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
     float* vnorm = nullptr;      // |v|^2 per list entry
     __half* vaug = nullptr;      // [E, 16] fp16 augmented-K block of every entry: (hi, lo, 0...) with |v|^2 = 2048 hi + lo (tensor-core path)
@@ -1094,6 +1096,7 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->vnorm);
     cudaFree(h->vaug);
     cudaFree(h->vecs16);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     cudaFree(h->aaug);
     h->ws.release();
     h->ws_seed.release();
@@ -1439,10 +1442,27 @@ int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t 
     if (int rc = lira_probe_search_dev(h, m, ws.q.as<float>(), h->ds, Q, mode, value, k, dedup, ws.D.as<float>(),
                                        (int64_t*)ws.I.p, ws.nprobe.as<int>(), (int64_t*)ws.cmp.p, st)) return rc;
     if (Q) {
-        LIRA_CUDA_OK(cudaMemcpyAsync(D, ws.D.p, (size_t)Q * k * 4, cudaMemcpyDeviceToHost, st));
-        LIRA_CUDA_OK(cudaMemcpyAsync(I, ws.I.p, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-        if (cmp) LIRA_CUDA_OK(cudaMemcpyAsync(cmp, ws.cmp.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
-        if (nprobe) LIRA_CUDA_OK(cudaMemcpyAsync(nprobe, ws.nprobe.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+        // results: device -> pinned staging (asynchronous, full PCIe rate) -> the caller's buffers
+        const size_t bD = (size_t)Q * k * 4, bI = (size_t)Q * k * 8, bC = cmp ? (size_t)Q * 8 : 0, bN = nprobe ? (size_t)Q * 4 : 0;
+        const size_t oI = (bD + 255) & ~(size_t)255, oC = oI + ((bI + 255) & ~(size_t)255), oN = oC + ((bC + 255) & ~(size_t)255);
+        const size_t total = oN + bN;
+        if (total > h->h_stage_cap) {
+            if (h->h_stage) cudaFreeHost(h->h_stage);
+            h->h_stage = nullptr;
+            h->h_stage_cap = 0;
+            LIRA_CUDA_OK(cudaHostAlloc(&h->h_stage, total + total / 4, cudaHostAllocDefault));
+            h->h_stage_cap = total + total / 4;
+        }
+        char* sg = (char*)h->h_stage;
+        LIRA_CUDA_OK(cudaMemcpyAsync(sg, ws.D.p, bD, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaMemcpyAsync(sg + oI, ws.I.p, bI, cudaMemcpyDeviceToHost, st));
+        if (cmp) LIRA_CUDA_OK(cudaMemcpyAsync(sg + oC, ws.cmp.p, bC, cudaMemcpyDeviceToHost, st));
+        if (nprobe) LIRA_CUDA_OK(cudaMemcpyAsync(sg + oN, ws.nprobe.p, bN, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        memcpy(D, sg, bD);
+        memcpy(I, sg + oI, bI);
+        if (cmp) memcpy(cmp, sg + oC, bC);
+        if (nprobe) memcpy(nprobe, sg + oN, bN);
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     return finish_timing(h);

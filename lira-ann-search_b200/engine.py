@@ -141,14 +141,22 @@ class LiraIndex:
                                     int(bool(dedup)), C.ptr(D, C.c_f32p), C.ptr(I, C.c_i64p), C.ptr(cmp_, C.c_i64p)))
         return D, I, cmp_
 
-    def probe_search(self, model, q, mode, value, k, dedup=True):
-        """The whole query phase for a batch of host queries. Returns (D, I, nprobe, cmp)."""
+    def probe_search(self, model, q, mode, value, k, dedup=True, out=None):
+        """The whole query phase for a batch of host queries. Returns (D, I, nprobe, cmp); `out` = such a tuple of
+        C-contiguous arrays from an earlier call is filled in place (no allocation per batch)."""
         q = C.f32(q).reshape(-1, self.dim)
         Q = q.shape[0]
-        D = np.empty((Q, k), np.float32)
-        I = np.empty((Q, k), np.int64)
-        npb = np.empty(Q, np.int32)
-        cmp_ = np.empty(Q, np.int64)
+        if out is not None:
+            D, I, npb, cmp_ = out
+            if not (D.shape == (Q, k) and D.dtype == np.float32 and I.shape == (Q, k) and I.dtype == np.int64
+                    and npb.shape == (Q,) and npb.dtype == np.int32 and cmp_.shape == (Q,) and cmp_.dtype == np.int64
+                    and all(a.flags.c_contiguous for a in out)):
+                raise ValueError("out: expected (float32[Q,k], int64[Q,k], int32[Q], int64[Q]) C-contiguous arrays")
+        else:
+            D = np.empty((Q, k), np.float32)
+            I = np.empty((Q, k), np.int64)
+            npb = np.empty(Q, np.int32)
+            cmp_ = np.empty(Q, np.int64)
         C.check(C.lib().lira_probe_search(self._h, model._h, C.ptr(q, C.c_f32p), Q, int(mode), float(value), int(k),
                                           int(bool(dedup)), C.ptr(D, C.c_f32p), C.ptr(I, C.c_i64p),
                                           C.ptr(npb, C.c_i32p), C.ptr(cmp_, C.c_i64p)))

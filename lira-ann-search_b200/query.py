@@ -163,3 +163,51 @@ def search_sweep(index: LiraIndex, model, x_q, gt_ids, k, thresholds=None, mode=
             out(f"QPS          : {row['QPS']:g} q/s")
             out("----------------------------------------")
     return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# redundancy assignment -- LIRA_smallscale.py:77-97 / LIRA_largescale.py:51-72
+# ---------------------------------------------------------------------------------------------
+def mul_partition_by_model(data_partition_score, data_predicts, xd_id_sorted_pre, data_2_bkt, cluster_cnts, cluster_ids,
+                           begin, end):
+    """The reference's per-point Python loop, vectorised (same arguments, same in-place effects on `data_2_bkt`,
+    `cluster_cnts` and `cluster_ids`, same append order inside every `cluster_ids[c]`).
+
+    For each point t of xd_id_sorted_pre[begin:end] (LIRA_smallscale.py:79-97): partitions ranked by score, descending;
+    n_actual = min(n_mul - 1, #partitions predicted for t); with `loc` the rank of t's current partition:
+      loc >= n_actual            -> the n_actual best go to columns 1..n_actual             (current partition kept in column 0)
+      else, n_eff == n_actual    -> the n_actual best replace columns 0..n_actual-1
+      else                       -> the n_actual + 1 best replace columns 0..n_actual
+    and t is appended to every chosen partition other than its current one. Equal scores are ranked by partition id
+    (torch.argsort leaves their order unspecified)."""
+    score = data_partition_score.detach().cpu().numpy() if hasattr(data_partition_score, "detach") else np.asarray(data_partition_score)
+    pred = data_predicts.detach().cpu().numpy() if hasattr(data_predicts, "detach") else np.asarray(data_predicts)
+    order = xd_id_sorted_pre.detach().cpu().numpy() if hasattr(xd_id_sorted_pre, "detach") else np.asarray(xd_id_sorted_pre)
+    t = np.asarray(order[begin:end], np.int64)
+    if t.size == 0:
+        return
+    n_mul = data_2_bkt.shape[1]
+    top = np.argsort(-score[t], axis=1, kind="stable")[:, :n_mul]          # the n_mul best partitions of every point
+    width = top.shape[1]
+    n_eff = (pred[t] != 0).sum(1)
+    n_act = np.minimum(n_mul - 1, n_eff)
+    cur = np.asarray(data_2_bkt[t, 0], np.int64)
+    hit = top == cur[:, None]
+    loc = np.where(hit.any(1), hit.argmax(1), width)                        # beyond the best n_mul: certainly >= n_actual
+    keep_cur = loc >= n_act
+    n_take = np.where(keep_cur | (n_eff == n_act), n_act, n_act + 1)
+    first_col = np.where(keep_cur, 1, 0)
+    j = np.arange(width)[None, :]
+    chosen = j < n_take[:, None]                                            # [points, rank]: this rank is written
+    rows, ranks = np.nonzero(chosen)
+    data_2_bkt[t[rows], first_col[rows] + ranks] = top[rows, ranks]
+    new = chosen & (top != cur[:, None])                                    # appended to a partition other than the current
+    rows, ranks = np.nonzero(new)                                           # row-major: points in order, ranks ascending
+    part, pts = top[rows, ranks], t[rows]
+    np.add.at(cluster_cnts, part, 1)
+    by_part = np.argsort(part, kind="stable")
+    part_s, pts_s = part[by_part], pts[by_part]
+    cuts = np.flatnonzero(np.diff(part_s)) + 1
+    for c, ids in zip(part_s[np.r_[0, cuts]] if part_s.size else [], np.split(pts_s, cuts) if part_s.size else []):
+        cluster_ids[int(c)].extend(int(x) for x in ids)
+

@@ -119,7 +119,13 @@ def run_reference_python(x_d, x_q, gt, n_bkt, k, metric, workdir, seed=0, epochs
     _, data_predicts, _, data_score = MP.model_evaluate(model, trl, crit, "cpu")
     order = torch.argsort(torch.sum(data_predicts, axis=1), descending=True)
     n_red = int(n_d * cfg.redundancy_ratio)
+    # inputs of the redundancy assignment, for the vectorised mirror (lira_ann_search_b200.query.mul_partition_by_model)
+    out["red_score"] = data_score.numpy().astype(np.float32)
+    out["red_order"] = order.numpy().astype(np.int64)
+    out["red_end"] = np.int64(n_red)
+    out["red_cnts_before"] = np.asarray(cluster_cnts, np.int64).copy()
     S.mul_partition_by_model(data_score, data_predicts, order, data_2_bkt, cluster_cnts, cluster_ids, begin=0, end=n_red)
+    out["red_cnts_after"] = np.asarray(cluster_cnts, np.int64).copy()
     cnt_q1, ids_q1 = U.get_knn_distr_redundancy(knn_query, data_2_bkt, cfg)
     idx1 = U.create_inner_indexes(x_d, cluster_ids, cfg)
     _, cmp1, found1 = S.get_cmp_recall(idx1, x_q, cluster_ids, cfg)
