@@ -146,17 +146,24 @@ int64_t lira_launch_count(void);
 int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes,
                            int64_t* scan_pairs);
 int lira_index_set_timing(lira_index_t* h, int enable);
-/* The online search (lira_search*, lira_probe_search*, lira_select_search*) has two exact implementations
- * of the list scan: fp32 CUDA cores (always valid) and tcgen05 tensor cores (taken for batches of >= 256
- * queries when every stored value and every query value is an integer of at most 11 bits and d <= 128, so
- * that TF32 products and fp32 sums are exact and both paths return identical bits).
+/* The online search (lira_search*, lira_probe_search*, lira_select_search*) has two implementations of the list
+ * scan with the same results: fp32 CUDA cores (always valid) and tcgen05 tensor cores, taken for batches of
+ * >= 256 queries and d <= 256 in one of two modes decided when the index is created:
+ *   mode 1 (exact): every stored value and every query value is an integer of at most 11 bits and |x|^2 < 2^22;
+ *           the kernel streams an fp16 copy of the rows, products and fp32 sums are exact, both paths return
+ *           identical bits;
+ *   mode 2 (approximate filter + exact re-rank, k <= 16): any other finite data; the kernel streams fp16(sigma v),
+ *           keeps every candidate whose rounded score is within a rigorous error margin of the running bound, and
+ *           every survivor is scored again exactly in fp32 from the original rows, so ids and distances agree with
+ *           the CUDA-core scan up to fp32 summation order (ties / 1e-6 relative).
  * set_use_tensor_cores(0) pins the CUDA-core scan; last_path reports which one ran (0 CUDA cores, 1 tensor
- * cores); tensor_core_eligible tells whether the stored vectors qualify. */
+ * cores); tensor_core_eligible / tensor_core_mode tell whether and how the stored vectors qualify (0, 1, 2). */
 int lira_index_set_use_tensor_cores(lira_index_t* h, int enable);
 int lira_index_last_path(const lira_index_t* h);
 int lira_index_last_redo(const lira_index_t* h); /* queries of the last tensor-core batch whose candidate buffer
                                                     overflowed and that were answered by the CUDA-core scan */
 int lira_index_tensor_core_eligible(const lira_index_t* h);
+int lira_index_tensor_core_mode(const lira_index_t* h);
 
 #ifdef __cplusplus
 }

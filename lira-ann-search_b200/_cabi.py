@@ -58,6 +58,7 @@ SIGNATURES = {
     "lira_index_last_path": (c_int, [c_vp]),
     "lira_index_last_redo": (c_int, [c_vp]),
     "lira_index_tensor_core_eligible": (c_int, [c_vp]),
+    "lira_index_tensor_core_mode": (c_int, [c_vp]),
 }
 
 _lib = None

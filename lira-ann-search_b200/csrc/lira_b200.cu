@@ -178,7 +178,10 @@ struct lira_index {
     CUtensorMap tmap_vaug, tmap_aaug;
     int nprobe_cap = 64;         // threshold selection without a host round trip keeps at most this many lists per query (adaptive)
     bool tc_force_sync = false;  // next tensor-core attempt uses the exact pair count (after a truncated / inexact optimistic run)
-    bool tc_ok = false;          // every stored value is a small integer: tensor-core path is exact
+    bool tc_ok = false;          // the tensor-core scan can serve this index (tc_mode != 0)
+    int tc_mode = 0;             // 1: exact (small integers, bit-identical results); 2: approximate filter + exact re-rank (real-valued data)
+    float tc_sigma = 1.0f;       // power-of-two scale of the fp16 shadow copy
+    float tc_vmax = 0.0f;        // largest |v| of the index (mode 2: error margin)
     bool use_tc = true;
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
     int last_redo = 0;           // queries of the last tensor-core batch redone on the CUDA cores
@@ -624,6 +627,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     *n_redo = 0;
     *retry = false;
     if (!h->tc_ok || Q < 256) return 0;
+    const bool approx = h->tc_mode == 2;
+    if (approx && k > TC_KMAX_TIGHTEN) return 0;   // the margin logic lives in the compaction path (k <= 16)
     // exhaustive probe sets (exact kNN over base segments): only with the in-kernel bound tightening (k <= 16); a
     // static seed bound alone would let a large share of a million-row base through
     if (ps.kind == 2 && k > TC_KMAX_TIGHTEN) return 0;
@@ -637,7 +642,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 12, cudaMemcpyHostToDevice, st));
     const bool optimistic = ps.kind == 0 && !h->tc_force_sync;   // no host round trip before the scan (checked at the end)
     h->tc_force_sync = false;
-    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), ws.flags.as<int>(), nullptr, nullptr, 0);
+    // |q|^2; exact mode: flags[0] is cleared unless the batch is exact in fp16 (approximate mode: the gather below clears it
+    // when a scaled query value does not fit fp16)
+    row_norms_kernel<<<grid_for(Q, 128), 128, 0, st>>>(d_q, ldq, h->ds, Q, ws.qnorm.as<float>(), approx ? nullptr : ws.flags.as<int>(), nullptr);
     LIRA_LAUNCH_CHECK();
     long long P = 0;
     const long long* po = nullptr;
@@ -660,7 +667,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.thr.ensure((size_t)Q * 4)) return rc;
     const int nk = (h->d16 + TC_KH - 1) / TC_KH;
     // L2: the gathered fp16 query rows carry the factor 2 of  s = 2 q.v - |v|^2  (exact: integers of <= 11 bits, doubled)
-    const float qscale = h->metric == LIRA_METRIC_IP ? 1.0f : 2.0f;
+    const bool is_ip = h->metric == LIRA_METRIC_IP;
+    const float qscale = (is_ip ? 1.0f : 2.0f) * h->tc_sigma;
+    // approximate mode: |accumulator - exact| <= M(q) = margin_c sqrt(sigma^2 |q|^2) + margin_abs (units of the scaled copy):
+    // operand rounding (2^-11 relative each, 5 % slack), fp32 accumulation inside the tensor core (2^-21 per term, generous),
+    // fp16 subnormal flushing of tiny components, and the (hi, lo) representation of sigma^2 |v|^2
+    float margin_c = 0.f, margin_abs = 0.f;
+    if (approx) {
+        const float W = h->tc_sigma * h->tc_vmax, sd = std::sqrt((float)h->d);
+        const float per = 1.05f * 0.0009765625f + (float)h->d16 * 4.76837158e-7f;
+        margin_c = W * ((is_ip ? 1.0f : 2.0f) * per + sd * 1.1920929e-7f);
+        margin_abs = W * sd * 5.9604645e-8f + (is_ip ? 0.0f : W * W * 9.5367432e-7f);
+    }
+    int* d_ok = approx ? ws.flags.as<int>() : nullptr;
     Workspace& sw = h->ws_seed;
     if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
@@ -687,7 +706,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         if (int rc = prepare_groups(h, sw, Q, seed, TC_M, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
         if (int rc = sw.gq.ensure((size_t)(Pseed + TC_M) * h->d16 * 2)) return rc;
         gather_group_queries_kernel<<<grid_for(Pseed * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(
-            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<__half>(), h->d16, qscale);
+            d_q, ldq, h->ds, sw.group_queries.as<int>(), Pseed, sw.group_offsets.as<long long>() + h->B, sw.gq.as<__half>(), h->d16, qscale, d_ok);
         LIRA_LAUNCH_CHECK();
         CUtensorMap tmap_sq;
         if (int rc = make_tmap_f16(&tmap_sq, sw.gq.as<__half>(), Pseed, h->d16, h->d16)) return rc;
@@ -700,6 +719,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.nk = nk;
         sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_TC;   // 0: whole lists
         sp.exp = 0;
+        sp.margin_c = margin_c;
+        sp.margin_abs = margin_abs;
+        sp.qn_scale = h->tc_sigma * h->tc_sigma;
         sp.qnorm = ws.qnorm.as<float>();
         sp.thr = ws.thr.as<uint32_t>();
         sp.cand_key = nullptr;
@@ -734,7 +756,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // ---- queries in group order (one TMA box per tile) ----
     if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
     gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale);
+                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale, d_ok);
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
     if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
@@ -758,6 +780,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     tp.cap = cap;
     tp.k = k;
     tp.is_ip = h->metric == LIRA_METRIC_IP;
+    tp.margin_c = margin_c;
+    tp.margin_abs = margin_abs;
+    tp.qn_scale = h->tc_sigma * h->tc_sigma;
     tp.trace = nullptr;
     tp.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) : 0;
     const char* trace_path = getenv("LIRA_TC_TRACE");   // debug: per-chunk clock stamps of CTA 0 -> CSV
@@ -773,16 +798,19 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
     RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), cap, po, ws.probe_slot.as<int>(), h->ids, k,
-                    (int)Q, dedup, h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1};
+                    (int)Q, dedup, h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1,
+                    h->vecs, (long long)h->ds, d_q, ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, margin_c, margin_abs,
+                    1.0f / (h->tc_sigma * h->tc_sigma)};
     const int warps = 8;
-    if (k <= 32) refine_topk_kernel<1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else refine_topk_kernel<4><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     LIRA_LAUNCH_CHECK();
     int fl[3] = {1, 0, 0};
     LIRA_CUDA_OK(cudaMemcpyAsync(fl, ws.flags.p, 12, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     *n_redo = fl[1];
-    if (optimistic && (fl[0] == 0 || fl[2] != 0)) {
+    if ((optimistic && (fl[0] == 0 || fl[2] != 0)) || (approx && fl[0] == 0)) {
         // the optimistic run is void: the batch is not exact in fp16 (-> the caller's CUDA-core path), or a probe set was
         // truncated (-> once more with the exact pair count and a larger cap from now on)
         if (fl[2] != 0) { h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4); *retry = fl[0] != 0; }
@@ -929,38 +957,57 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     LIRA_CUDA_OK(cudaMemcpy(h->d_list_order, order.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
     if (int rc = make_tmap(&h->tmap, h->vecs, h->E, h->ds, h->ds)) return rc;
     for (auto& e : h->ev) LIRA_CUDA_OK(cudaEventCreate(&e));
-    // |v|^2 per entry and the exactness flag that gates the tensor-core path
+    // |v|^2 per entry, the exactness flag and the largest norm: they decide how the tensor-core scan may be used
+    //   mode 1 (exact):       every value is an integer of <= 11 bits -> fp16 shadow copy is exact, results bit-identical
+    //   mode 2 (approximate): any other finite data with d <= 256 -> fp16(sigma v) shadow copy, rigorous error margin in the
+    //                         filter, every surviving candidate scored again exactly from the fp32 rows
     LIRA_CUDA_OK(cudaMalloc(&h->vnorm, (size_t)std::max<long long>(h->E, 1) * 4));
     int* d_flag = nullptr;
-    LIRA_CUDA_OK(cudaMalloc(&d_flag, 4));
-    int one = 1;
-    LIRA_CUDA_OK(cudaMemcpy(d_flag, &one, 4, cudaMemcpyHostToDevice));
-    LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)std::max<long long>(h->E, 1) * 32));
-    LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
-    {
-        std::vector<__half> a(128 * 16, __float2half(0.0f));
-        for (int r = 0; r < 128; ++r) { a[r * 16] = __float2half(-2048.0f); a[r * 16 + 1] = __float2half(-1.0f); }
-        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
-    }
+    LIRA_CUDA_OK(cudaMalloc(&d_flag, 8));
+    int init[2] = {1, 0};
+    LIRA_CUDA_OK(cudaMemcpy(d_flag, init, 8, cudaMemcpyHostToDevice));
     h->d16 = (h->ds + 7) / 8 * 8;
-    // fp16 shadow copy of the rows for the tensor-core scan (dropped again below when the data is not exact in fp16)
-    const bool want16 = h->d16 <= TC_MAX_KB * TC_KH;
-    if (want16) LIRA_CUDA_OK(cudaMalloc(&h->vecs16, (size_t)std::max<long long>(h->E, 1) * h->d16 * 2));
-    if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
-    if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
+    const bool want16 = h->d16 <= TC_MAX_KB * TC_KH && h->E > 0;
     if (h->E > 0) {
-        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag, h->vaug,
-                                                                              h->vecs16, h->d16);
+        row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag,
+                                                                              (uint32_t*)(d_flag + 1));
         g_launches.fetch_add(1);
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
-    LIRA_CUDA_OK(cudaMemcpy(&one, d_flag, 4, cudaMemcpyDeviceToHost));
+    LIRA_CUDA_OK(cudaMemcpy(init, d_flag, 8, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
-    h->tc_ok = (one == 1) && h->E > 0 && want16;
-    if (!h->tc_ok) {   // the CUDA-core scan never reads these
-        cudaFree(h->vecs16); h->vecs16 = nullptr;
-        cudaFree(h->vaug); h->vaug = nullptr;
-    } else {
+    float max_norm2;
+    memcpy(&max_norm2, &init[1], 4);
+    h->tc_mode = 0;
+    h->tc_sigma = 1.0f;
+    if (want16 && init[0] == 1) h->tc_mode = 1;
+    else if (want16 && max_norm2 > 0.f && max_norm2 < 1e30f && !getenv("LIRA_NO_APPROX_TC")) {
+        // sigma = 2^e with sigma * max|v| in (48, 96]: fp16 never overflows (|sigma v_i| <= 96, sigma^2 |v|^2 <= 9216) and
+        // ordinary components stay far above the fp16 subnormal range
+        const float vmax = std::sqrt(max_norm2);
+        int e = (int)std::floor(std::log2(96.0f / vmax));
+        e = std::max(-60, std::min(60, e));
+        h->tc_sigma = std::ldexp(1.0f, e);
+        h->tc_vmax = vmax;
+        h->tc_mode = 2;
+    }
+    h->tc_ok = h->tc_mode != 0;
+    if (h->tc_ok) {
+        LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)h->E * 32));
+        LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
+        LIRA_CUDA_OK(cudaMalloc(&h->vecs16, (size_t)h->E * h->d16 * 2));
+        std::vector<__half> a(128 * 16, __float2half(0.0f));
+        for (int r = 0; r < 128; ++r) {
+            a[r * 16] = __float2half(h->tc_mode == 1 ? -2048.0f : -1.0f);
+            a[r * 16 + 1] = __float2half(-1.0f);
+        }
+        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+        shadow_rows_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, h->tc_sigma,
+                                                                                h->tc_mode == 1, h->vecs16, h->d16, h->vaug);
+        g_launches.fetch_add(1);
+        LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
+        if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
         if (int rc = make_tmap_f16(&h->tmap16, h->vecs16, h->E, h->d16, h->d16)) return rc;
     }
     cudaDeviceProp prop;
@@ -1124,6 +1171,7 @@ int lira_index_set_use_tensor_cores(lira_index_t* h, int enable) {
 int lira_index_last_path(const lira_index_t* h) { return h ? h->last_path : -1; }
 int lira_index_last_redo(const lira_index_t* h) { return h ? h->last_redo : -1; }
 int lira_index_tensor_core_eligible(const lira_index_t* h) { return h ? (h->tc_ok ? 1 : 0) : -1; }
+int lira_index_tensor_core_mode(const lira_index_t* h) { return h ? h->tc_mode : -1; }
 
 int lira_index_set_timing(lira_index_t* h, int enable) {
     LIRA_REQUIRE(h, "null index");

@@ -83,6 +83,10 @@ struct TcParams {
     int cap;
     int k;
     int is_ip;
+    // approximate mode (real-valued data, fp16-rounded operands): the accumulator value differs from the exact one by at
+    // most M(q) = margin_c * sqrt(qn_scale |q|^2) + margin_abs (all in the units of the scaled shadow copy); 0 = exact mode
+    float margin_c, margin_abs;
+    float qn_scale;                  // |q|^2 is staged as qn_scale * qnorm[q] (sigma^2 of the shadow copy; 1 in exact mode)
     int exp;                         // experiments (LIRA_TC_EXP): bit 0 = skip the survivor path (wrong results, timing only)
     long long* trace;                // debug (LIRA_TC_TRACE): [TC_TRACE_ROLES][TC_TRACE_CHUNKS] SM clock stamps of CTA 0, or null
 };
@@ -306,7 +310,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         auto row_data = [&]() {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                rqn[j] = (rq[j] >= 0 && !p.is_ip) ? __ldg(p.qnorm + rq[j]) : 0.f;
+                rqn[j] = rq[j] >= 0 ? __ldg(p.qnorm + rq[j]) * p.qn_scale : 0.f;
                 rthr[j] = (rq[j] >= 0 && !SEED) ? *reinterpret_cast<const volatile uint32_t*>(p.thr + rq[j]) : 0xFF800000u;
             }
         };
@@ -486,7 +490,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (it.list < 0) break;
             const bool row_ok = row < it.q_count;
             int q = 0, cnt = 0;
-            float qn = 0.f, tq = -INFINITY;
+            float qn = 0.f, tq = -INFINITY, M = 0.f;
             float gmin[SEED ? TC_G : 1];
 #pragma unroll
             for (int g = 0; g < (SEED ? TC_G : 1); ++g) gmin[g] = INFINITY;
@@ -496,11 +500,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             uint32_t thr_pref = 0xFF800000u;
             if (row_ok) {
                 q = q_s;
-                qn = qn_s;
+                qn = p.is_ip ? 0.f : qn_s;
+                M = p.margin_c > 0.f ? fmaf(p.margin_c, sqrtf(qn_s), p.margin_abs) : 0.f;
                 if (!SEED) {
                     thr_q = p.thr + q;
                     thr_pref = thr_s;
-                    tq = ordered_to_f32(thr_pref) - qn;   // score <= T  <=>  t <= tq   (qn = 0 for IP)
+                    // exact score <= T  <=  accumulator-side t <= T - qn + M  (qn = 0 for IP, M = 0 in exact mode): tq is
+                    // the bound the (possibly rounded) accumulator values are compared with
+                    tq = ordered_to_f32(thr_pref) - qn + M;
                     cand = p.cand_key + ((size_t)(it.q_begin + row) * TC_PARTS + part) * cap;
                 }
             }
@@ -527,7 +534,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_fence_after();
                 if (warp == 0) stamp(5, m);
                 if (warp == 5) stamp(7, m);
-                if (!SEED && row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn);
+                if (!SEED && row_ok) tq = fminf(tq, ordered_to_f32(thr_now) - qn + M);
                 for (int h = 0; h < nh; ++h) {   // the two 128-column halves of the accumulator, one after the other
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_NS + h * TC_N + part * NCOL;
                 uint32_t ra[32], rb[NG > 1 ? 32 : 1];
@@ -615,14 +622,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                     const uint32_t sk = __shfl_sync(0xffffffffu, sc, __ffs(mk) - 1);     // k-th best score
                                     // kept: everything at or below the k-th score (ties stay, their id order is settled by
                                     // the refine pass); ranks are the sorted order, so the kept keys are ranks 0 .. n_keep-1
-                                    const bool keep = sc <= sk;
+                                    // (approximate mode: the k kept candidates' exact scores are at most sk + M, and an entry
+                                    //  can only be dropped when its exact score is certainly above that: approx > sk + 2 M)
+                                    const float sk_f = ordered_to_f32(sk);
+                                    const float M_L = __shfl_sync(0xffffffffu, M, L);
+                                    const bool keep = sc <= (M_L > 0.f ? f32_to_ordered(sk_f + 2.f * M_L) : sk);
                                     if (keep) reg[rank] = key;
                                     const int n_keep = __popc(__ballot_sync(0xffffffffu, keep));
                                     if (lane == L) {
                                         cnt = n_keep;
                                         if (n_keep >= TC_CAPK - 4) { lost = true; cnt = p.k; }   // (nearly) all ties: give the query up
-                                        tq = fminf(tq, ordered_to_f32(sk) - qn);
-                                        atomicMin(p.thr + q, sk);
+                                        tq = fminf(tq, sk_f + M - qn + M);
+                                        atomicMin(p.thr + q, M > 0.f ? f32_to_ordered(sk_f + M) : sk);
                                     }
                                     __syncwarp();
                                 }
@@ -653,7 +664,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     tc_sort16(b); tc_sort16(c); tc_merge_low16(b, c);
                     tc_merge_low16(a, b);
                     const float tk = tc_pick16(a, p.k - 1);
-                    atomicMin(p.thr + q, f32_to_ordered(tk + qn));
+                    atomicMin(p.thr + q, f32_to_ordered(tk + qn + M));
                 }
             } else if (row_ok) {
                 p.cand_count[(size_t)(it.q_begin + row) * TC_PARTS + part] = lost ? cap + 1 : cnt;
@@ -672,12 +683,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // |x|^2 per row in fp32 (sequential order); *exact_flag is cleared unless every value is an integer of at
 // most 11 bits (exact in fp16) and every |x|^2 < 2^22: then all products / partial sums of the tensor-core
 // path are integers below 2^24 and its result equals the fp32 direct-difference result bit for bit.
-// vaug (may be null): the row's augmented-K block [hi, lo, 0 x 14] in fp16 with |x|^2 = 2048 hi + lo, hi and lo
-// integers below 2048 (exact in fp16) when |x|^2 is an integer below 2^22; the A side holds (-2048, -1, 0 ...).
-// x16 (may be null): the fp16 shadow copy of the rows, [n, d16] with zero padding (d16 % 8 == 0).
+// max_norm_bits (may be null): atomicMax of the float bits of |x|^2 (a NaN / inf row makes it NaN / inf).
 __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, long long n, float* __restrict__ out,
-                                 int* __restrict__ exact_flag, __half* __restrict__ vaug, __half* __restrict__ x16, int d16) {
+                                 int* __restrict__ exact_flag, uint32_t* __restrict__ max_norm_bits) {
     bool bad = false;
+    float mx = 0.f;
+    bool nan = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float* r = x + i * ld;
         float s = 0.f;
@@ -686,35 +697,55 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long ld, int d, lo
             s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
             bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
             bad |= !(fabsf(v.x) <= 2047.f && fabsf(v.y) <= 2047.f && fabsf(v.z) <= 2047.f && fabsf(v.w) <= 2047.f);
-            if (x16) {
-                __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(x16 + i * d16 + j) = pk;
-            }
         }
-        if (x16)
-            for (int j = d; j < d16; j += 4) *reinterpret_cast<uint2*>(x16 + i * d16 + j) = make_uint2(0u, 0u);
         out[i] = s;
-        if (vaug) {
-            const float hi = floorf(s * (1.0f / 2048.0f));
-            __half2 h = __floats2half2_rn(hi, s - hi * 2048.0f);
-            uint4 w = make_uint4(*reinterpret_cast<uint32_t*>(&h), 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(vaug + i * 16) = w;
-            *reinterpret_cast<uint4*>(vaug + i * 16 + 8) = make_uint4(0u, 0u, 0u, 0u);
-        }
         bad |= !(s < 4194304.0f);  // |x|^2 < 2^22  =>  |q|^2 + |v|^2 + 2|q.v| < 2^24
+        nan |= !(s == s);
+        mx = fmaxf(mx, s);
     }
     if (bad && exact_flag) *exact_flag = 0;
+    if (max_norm_bits) atomicMax(max_norm_bits, nan ? 0x7FC00000u : __float_as_uint(mx));
+}
+
+// The fp16 shadow copy of the rows for the tensor-core scan: x16[n, d16] = fp16(sigma x) (zero padded, d16 % 8 == 0) and
+// the row's augmented-K block vaug[n, 16] that puts -sigma^2 |x|^2 into the accumulator:
+//   exact mode (integers of <= 11 bits, sigma = 1):  (hi, lo, 0 ..) with |x|^2 = 2048 hi + lo, A side (-2048, -1, 0 ..)
+//   approximate mode (real-valued data):             (hi, lo, 0 ..) with sigma^2 |x|^2 = hi + lo (+- 2^-21 relative), A side (-1, -1, 0 ..)
+__global__ void shadow_rows_kernel(const float* __restrict__ x, long ld, int d, long long n, const float* __restrict__ norm,
+                                   float sigma, int exact_mode, __half* __restrict__ x16, int d16, __half* __restrict__ vaug) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* r = x + i * ld;
+        for (int j = 0; j < d; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(r + j);
+            __half2 h0 = __floats2half2_rn(v.x * sigma, v.y * sigma), h1 = __floats2half2_rn(v.z * sigma, v.w * sigma);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(x16 + i * d16 + j) = pk;
+        }
+        for (int j = d; j < d16; j += 4) *reinterpret_cast<uint2*>(x16 + i * d16 + j) = make_uint2(0u, 0u);
+        const float s = norm[i] * sigma * sigma;
+        float hi, lo;
+        if (exact_mode) {
+            hi = floorf(s * (1.0f / 2048.0f));
+            lo = s - hi * 2048.0f;
+        } else {
+            hi = __half2float(__float2half_rn(s));
+            lo = s - hi;
+        }
+        __half2 h = __floats2half2_rn(hi, lo);
+        *reinterpret_cast<uint4*>(vaug + i * 16) = make_uint4(*reinterpret_cast<uint32_t*>(&h), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(vaug + i * 16 + 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // gq[slot, :] = fp16(scale * q[group_queries[slot], :])  (queries in group order, so a tile of a group is one TMA box;
 // zero padded to d16 columns). n_slots (device scalar = group_offsets[B]) is the number of valid slots: explicit probe
 // sets may hold invalid (-1) entries, so it can be smaller than the host-side bound P the buffers were sized with.
+// ok_flag (may be null) is cleared when a scaled value does not fit fp16 (approximate mode: the batch then takes the CUDA cores).
 __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
                                             long long P, const long long* __restrict__ n_slots, __half* __restrict__ gq, int d16,
-                                            float scale) {
+                                            float scale, int* __restrict__ ok_flag) {
     const int per_row = d16 / 4;
     const long long total = (*n_slots < P ? *n_slots : P) * per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -722,6 +753,9 @@ __global__ void gather_group_queries_kernel(const float* __restrict__ q, long ld
         const int c = (int)(i % per_row) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < ds) v = *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+        if (ok_flag && !(fabsf(v.x * scale) <= 60000.f && fabsf(v.y * scale) <= 60000.f && fabsf(v.z * scale) <= 60000.f &&
+                         fabsf(v.w * scale) <= 60000.f))
+            *ok_flag = 0;
         __half2 h0 = __floats2half2_rn(v.x * scale, v.y * scale), h1 = __floats2half2_rn(v.z * scale, v.w * scale);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -793,14 +827,31 @@ struct RefineParams {
     long long* out_ids;
     int* redo;      // [Q] 1 when a region of the query overflowed `cap` (its row is left for the exact path)
     int* n_redo;    // number of such queries
+    // approximate mode (EXACT = true): the regions hold approximate scores; every candidate that can still make the top k
+    // is scored again exactly from the fp32 rows (direct difference / dot product in fp32, as the CUDA-core scan does)
+    const float* vecs;      // [E, ldv] fp32 list rows
+    long long ldv;
+    const float* q;         // [Q, ldq] queries
+    long long ldq;
+    int d;
+    const float* qnorm;     // [Q] |q|^2
+    float qn_scale, margin_c, margin_abs, inv_scale;   // scaled units of the shadow copy; inv_scale = 1 / sigma^2
 };
 
-template <int S>
+template <int S, bool EXACT>
 __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= p.Q) return;
     const int k = p.k;
+    // EXACT: this lane's dimensions (lane, lane + 32, ...) of the query, d <= 256; the error bound M of the approximate scores
+    float qreg[EXACT ? 8 : 1];
+    float M = 0.f;
+    if (EXACT) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qreg[j] = (lane + 32 * j < p.d) ? p.q[(size_t)q * p.ldq + lane + 32 * j] : 0.f;
+        M = fmaf(p.margin_c, sqrtf(p.qnorm[q] * p.qn_scale), p.margin_abs);
+    }
     unsigned long long key[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) key[s] = KEY_INF;
@@ -829,17 +880,38 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
             unsigned long long x[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = (r0 + r < cnt) ? srcp[r0 + r] : KEY_INF;
+            if (!EXACT) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-                if (x[r] != KEY_INF) x[r] = (x[r] & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(x[r]));  // entry -> global id
+                for (int r = 0; r < 16; ++r)
+                    if (x[r] != KEY_INF) x[r] = (x[r] & 0xFFFFFFFF00000000ull) | (uint32_t)__ldg(p.list_ids + key_pos(x[r]));  // entry -> global id
+            }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 if (r0 + r >= max_cnt) break;
-                uint32_t mm = __ballot_sync(0xffffffffu, x[r] < kth);
+                uint32_t mm = EXACT ? __ballot_sync(0xffffffffu, x[r] != KEY_INF) : __ballot_sync(0xffffffffu, x[r] < kth);
                 while (mm) {
                     const int sl = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    const unsigned long long y = shfl_u64(x[r], sl);
+                    unsigned long long y = shfl_u64(x[r], sl);
+                    if (EXACT) {
+                        // the approximate score minus its error bound is a lower bound of the exact score
+                        const float lower = (key_score(y) - M) * p.inv_scale;
+                        if (kth != KEY_INF && lower > key_score(kth)) continue;
+                        const uint32_t entry = key_pos(y);
+                        const float* v = p.vecs + (size_t)entry * p.ldv;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (lane + 32 * j < p.d) {
+                                const float vv = __ldg(v + lane + 32 * j);
+                                if (p.is_ip) acc = fmaf(qreg[j], vv, acc);
+                                else { const float df = qreg[j] - vv; acc = fmaf(df, df, acc); }
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        y = make_key(p.is_ip ? -acc : acc, (uint32_t)__ldg(p.list_ids + entry));
+                    }
                     if (!(y < kth)) continue;
                     bool dup = false;
                     if (p.dedup) {

@@ -222,6 +222,12 @@ class LiraIndex:
     def tensor_core_eligible(self) -> bool:
         return bool(C.lib().lira_index_tensor_core_eligible(self._h))
 
+    @property
+    def tensor_core_mode(self) -> str:
+        """'exact' (small-integer data, bit-identical to the CUDA cores), 'approximate' (real-valued data: fp16 filter with
+        an error margin + exact fp32 re-rank) or 'none'."""
+        return {1: "exact", 2: "approximate"}.get(int(C.lib().lira_index_tensor_core_mode(self._h)), "none")
+
     # ---- instrumentation ------------------------------------------------------------------
     def set_timing(self, enable=True):
         C.check(C.lib().lira_index_set_timing(self._h, int(enable)))

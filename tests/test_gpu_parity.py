@@ -336,24 +336,55 @@ def test_tensor_core_region_compaction_without_seed(L, metric, k, monkeypatch):
     assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
 
 
-def test_tensor_core_path_is_not_taken_for_inexact_data(L):
-    x_d, x_q = synth(8000, 32, 300, seed=8, integer=False)  # real-valued: not exact in TF32
-    cl = random_lists(len(x_d), 8, np.random.RandomState(1))
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("d,scale", [(96, 1.0), (32, 37.5), (100, 1e-3)])
+def test_tensor_core_approximate_mode_for_real_valued_data(L, metric, d, scale):
+    """Real-valued data: fp16 filter with a rigorous error margin + exact fp32 re-rank of every survivor. Ids must equal the
+    oracle's except for fp32 ties, distances within 1e-5 relative, at any data scale (the shadow copy is rescaled)."""
+    rng = np.random.RandomState(d)
+    x_d, x_q = synth(30000, d, 600, seed=8 + d, integer=False)
+    x_d, x_q = (x_d * scale).astype(np.float32), (x_q * scale).astype(np.float32)
+    if d == 96:   # DEEP-style: unit vectors
+        x_d /= np.linalg.norm(x_d, axis=1, keepdims=True)
+        x_q /= np.linalg.norm(x_q, axis=1, keepdims=True)
+    B = 16
+    cl = random_lists(len(x_d), B, rng, redundancy=0.4, empty=(2,))
     off, ids, vecs = lists_csr(x_d, cl)
-    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
-    assert not index.tensor_core_eligible
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    assert index.tensor_core_eligible and index.tensor_core_mode == "approximate"
+    nprobe = rng.randint(0, 6, len(x_q))
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    pids = np.concatenate([rng.choice(B, n, replace=False) for n in nprobe] + [np.empty(0, int)]).astype(np.int32)
+    for k in (10, 1, 16):
+        D, I, cmp_ = index.search(x_q, poff, pids, k)
+        assert index.last_path == "tensor-core"
+        I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 1)
+        assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, metric)
+        assert np.array_equal(cmp_, cmp_ref)
+    # k > 16 and the pinned CUDA-core scan agree as well
+    D, I, _ = index.search(x_q, poff, pids, 40)
+    assert index.last_path == "cuda-core"
+    index.set_use_tensor_cores(False)
+    D2, I2, _ = index.search(x_q, poff, pids, 10)
+    assert index.last_path == "cuda-core"
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, 10, metric, O.F64, 1)
+    assert_topk_equiv(D2, I2, D_ref, I_ref, x_q, x_d, metric)
+
+
+def test_tensor_core_exact_mode_falls_back_for_real_valued_queries(L):
+    x_d, x_q = synth(8000, 32, 300, seed=8, integer=False)  # real-valued queries
+    cl = random_lists(len(x_d), 8, np.random.RandomState(1))
+    xi, _ = synth(8000, 32, 300, seed=8, integer=True)      # integer base: exact mode
+    off, ids, vecs = lists_csr(xi, cl)
     poff = np.arange(len(x_q) + 1, dtype=np.int64) * 2
     pids = np.tile(np.array([0, 3], np.int32), len(x_q))
-    D, I, _ = index.search(x_q, poff, pids, 10)
-    assert index.last_path == "cuda-core"
-    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
-    assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, O.L2)
-    # integer base but a real-valued query batch: the batch check sends it to the CUDA cores
-    xi, _ = synth(8000, 32, 300, seed=8, integer=True)
     index2 = L.LiraIndex.from_csr(xi, off, ids, O.L2)
-    assert index2.tensor_core_eligible
+    assert index2.tensor_core_eligible and index2.tensor_core_mode == "exact"
     D, I, _ = index2.search(x_q, poff, pids, 10)
-    assert index2.last_path == "cuda-core"
+    assert index2.last_path == "cuda-core"   # the batch check sends it to the CUDA cores
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
+    assert_topk_equiv(D, I, D_ref, I_ref, x_q, xi, O.L2)
 
 
 def test_tensor_core_query_phase_matches_cuda_cores(L, golden):
