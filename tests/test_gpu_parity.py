@@ -494,3 +494,67 @@ def test_knn_tensor_core_path_matches_oracle(L):
     D2, I2 = L.knn(x_d, x_d[:512], k, O.L2)
     D2_ref, I2_ref = O.knn(x_d, x_d[:512], k, O.L2, O.F64)
     assert np.array_equal(I2, I2_ref) and np.array_equal(D2, D2_ref.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full size (config 1 shape: 1 M x 128, B = 1024, 10 000 queries, k = 10): size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("real", [False, True])
+def test_full_size_properties(L, real):
+    """At the full config-1 size the oracle is too slow for every query, so the result is checked through properties:
+    rows sorted best-first, ids distinct and members of the probed lists, distances equal to the exact value recomputed
+    from the returned ids, cmp = sum of the probed list sizes, idempotence, the tensor-core scan equal to the CUDA-core
+    scan on every row (bit-identical for integer data, up to fp32 ties for real-valued data), and the oracle on a sample."""
+    rng = np.random.RandomState(11)
+    N, d, Q, B, k, nprobe = 1_000_000, 128, 10_000, 1024, 10, 10
+    centres = rng.randn(256, d).astype(np.float32)
+    x_d = centres[rng.randint(0, 256, N)] + 0.5 * rng.randn(N, d).astype(np.float32)
+    x_q = centres[rng.randint(0, 256, Q)] + 0.5 * rng.randn(Q, d).astype(np.float32)
+    if real:
+        x_d /= np.linalg.norm(x_d, axis=1, keepdims=True)
+        x_q /= np.linalg.norm(x_q, axis=1, keepdims=True)
+    else:
+        x_d = np.clip(np.round(24 * x_d + 100), 0, 255).astype(np.float32)
+        x_q = np.clip(np.round(24 * x_q + 100), 0, 255).astype(np.float32)
+    d2b = np.full((N, 2), -1, np.int32)
+    d2b[:, 0] = rng.randint(0, B, N)
+    red = rng.choice(N, N * 3 // 100, replace=False)           # 3 % of the points get a second list
+    d2b[red, 1] = (d2b[red, 0] + 1 + rng.randint(0, B - 1, len(red))) % B
+    index = L.LiraIndex.from_data_2_bkt(x_d, d2b, B, O.L2)
+    assert index.tensor_core_mode == ("approximate" if real else "exact")
+    pids = np.stack([rng.choice(B, nprobe, replace=False) for _ in range(Q)]).astype(np.int32)
+    poff = np.arange(Q + 1, dtype=np.int64) * nprobe
+    D, I, cmp_ = index.search(x_q, poff, pids.reshape(-1), k)
+    assert index.last_path == "tensor-core"
+    # sorted best-first, full rows, distinct ids
+    assert np.all(np.diff(D, axis=1) >= 0) and np.all(I >= 0)
+    assert all(len(set(r)) == k for r in I[::97].tolist())
+    # every id lives in one of the probed lists of its query
+    member = (d2b[I][:, :, :, None] == pids[:, None, None, :]).any(axis=(2, 3))
+    assert member.all()
+    # distances are the exact values of the returned ids
+    exact = ((x_q[:, None, :].astype(np.float64) - x_d[I].astype(np.float64)) ** 2).sum(-1)
+    assert np.allclose(D, exact, rtol=1e-5, atol=1e-6)
+    # Computations column: sum of the probed list sizes
+    sizes = index.list_sizes()
+    assert np.array_equal(cmp_, sizes[pids].sum(1))
+    # idempotence, and the CUDA-core scan returns the same rows
+    D2, I2, _ = index.search(x_q, poff, pids.reshape(-1), k)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    index.set_use_tensor_cores(False)
+    Dc, Ic, cc = index.search(x_q, poff, pids.reshape(-1), k)
+    assert index.last_path == "cuda-core" and np.array_equal(cc, cmp_)
+    if real:
+        assert np.allclose(D, Dc, rtol=1e-5, atol=1e-6) and (I == Ic).all(1).mean() > 0.999
+    else:
+        assert np.array_equal(D, Dc) and np.array_equal(I, Ic)
+    # the oracle on a sample of the queries
+    off, ids, vecs = O.build_lists_from_data_2_bkt(x_d, d2b, B)
+    sel = np.arange(0, Q, 250)
+    po = np.arange(len(sel) + 1, dtype=np.int64) * nprobe
+    I_ref, D_ref, _ = O.search(off, ids, vecs, x_q[sel], po, pids[sel].reshape(-1), k, O.L2, O.F64, 1)
+    if real:
+        assert_topk_equiv(D[sel], I[sel], D_ref, I_ref, x_q[sel], x_d, O.L2)
+    else:
+        assert np.array_equal(I[sel], I_ref) and np.array_equal(D[sel], D_ref)
+
