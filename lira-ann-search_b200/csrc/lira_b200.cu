@@ -967,7 +967,7 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     int init[2] = {1, 0};
     LIRA_CUDA_OK(cudaMemcpy(d_flag, init, 8, cudaMemcpyHostToDevice));
     h->d16 = (h->ds + 7) / 8 * 8;
-    const bool want16 = h->d16 <= TC_MAX_KB * TC_KH && h->E > 0;
+    const bool want16 = h->d16 <= TC_MAX_KB_STREAM * TC_KH && h->E > 0;
     if (h->E > 0) {
         row_norms_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, d_flag,
                                                                               (uint32_t*)(d_flag + 1));

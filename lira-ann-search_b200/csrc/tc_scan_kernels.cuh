@@ -40,6 +40,13 @@ static constexpr int TC_KBLK_BYTES = TC_M * ROW_BYTES;  // 16 KiB: 128 rows x 12
 static constexpr int TC_AUG_BYTES = TC_N * 32;          // 4 KiB: 128 rows x 16 halves
 static constexpr int TC_SKB_BYTES = TC_NH * B_STAGE_BYTES;                        // 32 KiB: one K block of a chunk (256 rows x 128 B)
 static constexpr int TC_SLOT_BYTES = TC_SLOT_KB * TC_SKB_BYTES + TC_NH * TC_AUG_BYTES;   // 72 KiB
+static constexpr int TC_MAX_KB_STREAM = 16;   // d <= 1024 in the streaming mode below
+// Streaming mode (d > 256, e.g. GIST's 960): the query tile no longer fits next to the B ring, so BOTH operands stream, one K
+// block per ring slot: [A: 128 queries x 64 halves = 16 KiB][B: 256 vectors x 64 halves = 32 KiB][augmented-K boxes 8 KiB];
+// the A tile is re-read (from L2) for every chunk. The slots overlay the A area + the B ring of the resident mode.
+static constexpr int TC_STREAM_NSLOT = 3;
+static constexpr int TC_STREAM_SLOT_BYTES = TC_KBLK_BYTES + TC_SKB_BYTES + TC_NH * TC_AUG_BYTES;   // 56 KiB
+static_assert(TC_STREAM_NSLOT * TC_STREAM_SLOT_BYTES <= TC_A_KB * TC_KBLK_BYTES + TC_NSLOT * TC_SLOT_BYTES, "streaming ring must fit the operand area");
 static constexpr int TC_PARTS = 4;       // filter pass: column parts per accumulator = epilogue warps per TMEM lane quadrant
 static constexpr int TC_EPI_WARPS = 4 * TC_PARTS;   // filter pass: each epilogue warp takes 128 / TC_PARTS accumulator columns
 static constexpr int TC_SEED_EPI_WARPS = 4;         // seed pass: one warp per quadrant takes all 128 columns
@@ -215,9 +222,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint64_t* bars = (uint64_t*)(sGA + TC_AUG_BYTES);
     uint64_t* a_full = bars;                        // [2]
     uint64_t* a_empty = a_full + 2;                 // [2]
-    uint64_t* b_full = a_empty + 2;                 // [TC_NSLOT]
-    uint64_t* b_empty = b_full + TC_NSLOT;          // [TC_NSLOT]
-    uint64_t* t_full = b_empty + TC_NSLOT;          // [TC_NACC]
+    constexpr int NSLOT_MAX = TC_NSLOT > TC_STREAM_NSLOT ? TC_NSLOT : TC_STREAM_NSLOT;
+    uint64_t* b_full = a_empty + 2;                 // [NSLOT_MAX]
+    uint64_t* b_empty = b_full + NSLOT_MAX;         // [NSLOT_MAX]
+    uint64_t* t_full = b_empty + NSLOT_MAX;         // [TC_NACC]
     uint64_t* t_empty = t_full + TC_NACC;           // [TC_NACC]
     uint64_t* i_full = t_empty + TC_NACC;           // [TC_NQ]
     uint64_t* i_empty = i_full + TC_NQ;             // [TC_NQ]
@@ -237,7 +245,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const bool aug = !p.is_ip;   // inner product: the accumulator is q.v itself, no augmented block
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < NSLOT_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < TC_NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], N_EPI); }
         for (int i = 0; i < TC_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 1 + N_EPI); }  // MMA + epilogue warps
         mbar_init(ga_full, 1);
@@ -257,6 +265,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // A tiles: with d <= 128 (nk <= 2) two query tiles fit, so the next work item's queries load while this item's MMAs run
     const int nabuf = nk <= TC_A_KB / 2 ? 2 : 1;
     const int a_kb = TC_A_KB / nabuf;
+    // d > 256: streaming mode (see TC_STREAM_*): A rides in the ring slots, one K block per slot
+    const bool stream_a = nk > TC_A_KB;
+    const int slot_kb = stream_a ? 1 : TC_SLOT_KB;                          // K blocks per ring slot
+    const int nslot = stream_a ? TC_STREAM_NSLOT : TC_NSLOT;
+    const uint32_t slot_bytes = stream_a ? TC_STREAM_SLOT_BYTES : TC_SLOT_BYTES;
+    uint8_t* const ring = stream_a ? sA : sB;
+    const uint32_t slot_b_off = stream_a ? TC_KBLK_BYTES : 0;               // B operand inside a slot
+    const uint32_t slot_aug_off = slot_b_off + slot_kb * TC_SKB_BYTES;      // augmented-K boxes inside a slot
 
     // debug timeline of CTA 0: one clock stamp per (role, chunk)
     auto stamp = [&](int role, uint32_t chunk) {
@@ -348,36 +364,40 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 ++stage;
             };
             const int ab = n % nabuf;
-            mbar_wait(&a_empty[ab], ((n / nabuf) & 1) ^ 1u);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
-                for (int kb = 0; kb < nk; ++kb)
-                    tma_load_2d(sA + (size_t)(ab * a_kb + kb) * TC_KBLK_BYTES, &tmap_q, kb * TC_KH, it.q_begin, &a_full[ab]);
+            if (!stream_a) {
+                mbar_wait(&a_empty[ab], ((n / nabuf) & 1) ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[ab], (uint32_t)nk * TC_KBLK_BYTES);
+                    for (int kb = 0; kb < nk; ++kb)
+                        tma_load_2d(sA + (size_t)(ab * a_kb + kb) * TC_KBLK_BYTES, &tmap_q, kb * TC_KH, it.q_begin, &a_full[ab]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             const long long lo = it.lo, hi = it.hi;
             for (long long row0 = lo; row0 < hi; row0 += TC_NS, ++mp) {
                 stamp(0, mp);
                 if (stage < N_STAGES) advance_prefetch();
                 const int nh = hi - row0 > TC_N ? TC_NH : 1;   // boxes of 128 rows in this chunk (the tail of a list may need one only)
-                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {   // one slot = up to TC_SLOT_KB K blocks (+ the aug boxes with the first)
-                    const int nkb = min(TC_SLOT_KB, nk - kb0);
+                for (int kb0 = 0; kb0 < nk; kb0 += slot_kb) {   // one slot = up to slot_kb K blocks (+ the aug boxes with the first)
+                    const int nkb = min(slot_kb, nk - kb0);
                     const bool with_aug = aug && kb0 == 0;
                     mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
                     if (elect_one()) {
-                        uint8_t* slot = sB + (size_t)bs.stage * TC_SLOT_BYTES;
-                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)(nkb * nh) * B_STAGE_BYTES + (with_aug ? nh * TC_AUG_BYTES : 0));
+                        uint8_t* slot = ring + (size_t)bs.stage * slot_bytes;
+                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)(nkb * nh) * B_STAGE_BYTES + (with_aug ? nh * TC_AUG_BYTES : 0) +
+                                                                     (stream_a ? (uint32_t)TC_KBLK_BYTES : 0u));
+                        if (stream_a) tma_load_2d(slot, &tmap_q, kb0 * TC_KH, it.q_begin, &b_full[bs.stage]);   // this K block of the queries
                         for (int j = 0; j < nkb; ++j)
                             for (int x = 0; x < nh; ++x)
-                                tma_load_2d(slot + (size_t)j * TC_SKB_BYTES + (size_t)x * B_STAGE_BYTES, &tmap_v, (kb0 + j) * TC_KH,
+                                tma_load_2d(slot + slot_b_off + (size_t)j * TC_SKB_BYTES + (size_t)x * B_STAGE_BYTES, &tmap_v, (kb0 + j) * TC_KH,
                                             (int)row0 + x * TC_N, &b_full[bs.stage]);
                         if (with_aug)
                             for (int x = 0; x < nh; ++x)
-                                tma_load_2d(slot + TC_SLOT_KB * TC_SKB_BYTES + (size_t)x * TC_AUG_BYTES, &tmap_vaug, 0, (int)row0 + x * TC_N,
+                                tma_load_2d(slot + slot_aug_off + (size_t)x * TC_AUG_BYTES, &tmap_vaug, 0, (int)row0 + x * TC_N,
                                             &b_full[bs.stage]);
                     }
                     __syncwarp();
-                    bs.advance(TC_NSLOT);
+                    bs.advance(nslot);
                 }
             }
             while (stage < N_STAGES) advance_prefetch();   // short list: the rest of the look-ahead (waited for)
@@ -390,7 +410,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         int cta_items = 0;
         if constexpr (TRACE) cta_t0 = (long long)global_timer_ns();
         if (aug) { mbar_wait(ga_full, 0); tc_fence_after(); }
-        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+        const uint32_t sA_u32 = smem_u32(sA), ring_u32 = smem_u32(ring);
         const uint64_t ga_desc = tc_smem_desc_sw32(smem_u32(sGA));
         for (int n = 0;; ++n) {
             const int qs = n % TC_NQ;
@@ -400,8 +420,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (lane == 0) mbar_arrive(&i_empty[qs]);
             if (it.list < 0) break;
             const int ab = n % nabuf;
-            mbar_wait(&a_full[ab], (n / nabuf) & 1);
-            tc_fence_after();
+            if (!stream_a) {
+                mbar_wait(&a_full[ab], (n / nabuf) & 1);
+                tc_fence_after();
+            }
             const long long lo = it.lo, hi = it.hi;
             if constexpr (TRACE) {
                 if (p.trace && lane == 0 && blockIdx.x < TC_TRACE_CTAS && n < TC_TRACE_ITEMS) {
@@ -416,19 +438,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 stamp(1, m);
                 const uint32_t d_tmem = tmem_base + acc * TC_NS;
                 const uint32_t idesc = hi - row0 > TC_N ? TC_IDESC_F16 : TC_IDESC_F16_N128;   // (the tail of a list: N = 128)
-                for (int kb0 = 0; kb0 < nk; kb0 += TC_SLOT_KB) {
-                    const int nkb = min(TC_SLOT_KB, nk - kb0);
+                for (int kb0 = 0; kb0 < nk; kb0 += slot_kb) {
+                    const int nkb = min(slot_kb, nk - kb0);
                     mbar_wait(&b_full[bs.stage], bs.phase);
                     tc_fence_after();
                     if (kb0 == 0) stamp(2, m);
-                    if (kb0 + TC_SLOT_KB >= nk) stamp(3, m);
-                    const uint32_t slot = sB_u32 + (uint32_t)bs.stage * TC_SLOT_BYTES;
+                    if (kb0 + slot_kb >= nk) stamp(3, m);
+                    const uint32_t slot = ring_u32 + (uint32_t)bs.stage * slot_bytes;
                     if (elect_one()) {
                         if (aug && kb0 == 0)   // s = -|v|^2 ...
-                            tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + TC_SLOT_KB * TC_SKB_BYTES), idesc, 0u);
+                            tc_mma_f16(d_tmem, ga_desc, tc_smem_desc_sw32(slot + slot_aug_off), idesc, 0u);
                         for (int jb = 0; jb < nkb; ++jb) {   // ... + (2 q) . v
-                            const uint32_t a_addr = sA_u32 + (uint32_t)(ab * a_kb + kb0 + jb) * TC_KBLK_BYTES;
-                            const uint32_t b_addr = slot + (uint32_t)jb * TC_SKB_BYTES;
+                            const uint32_t a_addr = stream_a ? slot : sA_u32 + (uint32_t)(ab * a_kb + kb0 + jb) * TC_KBLK_BYTES;
+                            const uint32_t b_addr = slot + slot_b_off + (uint32_t)jb * TC_SKB_BYTES;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)  // 4 x K = 16 fp16 (32 bytes) inside the 128-byte swizzle row
                                 tc_mma_f16(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), idesc,
@@ -437,14 +459,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         tc_commit(&b_empty[bs.stage]);  // frees the slot when these MMAs have read it
                     }
                     __syncwarp();
-                    bs.advance(TC_NSLOT);
+                    bs.advance(nslot);
                 }
                 if (elect_one()) tc_commit(&t_full[acc]);            // accumulator complete -> epilogue
                 __syncwarp();
                 stamp(4, m);
             }
-            if (elect_one()) tc_commit(&a_empty[ab]);                // all MMAs reading this A tile are done
-            __syncwarp();
+            if (!stream_a) {
+                if (elect_one()) tc_commit(&a_empty[ab]);            // all MMAs reading this A tile are done
+                __syncwarp();
+            }
             ++cta_items;
         }
         if constexpr (TRACE) {
@@ -907,6 +931,11 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
                                 if (p.is_ip) acc = fmaf(qreg[j], vv, acc);
                                 else { const float df = qreg[j] - vv; acc = fmaf(df, df, acc); }
                             }
+                        }
+                        for (int jj = lane + 256; jj < p.d; jj += 32) {   // d > 256: the rest of the query row from L1 / L2
+                            const float vv = __ldg(v + jj), qq = __ldg(p.q + (size_t)q * p.ldq + jj);
+                            if (p.is_ip) acc = fmaf(qq, vv, acc);
+                            else { const float df = qq - vv; acc = fmaf(df, df, acc); }
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

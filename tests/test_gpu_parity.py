@@ -558,3 +558,47 @@ def test_full_size_properties(L, real):
     else:
         assert np.array_equal(I[sel], I_ref) and np.array_equal(D[sel], D_ref)
 
+
+def test_gist_shape_top_nprobe_sweep(L):
+    """Config 3 shape (GIST: d = 960, real-valued, top-nprobe selection, nprobe swept): beyond d = 256 the query tile is
+    streamed through the ring together with the list rows (both operands, one K block per slot); approximate mode +
+    exact re-rank. Ids / distances vs the oracle, and vs the fp32 CUDA-core scan."""
+    import torch
+    rng = np.random.RandomState(960)
+    x_d, x_q = synth(12000, 960, 300, seed=3, integer=False)
+    x_d, x_q = (0.1 * x_d + 0.5).astype(np.float32), (0.1 * x_q + 0.5).astype(np.float32)   # [0, 1]-ish like GIST
+    B, k = 32, 10
+    cl = random_lists(len(x_d), B, rng, redundancy=0.1)
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    assert index.tensor_core_mode == "approximate"
+    scores = rng.rand(len(x_q), B).astype(np.float32)
+    dev = torch.device("cuda:0")
+    d_s, d_q = torch.as_tensor(scores, device=dev), torch.as_tensor(x_q, device=dev)
+    for nprobe in (1, 2, 8, 32):
+        index.set_use_tensor_cores(True)
+        D, I, npb, cmp_ = [t.cpu().numpy() for t in index.select_search_dev(d_s, d_q, L.SELECT_TOPN, nprobe, k)]
+        assert index.last_path == "tensor-core" and np.all(npb == nprobe)
+        poff, pids = O.select(scores, O.SELECT_TOPN, nprobe)
+        I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, O.L2, O.F64, 1)
+        assert_topk_equiv(D, I, D_ref, I_ref, x_q, x_d, O.L2)
+        assert np.array_equal(cmp_, cmp_ref)
+        index.set_use_tensor_cores(False)
+        Dc, Ic, _, _ = [t.cpu().numpy() for t in index.select_search_dev(d_s, d_q, L.SELECT_TOPN, nprobe, k)]
+        assert index.last_path == "cuda-core"
+        assert_topk_equiv(Dc, Ic, D_ref, I_ref, x_q, x_d, O.L2)
+    # integer data of the same width: exact mode through the streaming ring, bit-identical
+    xi_d, xi_q = synth(6000, 300, 300, seed=4, integer=True)
+    cl = random_lists(len(xi_d), 8, rng, redundancy=0.1)
+    off, ids, vecs = lists_csr(xi_d, cl)
+    index = L.LiraIndex.from_csr(xi_d, off, ids, O.L2)
+    assert index.tensor_core_mode == "exact"
+    poff = np.arange(len(xi_q) + 1, dtype=np.int64) * 3
+    pids = np.stack([rng.choice(8, 3, replace=False) for _ in range(len(xi_q))]).astype(np.int32).reshape(-1)
+    D, I, _ = index.search(xi_q, poff, pids, k)
+    assert index.last_path == "tensor-core"
+    I_ref, D_ref, _ = O.search(off, ids, vecs, xi_q, poff, pids, k, O.L2, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
+    # beyond d = 1024: CUDA cores
+    x_w, _ = synth(600, 1100, 4, seed=5, integer=False)
+    assert L.LiraIndex.from_csr(x_w, np.array([0, 600], np.int64), np.arange(600, dtype=np.int32), O.L2).tensor_core_mode == "none"
