@@ -629,9 +629,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (!h->tc_ok || Q < 256) return 0;
     const bool approx = h->tc_mode == 2;
     if (approx && k > TC_KMAX_TIGHTEN) return 0;   // the margin logic lives in the compaction path (k <= 16)
-    // exhaustive probe sets (exact kNN over base segments): only with the in-kernel bound tightening (k <= 16); a
-    // static seed bound alone would let a large share of a million-row base through
-    if (ps.kind == 2 && k > TC_KMAX_TIGHTEN) return 0;
+    // exhaustive probe sets (exact kNN over base segments) with k > 16: no in-kernel tightening, so the static seed must be
+    // good: the CUDA-core seed scans two whole segments (below); a segment shorter than that would make the bound loose
+    if (ps.kind == 2 && k > TC_KMAX_TIGHTEN && h->E < 4 * 8192) return 0;
     LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
     Workspace& ws = h->ws;
     if (int rc = ws.qnorm.ensure((size_t)Q * 4)) return rc;
@@ -748,7 +748,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         long long Pseed = 0;
         const long long* po_seed = nullptr;
         if (int rc = prepare_groups(h, sw, Q, seed, SCAN_TM_MAX, nullptr, &Pseed, &po_seed, nullptr, nullptr, nullptr, st)) return rc;
-        if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, TC_SEED_ROWS, false, st)) return rc;
+        // (exact kNN: the first two segments whole -- the k-th best of 16 384 base rows lets k N / 16 384 rows per query through)
+        if (int rc = simt_scan(h, sw, d_q, ldq, Pseed, k, 0, ps.kind == 2 ? 8192 : TC_SEED_ROWS, false, st)) return rc;
         seed_threshold_kernel<<<grid_for(Q, 128), 128, 0, st>>>(sw.part_key.as<unsigned long long>(), sw.probe_slot.as<int>(),
                                                                 ws.top1.as<int>(), (int)Q, k, ws.thr.as<uint32_t>());
         LIRA_LAUNCH_CHECK();
