@@ -882,28 +882,34 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
     unsigned long long kth = KEY_INF;
     bool overflow = false;
     const long long lo = p.probe_offsets[q], hi = p.probe_offsets[q + 1];
-    constexpr int PPP = 32 / TC_PARTS;   // probes per pass
-    for (long long j0 = lo; j0 < hi; j0 += PPP) {
-        // PPP probes = 32 regions per pass: lane l looks at region (probe j0 + l / TC_PARTS, part l % TC_PARTS)
-        const long long j = j0 + (lane / TC_PARTS);
-        int region = -1, cnt = 0;
-        if (j < hi) {
-            const int slot = p.probe_slot[j];
-            if (slot >= 0) {
-                region = slot * TC_PARTS + (lane % TC_PARTS);
-                cnt = p.cand_count[region];
+    constexpr int PPP = 32 / TC_PARTS;   // probes per 32 regions
+    for (long long j0 = lo; j0 < hi; j0 += 2 * PPP) {
+        // 2 PPP probes = 64 regions per pass, TWO per lane: lane l looks at regions (probe j0 + l / TC_PARTS, part l % TC_PARTS) and
+        // (probe j0 + PPP + l / TC_PARTS, same part); the loads of both are in flight together, which halves the chain of dependent
+        // global round trips (slot -> count -> keys -> ids) a query with more than PPP probes has to wait for
+        int cnt2[2];
+        const unsigned long long* src2[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const long long j = j0 + w * PPP + (lane / TC_PARTS);
+            int region = -1, cnt = 0;
+            if (j < hi) {
+                const int slot = p.probe_slot[j];
+                if (slot >= 0) {
+                    region = slot * TC_PARTS + (lane % TC_PARTS);
+                    cnt = p.cand_count[region];
+                }
             }
+            overflow |= cnt > p.cap;
+            cnt2[w] = cnt < p.cap ? cnt : p.cap;
+            src2[w] = p.cand_key + (size_t)(region < 0 ? 0 : region) * p.cap;
         }
-        overflow |= cnt > p.cap;
-        cnt = cnt < p.cap ? cnt : p.cap;
-        const unsigned long long* srcp = p.cand_key + (size_t)(region < 0 ? 0 : region) * p.cap;
-        const int max_cnt = __reduce_max_sync(0xffffffffu, cnt);
-        for (int r0 = 0; r0 < max_cnt; r0 += 16) {
-            // every lane pulls up to 16 entries of ITS region: all key loads, then all id loads, are in flight together
-            // (two dependent round trips per block instead of two per region)
+        const int max_cnt = __reduce_max_sync(0xffffffffu, max(cnt2[0], cnt2[1]));
+        for (int r0 = 0; r0 < max_cnt; r0 += 8) {
+            // every lane pulls up to 8 entries of EACH of its two regions: all key loads, then all id loads, are in flight together
             unsigned long long x[16];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) x[r] = (r0 + r < cnt) ? srcp[r0 + r] : KEY_INF;
+            for (int r = 0; r < 16; ++r) x[r] = (r0 + (r & 7) < cnt2[r >> 3]) ? src2[r >> 3][r0 + (r & 7)] : KEY_INF;
             if (!EXACT) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r)
@@ -911,7 +917,7 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
             }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                if (r0 + r >= max_cnt) break;
+                if (r0 + (r & 7) >= max_cnt) continue;
                 uint32_t mm = EXACT ? __ballot_sync(0xffffffffu, x[r] != KEY_INF) : __ballot_sync(0xffffffffu, x[r] < kth);
                 while (mm) {
                     const int sl = __ffs(mm) - 1;
