@@ -284,7 +284,7 @@ def test_self_knn_drops_column_zero_like_compute_knn(L):
 # tensor-core (tcgen05) scan path: must return the same bits as the exact CUDA-core scan
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("metric", [O.L2, O.IP])
-@pytest.mark.parametrize("k,d", [(10, 128), (10, 96), (100, 64), (1, 20)])
+@pytest.mark.parametrize("k,d", [(10, 128), (10, 96), (100, 64), (1, 20), (10, 200), (16, 256), (10, 8)])
 def test_tensor_core_scan_is_bit_identical(L, metric, k, d):
     rng = np.random.RandomState(17 + k + d)
     x_d, x_q = synth(30000, d, 700, seed=31 + d, integer=True)
@@ -337,7 +337,7 @@ def test_tensor_core_region_compaction_without_seed(L, metric, k, monkeypatch):
 
 
 @pytest.mark.parametrize("metric", [O.L2, O.IP])
-@pytest.mark.parametrize("d,scale", [(96, 1.0), (32, 37.5), (100, 1e-3)])
+@pytest.mark.parametrize("d,scale", [(96, 1.0), (32, 37.5), (100, 1e-3), (250, 1.0), (400, 5.0)])
 def test_tensor_core_approximate_mode_for_real_valued_data(L, metric, d, scale):
     """Real-valued data: fp16 filter with a rigorous error margin + exact fp32 re-rank of every survivor. Ids must equal the
     oracle's except for fp32 ties, distances within 1e-5 relative, at any data scale (the shadow copy is rescaled)."""
@@ -602,3 +602,30 @@ def test_gist_shape_top_nprobe_sweep(L):
     # beyond d = 1024: CUDA cores
     x_w, _ = synth(600, 1100, 4, seed=5, integer=False)
     assert L.LiraIndex.from_csr(x_w, np.array([0, 600], np.int64), np.arange(600, dtype=np.int32), O.L2).tensor_core_mode == "none"
+
+
+@pytest.mark.parametrize("Q", [256, 257, 383, 1000])
+def test_tensor_core_batch_size_edges(L, Q):
+    """Batch sizes around the tensor-core threshold (256) and off every tile size; lists of 0, 1 and 129 entries; a query
+    that probes nothing and one that probes the same list twice."""
+    rng = np.random.RandomState(Q)
+    x_d, x_q = synth(9000, 48, Q, seed=Q, integer=True)
+    B = 12
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3, empty=(4,))
+    cl[5] = cl[5][:1]
+    cl[6] = cl[6][:129]
+    off, ids, vecs = lists_csr(x_d, cl)
+    nprobe = rng.randint(1, 5, Q)
+    nprobe[0] = 0
+    sets = [rng.choice(B, n, replace=False) for n in nprobe]
+    sets[1] = np.array([6, 6, 5])   # a repeated list
+    poff = np.zeros(Q + 1, np.int64)
+    np.cumsum([len(x) for x in sets], out=poff[1:])
+    pids = np.concatenate(sets + [np.empty(0, int)]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    for k in (10, 3):
+        D, I, cmp_ = index.search(x_q, poff, pids, k)
+        assert index.last_path == "tensor-core"
+        I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, O.L2, O.F64, 1)
+        assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
+
