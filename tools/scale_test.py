@@ -6,6 +6,12 @@ part is the library's grouped list scan with explicit probe sets (nprobe nearest
 Checks the ids of a query sample against a brute-force scan of the probed entries and prints one JSON line.
 
     python tools/scale_test.py [--N 12500000] [--Q 10000] [--B 1024] [--nprobe 16] [--steps 5]
+
+Under torchrun (WORLD_SIZE > 1) the entries of every list are striped over the ranks (entry j of a list -> rank j mod world,
+SURVEY.md 8e): every rank builds the same dataset, keeps its stripe, answers every query on it, and the per-rank top-k lists
+are merged by an NCCL all-gather + lira_merge_ranks_dev; the merged result is checked against the brute-force scan.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/scale_test.py --N 8000000
 """
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,7 +32,13 @@ ap.add_argument("--real", action="store_true", help="real-valued unit vectors (D
 ap.add_argument("--compare-cuda-cores", action="store_true", help="also time the fp32 CUDA-core scan")
 args = ap.parse_args()
 L._cabi.require_gpu()
-dev = torch.device("cuda:0")
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device(f"cuda:{local}")
+if world > 1:
+    import torch.distributed as tdist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    tdist.init_process_group("nccl", device_id=dev)
 N, d, Q, B, k = args.N, args.d, args.Q, args.B, args.k
 t0 = time.time()
 g = torch.Generator(device=dev).manual_seed(43)
@@ -78,7 +90,18 @@ del x_d
 torch.cuda.synchronize()
 print(f"[scale] data + lists on the device: {time.time() - t0:.1f}s; E = {E} entries, list sizes {int(sizes.min())}..{int(sizes.max())}",
       file=sys.stderr, flush=True)
-index = L.LiraIndex.from_device(vecs, ids, off.cpu().numpy(), d, "L2")
+if world > 1:
+    # this rank's stripe of every list: entries at positions j = rank (mod world) of the list
+    pos = torch.arange(E, device=dev) - torch.repeat_interleave(off[:-1], sizes)
+    mine = (pos % world) == rank
+    my_vecs, my_ids = vecs[mine].contiguous(), ids[mine].contiguous()
+    my_sizes = torch.clamp((sizes - rank + world - 1) // world, min=0)
+    my_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    my_off[1:] = torch.cumsum(my_sizes, 0)
+    del pos, mine
+else:
+    my_vecs, my_ids, my_off = vecs, ids, off
+index = L.LiraIndex.from_device(my_vecs, my_ids, my_off.cpu().numpy(), d, "L2", device=local)
 expect_mode = "none" if d > 1024 else ("approximate" if args.real else "exact")   # d > 1024: the fp32 CUDA-core scan answers
 assert index.tensor_core_mode == expect_mode
 # probe sets: nprobe nearest centroids
@@ -86,16 +109,26 @@ pids = torch.cdist(x_q, cent).topk(args.nprobe, dim=1, largest=False).indices.to
 poff = (torch.arange(Q + 1, device=dev, dtype=torch.int64) * args.nprobe).contiguous()
 index.set_timing(True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for _ in range(3):
+def answer():
     D, I, cmp_ = index.search_dev(x_q, poff, pids, k)
+    if world > 1:
+        from lira_ann_search_b200.parallel import allgather_merge
+        D, I = allgather_merge(D, I, k, "L2", dedup=True, device=local)
+    return D, I, cmp_
+
+
+for _ in range(3):
+    D, I, cmp_ = answer()
 torch.cuda.synchronize()
 assert index.last_path == ("cuda-core" if expect_mode == "none" else "tensor-core")
 ms, scan_ms, scan_bytes, scan_pairs = [], [], [], []
 for _ in range(args.steps):
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        tdist.barrier()
     e0.record()
-    D, I, cmp_ = index.search_dev(x_q, poff, pids, k)
+    D, I, cmp_ = answer()
     e1.record()
     e1.synchronize()
     ms.append(e0.elapsed_time(e1))
@@ -133,9 +166,17 @@ if args.compare_cuda_cores:
     simt_ms = e0.elapsed_time(e1)
     same_ids = float((I2 == I).all(1).float().mean())
     index.set_use_tensor_cores(True)
+if world > 1:   # the slowest rank's time counts; every rank scanned its stripe
+    t = torch.tensor([float(np.mean(ms))], device=dev)
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    ms = [float(t.item())]
+    c = cmp_.double().clone()
+    tdist.all_reduce(c)
+    cmp_ = c
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 s_ms = float(np.mean(scan_ms))
-print(json.dumps({"workload": "unit vectors, full 2x redundancy (DEEP style)" if args.real else "config 5 shard (1/8 of BigANN-100M shape, full 2x redundancy)", "N": N, "entries": E, "Q": Q, "B": B,
+if rank == 0:
+  print(json.dumps({"n_gpus": world, "sharding": "list entries striped over the ranks + NCCL all-gather + merge" if world > 1 else "none", "workload": "unit vectors, full 2x redundancy (DEEP style)" if args.real else "config 5 shard (1/8 of BigANN-100M shape, full 2x redundancy)", "N": N, "entries": E, "Q": Q, "B": B,
                   "nprobe": args.nprobe, "k": k, "ms_per_batch": float(np.mean(ms)), "qps": Q / (float(np.mean(ms)) * 1e-3),
                   "scan_kernel_ms": s_ms, "scan_algorithmic_bytes": float(np.mean(scan_bytes)),
                   "scan_gbs_algorithmic": float(np.mean(scan_bytes)) / (s_ms * 1e-3) / 1e9,
@@ -146,3 +187,5 @@ print(json.dumps({"workload": "unit vectors, full 2x redundancy (DEEP style)" if
                   "checked_queries": min(args.check, Q), "mismatches": bad, "redo": index.last_redo,
                   "tensor_core_mode": index.tensor_core_mode,
                   "cuda_core_ms_per_batch": simt_ms, "rows_with_identical_ids_vs_cuda_cores": same_ids if simt_ms else None}), flush=True)
+if world > 1:
+    tdist.destroy_process_group()
