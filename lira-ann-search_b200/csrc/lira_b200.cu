@@ -614,6 +614,7 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
 }
 
 static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows of each of the two best probed lists
+static constexpr int TC_SEED_ROWS_MAIN = 2048;   // seed pass on the filter's own work items: first rows of every probed list (0 = all; measured best)
 static constexpr int TC_SEED_ROWS_TC = 0;     // tensor-core seed (k <= 16): rows of each of the two best probed lists (0 = all: the pass streams
                                               // (nearly) every list once anyway, and whole lists halve the survivors of the filter pass)
 
@@ -682,7 +683,47 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     }
     int* d_ok = approx ? ws.flags.as<int>() : nullptr;
     Workspace& sw = h->ws_seed;
-    if (k <= TC_KMAX_TIGHTEN) {
+    // ---- queries in group order (one TMA box per tile) ----
+    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
+    gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
+                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale, d_ok);
+    LIRA_LAUNCH_CHECK();
+    CUtensorMap tmap_q;
+    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
+    // Seed, k <= 16 and probe sets that are a small part of the index: the seed pass runs on the SAME work items as the filter
+    // pass (no second grouping, no second gather) and EVERY (query, list) pair takes part: the k-th smallest of the 64 group
+    // minima of a query's row in a list bounds the final k-th score, the smallest over the query's lists wins (atomicMin).
+    // Exhaustive probe sets (exact kNN) keep the two-segment seed below: a full extra pass would double their work.
+    const bool seed_on_main = k <= TC_KMAX_TIGHTEN && ps.kind != 2 && !getenv("LIRA_TC_SEED_SEPARATE");
+    if (seed_on_main) {
+        fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u /* f32_to_ordered(+inf) */);
+        LIRA_LAUNCH_CHECK();
+        TcParams sp;
+        sp.group_queries = ws.group_queries.as<int>();
+        sp.list_offsets = h->d_offsets;
+        sp.items = ws.items.as<ScanItem>();
+        sp.n_items = ws.n_items.as<int>();
+        sp.work_counter = ws.n_items.as<int>() + 1;
+        sp.nk = nk;
+        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_MAIN;
+        sp.exp = 0;
+        sp.margin_c = margin_c;
+        sp.margin_abs = margin_abs;
+        sp.qn_scale = h->tc_sigma * h->tc_sigma;
+        sp.qnorm = ws.qnorm.as<float>();
+        sp.thr = ws.thr.as<uint32_t>();
+        sp.cand_key = nullptr;
+        sp.cand_count = nullptr;
+        sp.cap = 0;
+        sp.trace = nullptr;
+        sp.k = k;
+        sp.is_ip = h->metric == LIRA_METRIC_IP;
+        if (!getenv("LIRA_TC_NO_SEED")) {
+            tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
+            LIRA_LAUNCH_CHECK();
+            LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.as<int>() + 1, 0, 4, st));   // the filter pass takes its tickets from 0 again
+        }
+    } else if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
         if (int rc = sw.probe_ids.ensure((size_t)(Q + 1) * 4)) return rc;
@@ -755,13 +796,6 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                                                                 ws.top1.as<int>(), (int)Q, k, ws.thr.as<uint32_t>());
         LIRA_LAUNCH_CHECK();
     }
-    // ---- queries in group order (one TMA box per tile) ----
-    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
-    gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale, d_ok);
-    LIRA_LAUNCH_CHECK();
-    CUtensorMap tmap_q;
-    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
     // ---- filter on the tensor cores ----
     // one private candidate region per (pair, column part); every valid pair's owner writes its count
     const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
