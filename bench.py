@@ -291,7 +291,7 @@ def run_reference(args, wl, wl_path, thr, log):
         sample = f"first {n_sample} queries, threshold {thr:g}, recall@{k} {recall_at(out_ids, wl['gt'][:n_sample], k):.4f}"
     line = {"metric": "qps_at_recall10_ge_0.95", "value": value, "unit": "queries/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / value,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "sift1m-shape", "N": int(wl["x_d"].shape[0]), "d": int(wl["x_d"].shape[1]),
                        "Q": int(len(wl["x_q"])), "B": int(wl["centroids"].shape[0]), "k": k, "threshold": thr},
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": used, "kind": kind, "sample": sample,
