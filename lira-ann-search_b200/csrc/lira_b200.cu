@@ -499,9 +499,9 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
                         (nosync && ps.mode != LIRA_SELECT_TOPN) ? per_q_cap : 0, d_trunc_flag};
         select_kernel<4><<<qgrid, warps * 32, 0, st>>>(sp);
         LIRA_LAUNCH_CHECK();
-        exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.nsel.as<int>(), ws.probe_offsets.as<long long>(), (int)Q);
-        LIRA_LAUNCH_CHECK();
-        exclusive_scan_kernel<<<1, 1024, 0, st>>>(ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
+        // both prefix sums in one launch: block 0 the probe offsets over the queries, block 1 the group offsets over the lists
+        exclusive_scan_kernel<<<2, 1024, 0, st>>>(ws.nsel.as<int>(), ws.probe_offsets.as<long long>(), (int)Q,
+                                                  ws.list_count.as<int>(), ws.group_offsets.as<long long>(), B);
         LIRA_LAUNCH_CHECK();
         // the one host round trip of the query phase: P sizes the partial-result buffers
         if (nosync) {

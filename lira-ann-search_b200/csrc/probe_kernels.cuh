@@ -268,7 +268,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
 
 // exclusive scan of int counts into long long offsets (n+1 entries), single CTA of 1024 threads, 8 elements per
 // thread and round
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* in, long long* out, int n) {
+// (in1 / out1 / n1, optional: a second, independent scan done by block 1 of the same launch)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* in, long long* out, int n, const int* in1 = nullptr,
+                                                              long long* out1 = nullptr, int n1 = 0) {
+    if (blockIdx.x == 1) { in = in1; out = out1; n = n1; }
     __shared__ long long warp_sum[32];
     __shared__ long long carry_s;
     constexpr int PER = 8;
