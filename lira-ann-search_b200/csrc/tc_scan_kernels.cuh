@@ -1,24 +1,28 @@
-// K2-TC: the grouped list scan on the 5th-generation tensor cores (tcgen05 + TMEM), used for large
-// query batches where the fp32 CUDA-core scan is compute-bound by an order of magnitude.
+// K2-TC: the grouped list scan on the 5th-generation tensor cores (tcgen05 + TMEM), used for query batches
+// of 256 and more, where the fp32 CUDA-core scan is compute-bound by an order of magnitude.
 //
-//   seed     an exact CUDA-core scan (scan_lists_kernel) over the first rows of every query's best
-//            probed list gives T[q], a valid upper bound of the final k-th best score (any k real
-//            candidates bound it).
-//   filter   this file: for a tile of 128 queries x one inverted list, D = Q_tile . V^T is computed by
-//            tcgen05.mma kind::f16 from the fp16 shadow copy of the list rows (exact for this data, see below; half
-//            the HBM / shared-memory bytes and twice the MMA rate of TF32) that TMA staged in shared memory
-//            (128-byte swizzle, K-major), accumulators in TMEM (4 x 128 columns, so the epilogue of one
-//            chunk overlaps the MMAs of the next three). Epilogue warps read their query row with
-//            tcgen05.ld and keep only the candidates with  |q|^2 + |v|^2 - 2 q.v <= T[q]
-//            (one FADD + compare per pair); survivors are appended to the query's candidate buffer.
-//   refine   per query: candidates -> exact top-k with id de-duplication.
+//   seed     tc_scan_kernel<true>: the same pipeline as the filter over the first rows of every probed list, on the
+//            filter's own work items; per (query, list) row it keeps 64 group minima of the score, whose k-th smallest
+//            bounds the query's final k-th best score (k real, distinct candidates of one list); the smallest bound
+//            over a query's lists is T[q] (atomicMin). Exact kNN (exhaustive probe sets) seeds from two base segments.
+//   filter   tc_scan_kernel<false>: for a tile of 128 queries x one inverted list, D = Q_tile . V^T is computed by
+//            tcgen05.mma kind::f16 (M = 128, N = 256, K = 16) from the fp16 shadow copy of the list rows that TMA
+//            staged in shared memory (128-byte swizzle, K-major); an augmented K block adds -|v|^2, so the
+//            accumulator (2 x 256 TMEM columns: the epilogue of one chunk overlaps the MMAs of the next) holds
+//            2 q.v - |v|^2. 16 epilogue warps read their query rows with tcgen05.ld, test 32 columns at a time
+//            against T[q] - |q|^2 with a 3-input-max tree, append the survivors to private candidate regions and
+//            tighten T[q] whenever a region fills up and is compacted to its k best.
+//   refine   refine_topk_kernel: per query, candidate regions -> top-k over distinct ids (mode 2: after scoring every
+//            candidate that can still make it again exactly in fp32 from the original rows).
 //
-// Exactness: this path is taken only when every stored value and every query value of the batch is an
-// integer of at most 11 bits (exactly representable in fp16, e.g. SIFT / BigANN-style data) and
-// |x|^2 < 2^22. Then every product and partial sum is an integer below 2^24, the tensor-core result
-// (fp16 operands, fp32 accumulation) equals the fp32 direct-difference result bit for bit, and ids and
-// distances are identical to the CUDA-core path. Other data keeps the exact CUDA-core scan
-// (scan_kernels.cuh).
+// Mode 1 (exact): every stored value and every query value of the batch is an integer of at most 11 bits (exactly
+// representable in fp16, e.g. SIFT / BigANN-style data) and |x|^2 < 2^22. Then every product and partial sum is an
+// integer below 2^24, the tensor-core result (fp16 operands, fp32 accumulation) equals the fp32 direct-difference
+// result bit for bit, and ids and distances are identical to the CUDA-core path.
+// Mode 2 (approximate filter + exact re-rank, k <= 16): any other finite data; the shadow copy is fp16(sigma v), every
+// bound carries a rigorous margin M(q) for the rounding of the operands, and the refine pass re-scores the survivors
+// exactly, so the results agree with the CUDA-core path up to fp32 summation order.
+// d <= 256: the query tile is resident in shared memory; 256 < d <= 1024: both operands stream (TC_STREAM_*).
 #pragma once
 #include <cuda_fp16.h>
 #include "scan_kernels.cuh"
