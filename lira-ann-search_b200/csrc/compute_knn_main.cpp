@@ -10,6 +10,11 @@
 // The reference's IVF branch (nprobe != 0) trades accuracy for CPU time; the GPU search is exact at any size, so
 // every nprobe value produces the exact result (method: flat_exact, no _ivf_nprobe suffix). n_threads is accepted
 // and ignored.
+//
+// Not in the reference (opt-in):  compute_knn <dataset> <data_path> <k> --queries
+//   exact ground truth of the QUERY set against the base: reads {dataset}_query.fvecs (or .bvecs) and writes
+//   {data_path}/{dataset}/{dataset}_groundtruth.ivecs (per row: int32 k, then the k base ids, best first) -- the file
+//   utils.load_data (utils.py:54-76) and search.cpp:341-343 read. The reference ships it with the datasets.
 #include <sys/stat.h>
 
 #include <chrono>
@@ -63,13 +68,15 @@ bool exists(const std::string& p) {
 
 int main(int argc, char** argv) {
     if (argc < 4) {
-        std::cout << "Usage: " << argv[0] << " <dataset> <data_path> <k> [nprobe] [n_threads]" << std::endl;
+        std::cout << "Usage: " << argv[0] << " <dataset> <data_path> <k> [nprobe] [n_threads]   |   <dataset> <data_path> <k> --queries" << std::endl;
         std::cout << "  exact brute-force self-kNN on the GPU (any nprobe gives the exact result)" << std::endl;
         return 1;
     }
     const std::string dataset = argv[1], data_path = argv[2];
     const int k = std::atoi(argv[3]);
-    if (k < 1 || k > 127) { std::cerr << "Error: k must be in [1, 127]" << std::endl; return 1; }
+    bool query_mode = false;
+    for (int a = 4; a < argc; ++a) query_mode |= std::string(argv[a]) == "--queries";
+    if (k < 1 || k > (query_mode ? 128 : 127)) { std::cerr << "Error: k must be in [1, " << (query_mode ? 128 : 127) << "]" << std::endl; return 1; }
 
     std::cout << "=== GPU KNN Computation (liblira_b200) ===" << std::endl;
     std::cout << "Dataset: " << dataset << std::endl;
@@ -96,6 +103,45 @@ int main(int argc, char** argv) {
     const double read_time = now_s() - t0;
     std::cout << "Loaded " << n << " vectors of dimension " << dim << std::endl;
     std::cout << "Read time: " << read_time << "s" << std::endl;
+
+    if (query_mode) {
+        // ---- ground truth of the query set: k exact neighbours of every query, written as .ivecs ----
+        std::string qfile = dir + "/" + dataset + "_query.fvecs";
+        bool qb = false;
+        if (!exists(qfile)) { qfile = dir + "/" + dataset + "_query.bvecs"; qb = true; }
+        if (!exists(qfile)) { std::cerr << "Error: Cannot find query file for dataset " << dataset << std::endl; return 1; }
+        int64_t nq = 0;
+        int qdim = 0;
+        std::vector<float> queries;
+        if (!(qb ? read_vecs<uint8_t>(qfile, queries, nq, qdim) : read_vecs<float>(qfile, queries, nq, qdim))) {
+            std::cerr << "Error: Cannot open file " << qfile << std::endl;
+            return 1;
+        }
+        if (qdim != dim) { std::cerr << "Error: query dimension " << qdim << " != base dimension " << dim << std::endl; return 1; }
+        std::cout << "Loaded " << nq << " queries" << std::endl;
+        std::vector<float> Dq((size_t)nq * k);
+        std::vector<int64_t> Iq((size_t)nq * k);
+        const double tq = now_s();
+        if (lira_knn(data.data(), n, queries.data(), nq, dim, k, LIRA_METRIC_L2, 0, Dq.data(), Iq.data()) != 0) {
+            std::cerr << "Error: " << lira_last_error() << std::endl;
+            return 1;
+        }
+        const double search_time = now_s() - tq;
+        std::cout << "Search time: " << search_time << "s" << std::endl;
+        const std::string out = dir + "/" + dataset + "_groundtruth.ivecs";
+        std::ofstream f(out, std::ios::binary);
+        if (!f) { std::cerr << "Error: Cannot write " << out << std::endl; return 1; }
+        std::vector<int32_t> row(k + 1);
+        row[0] = k;
+        for (int64_t i = 0; i < nq; ++i) {
+            for (int j = 0; j < k; ++j) row[j + 1] = (int32_t)Iq[(size_t)i * k + j];
+            f.write(reinterpret_cast<const char*>(row.data()), (std::streamsize)(row.size() * sizeof(int32_t)));
+        }
+        std::cout << std::endl << "=== Summary ===" << std::endl;
+        std::cout << "Total time: " << (read_time + search_time) << "s" << std::endl;
+        std::cout << "Output file: " << out << std::endl;
+        return 0;
+    }
 
     // k + 1 neighbours of every base vector, column 0 (the vector itself) dropped: compute_knn.cpp:237, 254-259
     std::vector<float> D((size_t)n * (k + 1));

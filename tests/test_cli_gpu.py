@@ -43,6 +43,24 @@ def test_compute_knn_writes_the_reference_cache_files(tmp_path):
     assert r.returncode == 1 and "Cannot find base file" in r.stderr
 
 
+def test_compute_knn_query_ground_truth_mode(tmp_path):
+    """compute_knn <ds> <path> <k> --queries: exact ground truth of the query set as {ds}_groundtruth.ivecs (the layout
+    utils.read_xvecs / search.cpp:read_ivecs read), k = 100 like config 2."""
+    import lira_ann_search_b200 as L
+    exe = _need("compute_knn")
+    x_d, x_q = synth(20000, 32, 300, seed=9, integer=True)
+    ds = tmp_path / "toy"
+    ds.mkdir()
+    L.write_xvecs(str(ds / "toy_base.fvecs"), x_d)
+    L.write_xvecs(str(ds / "toy_query.fvecs"), x_q)
+    r = subprocess.run([exe, "toy", str(tmp_path), "100", "--queries"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    gt = L.read_xvecs(str(ds / "toy_groundtruth.ivecs"), dtype="int32")
+    assert gt.shape == (300, 100)
+    D_ref, I_ref = O.knn(x_d, x_q, 100, O.L2, O.F64)
+    assert np.array_equal(gt, I_ref)   # integer data: distances exact, ties by id
+
+
 @pytest.mark.parametrize("case", ["toy_l2", "toy_ip"])
 def test_search_matches_reference_search_cpp_stdout(golden, tmp_path, case):
     """bin/search on artifacts in index.py's layout against the stdout of the UNMODIFIED reference search.cpp
