@@ -66,14 +66,15 @@ x_q = gen(Q, 50)
 samp = x_d[torch.randperm(N, device=dev, generator=g)[:262_144]]
 cent = samp[:B].clone()
 for _ in range(8):
-    a = torch.cdist(samp, cent).argmin(1)
+    a = torch.cat([torch.cdist(samp[i:i + 32768], cent).argmin(1) for i in range(0, len(samp), 32768)])
     s = torch.zeros_like(cent).index_add_(0, a, samp)
     n = torch.bincount(a, minlength=B).clamp(min=1).unsqueeze(1)
     cent = s / n
 # two nearest partitions per vector
 b2 = torch.empty((N, 2), dtype=torch.int64, device=dev)
-for s in range(0, N, CH):
-    b2[s:s + CH] = torch.cdist(x_d[s:s + CH], cent).topk(2, dim=1, largest=False).indices
+ACH = max(16384, (1 << 28) // B)   # rows per assignment step: the [rows, B] distance matrix stays near 1 GiB
+for s in range(0, N, ACH):
+    b2[s:s + ACH] = torch.cdist(x_d[s:s + ACH], cent).topk(2, dim=1, largest=False).indices
 ids = torch.arange(N, device=dev).repeat_interleave(2)
 key = b2.reshape(-1) * N + ids
 order = torch.argsort(key)
