@@ -759,7 +759,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         sp.n_items = sw.n_items.as<int>();
         sp.work_counter = sw.n_items.as<int>() + 1;
         sp.nk = nk;
-        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_TC;   // 0: whole lists
+        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : (ps.kind == 2 ? 8192 : TC_SEED_ROWS_TC);   // 0: whole lists
         sp.exp = 0;
         sp.margin_c = margin_c;
         sp.margin_abs = margin_abs;
@@ -1607,7 +1607,9 @@ int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d,
     LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per call");
     if (int rc = check_device(device)) return rc;
     const int ds = round_up(d, 4);
-    const long long seg = 8192;
+    // base segments play the role of lists. k <= 16 on a large base: long segments (the in-kernel compaction keeps their
+    // candidate regions small), i.e. 8x fewer (query, segment) pairs, regions and refine work, and larger query batches
+    const long long seg = (k <= 16 && N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
     const int nseg = (int)((N + seg - 1) / seg);
     std::vector<int64_t> off(nseg + 1);
     for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
