@@ -40,6 +40,7 @@ extern "C" {
 
 typedef struct lira_index lira_index_t; /* inverted lists resident in HBM       */
 typedef struct lira_model lira_model_t; /* probing model + centroids + scaler   */
+typedef struct lira_knn_index lira_knn_t;    /* base vectors resident for exact kNN  */
 
 /* ---- library -------------------------------------------------------------------------- */
 const char* lira_last_error(void);
@@ -82,7 +83,11 @@ int lira_scan_all_pairs(lira_index_t* h, const float* q, int64_t Q, int k, int64
  * probe_offsets[Q+1] / probe_ids[P]: CSR of the probed lists per query.
  * dedup = 1: an id stored in several probed lists counts once before selection (Python recall
  *            semantics, LIRA_smallscale.py:210-214); dedup = 0: search.cpp:499-513 as shipped.
- * D[Q,k] metric value, I[Q,k] global ids (-1 padded), cmp[Q] (may be NULL) = sum of probed sizes. */
+ * D[Q,k] metric value, I[Q,k] global ids (-1 padded), cmp[Q] (may be NULL) = sum of probed sizes.
+ * A probed list id outside [0, B) is an error in lira_search (checked on the host). lira_search_dev cannot look at
+ * device memory before the launch: it skips such ids (they count neither in cmp nor in the results) and reports
+ * "probed list id out of range" from batches of >= 256 queries on the tensor-core scan, whose completion it waits for.
+ * Device inputs: the row stride may exceed d only if the padding columns d..ld-1 are zero (vectors and queries). */
 int lira_search(lira_index_t* h, const float* q, int64_t Q, const int64_t* probe_offsets,
                 const int32_t* probe_ids, int k, int dedup, float* D, int64_t* I, int64_t* cmp);
 int lira_search_dev(lira_index_t* h, const float* d_q, int64_t ldq, int64_t Q,
@@ -130,6 +135,16 @@ int lira_select_search_dev(lira_index_t* h, const float* d_scores, int64_t lds, 
  * base id. The caller drops column 0 for self-kNN as the reference does (compute_knn.cpp:254-259). */
 int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d, int k, int metric,
              int device, float* D, int64_t* I);
+/* The same with the base resident behind a handle (faiss: index.add(x) once, index.search(batch, k + 1) per batch of
+ * 10 000 rows -- compute_knn.cpp:208-244, utils.py:293-310, LIRA_largescale.py:225-229): the upload, the row norms and the
+ * fp16 shadow copy are made once at create, every search only moves its query batch. */
+int lira_knn_create(const float* base, int64_t N, int d, int metric, int device, lira_knn_t** out);
+int lira_knn_search(lira_knn_t* h, const float* query, int64_t Q, int k, float* D, int64_t* I);
+int lira_knn_free(lira_knn_t* h);
+int64_t lira_knn_ntotal(const lira_knn_t* h);
+int lira_knn_set_use_tensor_cores(lira_knn_t* h, int enable);
+int lira_knn_last_path(const lira_knn_t* h); /* last search: 0 CUDA cores, 1 tensor cores, 2 some batches on each */
+int lira_knn_last_redo(const lira_knn_t* h); /* queries of the last search answered again by the exact CUDA-core scan */
 
 /* ---- multi-GPU merge (e): per-rank top-k lists -> global top-k with id de-duplication ----
  * d_keys_in[R, Q, k]: rank-major gathered (score,id) lists as produced by lira_*_topk_keys_dev /
@@ -148,7 +163,7 @@ int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_m
 int lira_index_set_timing(lira_index_t* h, int enable);
 /* The online search (lira_search*, lira_probe_search*, lira_select_search*) has two implementations of the list
  * scan with the same results: fp32 CUDA cores (always valid) and tcgen05 tensor cores, taken for batches of
- * >= 256 queries and d <= 256 in one of two modes decided when the index is created:
+ * >= 256 queries and d <= 1024 (256 < d: both operands stream) in one of two modes decided when the index is created:
  *   mode 1 (exact): every stored value and every query value is an integer of at most 11 bits and |x|^2 < 2^22;
  *           the kernel streams an fp16 copy of the rows, products and fp32 sums are exact, both paths return
  *           identical bits;

@@ -6,7 +6,7 @@ the repository root). No CPU fallback: compute calls raise when the library or a
 """
 from . import _cabi
 from ._cabi import (METRIC_IP, METRIC_L2, SELECT_GE_ARGMAX, SELECT_GT, SELECT_TOPN, LiraError)
-from .engine import LiraIndex, LiraModel, ListView, centroid_features, knn, launch_count
+from .engine import KnnIndex, LiraIndex, LiraModel, ListView, centroid_features, knn, launch_count
 from .model_probing import MLP_2_Input, model_evaluate, model_infer, model_train
 from .query import (cpp_thresholds, get_cmp_recall, query_tuning, query_tuning_large, recall_at_k,
                     search_sweep)

@@ -49,6 +49,13 @@ SIGNATURES = {
     "lira_probe_search_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, ctypes.c_double, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lira_select_search_dev": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, ctypes.c_double, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lira_knn": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_int, c_int, c_int, c_int, c_f32p, c_i64p]),
+    "lira_knn_create": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "lira_knn_search": (c_int, [c_vp, c_f32p, c_i64, c_int, c_f32p, c_i64p]),
+    "lira_knn_free": (c_int, [c_vp]),
+    "lira_knn_ntotal": (c_i64, [c_vp]),
+    "lira_knn_set_use_tensor_cores": (c_int, [c_vp, c_int]),
+    "lira_knn_last_path": (c_int, [c_vp]),
+    "lira_knn_last_redo": (c_int, [c_vp]),
     "lira_pack_keys_dev": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
     "lira_merge_ranks_dev": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "lira_launch_count": (c_i64, []),

@@ -203,6 +203,7 @@ struct lira_model {
     int out_dim[6], in_dim[6], in_ld[6];
     CUtensorMap tm_cent, tm_w[6];
     cudaStream_t stream = nullptr;
+    int num_sms = 148;
     DevBuf feats, h1, cat, h2, h5, scores, q;
     // tensor-core front end (tc_dense_kernels.cuh): error-free hi / lo splits of the static operands ...
     bool use_tc = true;
@@ -333,12 +334,7 @@ static int model_forward_tc(lira_model* m, const float* d_q, long long ldq, long
         if (int rc = b->ensure(Qs * Bp * 4)) return rc;
     for (DevBuf* b : {&m->h1h, &m->h1l, &m->cath, &m->catl, &m->h2h, &m->h2l, &m->h5h, &m->h5l})
         if (int rc = b->ensure(Qs * 128 * 4)) return rc;
-    static int num_sms = 0;
-    if (!num_sms) {
-        cudaDeviceProp prop;
-        LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, m->device));
-        num_sms = prop.multiProcessorCount;
-    }
+    const int num_sms = m->num_sms;
     const int warps = 8;
     const int sgrid = (int)((Q + warps - 1) / warps);
     // queries: centred split (+ |q'|^2) for the distance features, raw split for vector_net
@@ -388,6 +384,7 @@ struct ProbeSpec {
     const long long* d_probe_offsets = nullptr;
     const int* d_probe_ids = nullptr;
     long long P = 0;
+    int* d_bad_flag = nullptr;   // kind 1: set to 1 when a probed list id is outside [0, B) (default: a scratch word nobody reads)
 };
 
 __global__ void csr_hist_kernel(const long long* probe_offsets, const int* probe_ids, const long long* list_offsets,
@@ -397,18 +394,23 @@ __global__ void csr_hist_kernel(const long long* probe_offsets, const int* probe
     if (q >= Q) return;
     if (mask && !mask[q]) return;
     long long c = 0;
+    int nv = 0;
     const long long lo = probe_offsets[q], hi = probe_offsets[q + 1];
     for (long long j = lo + lane; j < hi; j += 32) {
         const int b = probe_ids[j];
-        if (b < 0 || b >= B) { *bad = 1; continue; }
+        if (b < 0 || b >= B) { *bad = 1; continue; }   // ignored (and reported where the caller synchronises)
         atomicAdd(list_count + b, 1);
         c += list_offsets[b + 1] - list_offsets[b];
+        ++nv;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    }
     if (lane == 0) {
         if (cmp) cmp[q] = c;
-        nsel[q] = (int)(hi - lo);
+        nsel[q] = nv;
     }
 }
 
@@ -429,6 +431,10 @@ __global__ void scatter_csr_kernel(const long long* probe_offsets, const int* pr
 
 __global__ void uniform_groups_kernel(long long* group_offsets, int B, long long Q) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= B; i += gridDim.x * blockDim.x) group_offsets[i] = i * Q;
+}
+
+__global__ void iota_i32_kernel(int* out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (int)i;
 }
 
 __global__ void copy_nprobe_kernel(const int* nsel, int* out, int Q) {
@@ -518,7 +524,7 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
         }
     } else if (ps.kind == 1) {
         P = ps.P;
-        int* bad = ws.n_items.as<int>() + 8;
+        int* bad = ps.d_bad_flag ? ps.d_bad_flag : ws.n_items.as<int>() + 8;
         csr_hist_kernel<<<qgrid, warps * 32, 0, st>>>(ps.d_probe_offsets, ps.d_probe_ids, h->d_offsets, (int)Q, B,
                                                       ws.list_count.as<int>(), d_cmp, ws.nsel.as<int>(), bad, d_mask);
         LIRA_LAUNCH_CHECK();
@@ -640,8 +646,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (int rc = ws.flags.ensure(64)) return rc;
     if (int rc = ws.redo.ensure((size_t)Q * 4)) return rc;
     // [0] query batch exactly representable, [1] number of overflowed queries, [2] a query's probe set was truncated
-    static const int one_zero[3] = {1, 0, 0};
-    LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 12, cudaMemcpyHostToDevice, st));
+    // [3] an explicit probe set named a list outside [0, B)
+    static const int one_zero[4] = {1, 0, 0, 0};
+    LIRA_CUDA_OK(cudaMemcpyAsync(ws.flags.p, one_zero, 16, cudaMemcpyHostToDevice, st));
     const bool optimistic = ps.kind == 0 && !h->tc_force_sync;   // no host round trip before the scan (checked at the end)
     h->tc_force_sync = false;
     // |q|^2; exact mode: flags[0] is cleared unless the batch is exact in fp16 (approximate mode: the gather below clears it
@@ -651,7 +658,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     long long P = 0;
     const long long* po = nullptr;
     int q_exact = 1;
-    if (int rc = prepare_groups(h, ws, Q, ps, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st,
+    ProbeSpec psf = ps;
+    psf.d_bad_flag = ws.flags.as<int>() + 3;
+    if (int rc = prepare_groups(h, ws, Q, psf, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st,
                                 optimistic ? ws.flags.as<int>() + 2 : nullptr)) return rc;
     if (!q_exact || P == 0) return 0;  // not exact in fp16 (or nothing probed): exact CUDA-core path
     if (int rc = save_stats(h, ws, st)) return rc;
@@ -842,9 +851,10 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     LIRA_LAUNCH_CHECK();
-    int fl[3] = {1, 0, 0};
-    LIRA_CUDA_OK(cudaMemcpyAsync(fl, ws.flags.p, 12, cudaMemcpyDeviceToHost, st));
+    int fl[4] = {1, 0, 0, 0};
+    LIRA_CUDA_OK(cudaMemcpyAsync(fl, ws.flags.p, 16, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    LIRA_REQUIRE(fl[3] == 0, "probed list id out of range");
     *n_redo = fl[1];
     if ((optimistic && (fl[0] == 0 || fl[2] != 0)) || (approx && fl[0] == 0)) {
         // the optimistic run is void: the batch is not exact in fp16 (-> the caller's CUDA-core path), or a probe set was
@@ -911,6 +921,7 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
     long long P = 0;
     h->last_Q = Q;
     h->last_k = k;
+    h->last_redo = 0;
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
     bool done = false;
     int n_redo = 0;
@@ -1312,7 +1323,8 @@ int lira_scan_all_pairs(lira_index_t* h, const float* q, int64_t Q, int k, int64
     Workspace& ws = h->ws;
     const int B = h->B;
     // bound the partial-result workspace: process the queries in batches
-    const long long max_pairs = 64ll << 20;  // 64 Mi (query, list) pairs per batch
+    // at most 64 Mi (query, list) pairs per batch, and at most ~6 GB for the two P * k * 8-byte workspaces (partial keys + found ids)
+    const long long max_pairs = std::min<long long>(64ll << 20, (6ll << 30) / (16ll * k));
     long long qb = std::max<long long>(1, std::min<long long>(Q, max_pairs / std::max(B, 1)));
     for (long long q0 = 0; q0 < Q; q0 += qb) {
         const long long nq = std::min<long long>(qb, Q - q0);
@@ -1382,6 +1394,10 @@ int lira_model_create(const float* centroids, const float* scaler_mean, const fl
     if (int rc = check_device(device)) return rc;
     lira_model* m = new lira_model();
     m->device = device; m->B = B; m->Bp = round_up(B, 4); m->d = d; m->ds = round_up(d, 4);
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
+    }
     const int od[6] = {128, 64, 128, 64, 128, B};
     const int id[6] = {B, 128, d, 128, 128, 128};
     int rc = 0;
@@ -1599,59 +1615,142 @@ int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t 
     return finish_timing(h);
 }
 
-// ---- exact kNN (SIMT path): the base is cut into segments that play the role of lists --------
+// ---- exact kNN: the base is resident behind a handle, cut into segments that play the role of lists --------
+}  // extern "C"
+
+struct lira_knn_index {
+    int device = 0, d = 0, ds = 0, metric = 0;
+    long long N = 0, seg = 0;
+    int last_path = 0;           // 0 = CUDA cores, 1 = tensor cores, 2 = mixed (some batches of the last search on each)
+    DevBuf dbase, dids;
+    lira_index_t* index = nullptr;
+};
+
+namespace lira {
+// (re)cut the base into segments of `seg` rows: only the offsets change, the fp16 shadow copy and the norms are per row
+static int knn_set_segments(lira_knn_index* kn, long long seg) {
+    if (kn->seg == seg) return 0;
+    lira_index* h = kn->index;
+    const int nseg = (int)((kn->N + seg - 1) / seg);
+    std::vector<long long> off(nseg + 1);
+    for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, kn->N);
+    std::vector<int> order(nseg);
+    std::iota(order.begin(), order.end(), 0);   // equal sizes (the last one may be shorter): already size-descending
+    LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (h->d_offsets) LIRA_CUDA_OK(cudaFree(h->d_offsets));
+    if (h->d_list_order) LIRA_CUDA_OK(cudaFree(h->d_list_order));
+    h->d_offsets = nullptr;
+    h->d_list_order = nullptr;
+    LIRA_CUDA_OK(cudaMalloc(&h->d_offsets, (size_t)(nseg + 1) * 8));
+    LIRA_CUDA_OK(cudaMalloc(&h->d_list_order, (size_t)nseg * 4));
+    LIRA_CUDA_OK(cudaMemcpy(h->d_offsets, off.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice));
+    LIRA_CUDA_OK(cudaMemcpy(h->d_list_order, order.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice));
+    h->h_offsets = off;
+    h->B = nseg;
+    kn->seg = seg;
+    return 0;
+}
+}  // namespace lira
+
+extern "C" {
+
+int lira_knn_create(const float* base, int64_t N, int d, int metric, int device, lira_knn_t** out) {
+    LIRA_REQUIRE(out && base && N >= 1 && d >= 1, "bad argument");
+    LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per handle");
+    LIRA_REQUIRE(metric == LIRA_METRIC_L2 || metric == LIRA_METRIC_IP, "metric must be LIRA_METRIC_L2 or LIRA_METRIC_IP");
+    if (int rc = check_device(device)) return rc;
+    lira_knn_index* kn = new lira_knn_index();
+    kn->device = device; kn->d = d; kn->ds = round_up(d, 4); kn->metric = metric; kn->N = N;
+    auto body = [&]() -> int {
+        cudaStream_t st0 = nullptr;
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+        int r = upload_rows(kn->dbase, base, N, d, kn->ds, st0);
+        if (!r) r = kn->dids.ensure((size_t)N * 4);
+        if (!r) {
+            iota_i32_kernel<<<grid_for(N, 256), 256, 0, st0>>>(kn->dids.as<int>(), N);
+            g_launches.fetch_add(1);
+        }
+        cudaError_t e = cudaStreamSynchronize(st0);
+        cudaStreamDestroy(st0);
+        if (r) return r;
+        LIRA_CUDA_OK(e);
+        const long long seg = 8192;
+        const int nseg = (int)((N + seg - 1) / seg);
+        std::vector<int64_t> off(nseg + 1);
+        for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
+        if (int r2 = lira_index_create_dev(kn->dbase.as<float>(), kn->ds, d, off.data(), kn->dids.as<int>(), nseg, metric, device, &kn->index)) return r2;
+        kn->seg = seg;
+        return 0;
+    };
+    const int rc = body();
+    if (rc) { lira_knn_free(kn); return rc; }
+    *out = kn;
+    return 0;
+}
+
+int lira_knn_free(lira_knn_t* kn) {
+    if (!kn) return 0;
+    cudaSetDevice(kn->device);
+    if (kn->index) lira_index_free(kn->index);
+    kn->dbase.release();
+    kn->dids.release();
+    delete kn;
+    return 0;
+}
+
+int64_t lira_knn_ntotal(const lira_knn_t* kn) { return kn ? kn->N : -1; }
+int lira_knn_last_path(const lira_knn_t* kn) { return kn ? kn->last_path : -1; }
+int lira_knn_last_redo(const lira_knn_t* kn) { return (kn && kn->index) ? kn->index->last_redo : -1; }
+int lira_knn_set_use_tensor_cores(lira_knn_t* kn, int enable) {
+    LIRA_REQUIRE(kn && kn->index, "null handle");
+    kn->index->use_tc = enable != 0;
+    return 0;
+}
+
+int lira_knn_search(lira_knn_t* kn, const float* query, int64_t Q, int k, float* D, int64_t* I) {
+    LIRA_REQUIRE(kn && kn->index && query && D && I && Q >= 0, "bad argument");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_CUDA_OK(cudaSetDevice(kn->device));
+    lira_index* h = kn->index;
+    const int d = kn->d, ds = kn->ds;
+    // k <= 16 on a large base: long segments (the in-kernel compaction keeps their candidate regions small), i.e. 8x fewer
+    // (query, segment) pairs, regions and refine work, and larger query batches
+    const long long seg = (k <= 16 && kn->N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
+    if (int rc = knn_set_segments(kn, seg)) return rc;
+    const int nseg = h->B;
+    cudaStream_t st = h->stream;
+    Workspace& ws = h->ws;
+    int redo_total = 0, n_tc = 0, n_batches = 0;
+    const long long max_pairs = 4ll << 20;   // (query, segment) pairs per batch: bounds the per-pair workspaces (1 KiB each on the tensor-core path)
+    const long long qb = std::max<long long>(1, std::min<long long>(std::max<int64_t>(Q, 1), max_pairs / nseg));
+    for (long long q0 = 0; q0 < Q; q0 += qb) {
+        const long long nq = std::min<long long>(qb, Q - q0);
+        if (int r3 = upload_rows(ws.q, query + q0 * d, nq, d, ds, st)) return r3;
+        ProbeSpec ps;
+        ps.kind = 2;
+        if (int r3 = ws.D.ensure((size_t)nq * k * 4)) return r3;
+        if (int r3 = ws.I.ensure((size_t)nq * k * 8)) return r3;
+        if (int r3 = search_core(h, ws.q.as<float>(), ds, nq, ps, k, 1, ws.D.as<float>(), ws.I.as<long long>(), nullptr, nullptr, st)) return r3;
+        redo_total += h->last_redo;
+        n_tc += h->last_path == 1;
+        ++n_batches;
+        LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)q0 * k, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)q0 * k, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    h->last_redo = redo_total;
+    kn->last_path = n_tc == 0 ? 0 : (n_tc == n_batches ? 1 : 2);
+    return 0;
+}
+
 int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d, int k, int metric, int device,
              float* D, int64_t* I) {
     LIRA_REQUIRE(base && query && D && I && N >= 1 && Q >= 0 && d >= 1, "bad argument");
     LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
-    LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per call");
-    if (int rc = check_device(device)) return rc;
-    const int ds = round_up(d, 4);
-    // base segments play the role of lists. k <= 16 on a large base: long segments (the in-kernel compaction keeps their
-    // candidate regions small), i.e. 8x fewer (query, segment) pairs, regions and refine work, and larger query batches
-    const long long seg = (k <= 16 && N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
-    const int nseg = (int)((N + seg - 1) / seg);
-    std::vector<int64_t> off(nseg + 1);
-    for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
-    DevBuf dbase, dids;
-    lira_index_t* h = nullptr;
-    int rc = 0;
-    auto body = [&]() -> int {
-        cudaStream_t st0 = nullptr;
-        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
-        int r = upload_rows(dbase, base, N, d, ds, st0);
-        if (!r) r = dids.ensure((size_t)N * 4);
-        if (!r) {
-            std::vector<int32_t> ids(N);
-            std::iota(ids.begin(), ids.end(), 0);
-            cudaMemcpyAsync(dids.p, ids.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st0);
-            cudaStreamSynchronize(st0);
-        }
-        cudaStreamDestroy(st0);
-        if (r) return r;
-        if (int r2 = lira_index_create_dev(dbase.as<float>(), ds, d, off.data(), dids.as<int>(), nseg, metric, device, &h)) return r2;
-        cudaStream_t st = h->stream;
-        Workspace& ws = h->ws;
-        const long long max_pairs = 4ll << 20;   // (query, segment) pairs per batch: bounds the per-pair workspaces (1 KiB each on the tensor-core path)
-        const long long qb = std::max<long long>(1, std::min<long long>(std::max<int64_t>(Q, 1), max_pairs / nseg));
-        for (long long q0 = 0; q0 < Q; q0 += qb) {
-            const long long nq = std::min<long long>(qb, Q - q0);
-            if (int r3 = upload_rows(ws.q, query + q0 * d, nq, d, ds, st)) return r3;
-            ProbeSpec ps;
-            ps.kind = 2;
-            if (int r3 = ws.D.ensure((size_t)nq * k * 4)) return r3;
-            if (int r3 = ws.I.ensure((size_t)nq * k * 8)) return r3;
-            if (int r3 = search_core(h, ws.q.as<float>(), ds, nq, ps, k, 1, ws.D.as<float>(), ws.I.as<long long>(), nullptr, nullptr, st)) return r3;
-            LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)q0 * k, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-            LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)q0 * k, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-            LIRA_CUDA_OK(cudaStreamSynchronize(st));
-        }
-        return 0;
-    };
-    rc = body();
-    if (h) lira_index_free(h);
-    dbase.release();
-    dids.release();
+    lira_knn_t* kn = nullptr;
+    if (int rc = lira_knn_create(base, N, d, metric, device, &kn)) return rc;
+    const int rc = lira_knn_search(kn, query, Q, k, D, I);
+    lira_knn_free(kn);
     return rc;
 }
 
@@ -1663,19 +1762,6 @@ __global__ void pack_keys_kernel(const float* D, const long long* I, long long n
         keys[i] = id < 0 ? KEY_INF : make_key(is_ip ? -D[i] : D[i], (uint32_t)id);
     }
 }
-__global__ void rank_slots_kernel(long long* probe_offsets, int* probe_slot, long long Q, int R) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= Q * R; i += (long long)gridDim.x * blockDim.x) {
-        if (i <= Q) probe_offsets[i] = i * R;
-        if (i < Q * R) {
-            const long long q = i / R, r = i % R;
-            probe_slot[i] = (int)(r * Q + q);
-        }
-    }
-}
-struct RankMergeWs {
-    DevBuf po, ps;
-};
-static RankMergeWs g_rm[16];
 }  // namespace
 
 int lira_pack_keys_dev(const float* d_D, const int64_t* d_I, int64_t n, int metric, uint64_t* d_keys, int device,
@@ -1692,19 +1778,12 @@ int lira_pack_keys_dev(const float* d_D, const int64_t* d_I, int64_t n, int metr
 int lira_merge_ranks_dev(const uint64_t* d_keys_in, int R, int64_t Q, int k, int metric, int dedup, float* d_D,
                          int64_t* d_I, int device, void* stream) {
     LIRA_REQUIRE(d_keys_in && d_D && d_I && R >= 1 && Q >= 0 && k >= 1 && k <= 128, "bad argument");
-    LIRA_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
     LIRA_REQUIRE(Q * (long long)R < (1ll << 31), "Q * R too large");
     if (int rc = check_device(device)) return rc;
     if (Q == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    RankMergeWs& w = g_rm[device];
-    if (int rc = w.po.ensure((size_t)(Q + 1) * 8)) return rc;
-    if (int rc = w.ps.ensure((size_t)Q * R * 4)) return rc;
-    rank_slots_kernel<<<grid_for(Q * R + 1, 256), 256, 0, st>>>(w.po.as<long long>(), w.ps.as<int>(), Q, R);
-    LIRA_LAUNCH_CHECK();
-    MergeParams mp{(const unsigned long long*)d_keys_in, w.po.as<long long>(), w.ps.as<int>(), k, (int)Q, dedup, d_D,
-                   (long long*)d_I, metric == LIRA_METRIC_IP, nullptr};
-    return launch_merge(mp, st);
+    MergeParams mp{(const unsigned long long*)d_keys_in, nullptr, nullptr, k, (int)Q, dedup, d_D, (long long*)d_I,
+                   metric == LIRA_METRIC_IP, nullptr, R};
+    return launch_merge(mp, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -107,7 +107,9 @@ struct SelectParams {
     long lds;
     int Q, B;
     int mode;
-    double value;         // threshold (compared in fp64 like numpy's f32-vs-f64 compare) or nprobe
+    double value;         // threshold or nprobe. Thresholds are compared in fp32, i.e. score > float(value): search.cpp's
+                          // threshold is a float (search.cpp:413), and torch / numpy compare an fp32 array with a Python float in
+                          // fp32 as well (LIRA_smallscale.py:206: float32(0.1) > 0.1 is False)
     const long long* list_offsets;  // [B+1] for the Computations column
     int* sel;             // [Q, B] selected partitions of each query, in output order
     int* nsel;            // [Q]
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
     } else {
         float best = -INFINITY;
         int best_b = 0;
+        const float thr = (float)p.value;
         unsigned long long h1 = KEY_INF, h2 = KEY_INF;  // this lane's two best selected partitions
         for (int base = 0; base < p.B; base += 1024) {
             // 32 independent coalesced loads in flight per lane (the loop below is compute only)
@@ -211,8 +214,8 @@ __global__ void __launch_bounds__(256) select_kernel(const SelectParams p) {
                 bool hit = false;
                 const float v = vv[i];
                 if (b < p.B) {
-                    if (p.mode == SEL_GT) hit = (double)v > p.value;
-                    else if (p.mode == SEL_GE_ARGMAX) hit = (double)v >= p.value;
+                    if (p.mode == SEL_GT) hit = v > thr;
+                    else if (p.mode == SEL_GE_ARGMAX) hit = v >= thr;
                     else hit = true;
                     if (v > best) { best = v; best_b = b; }  // first maximum per lane (b ascending)
                 }

@@ -266,6 +266,8 @@ struct MergeParams {
     long long* out_ids;                  // [Q, k]
     int is_ip;
     const int* mask;                     // optional [Q]: only queries with mask[q] != 0 are written
+    int R = 0;                           // > 0: cross-GPU merge, part_key is [R, Q, k] rank-major and probe_offsets /
+                                         //      probe_slot are unused (slot of rank r = r * Q + q)
 };
 
 template <int S>
@@ -279,8 +281,9 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
 #pragma unroll
     for (int s = 0; s < S; ++s) key[s] = KEY_INF;
     unsigned long long kth = KEY_INF;
-    for (long long j = p.probe_offsets[q]; j < p.probe_offsets[q + 1]; ++j) {
-        const int slot = p.probe_slot[j];
+    const long long j_lo = p.R > 0 ? 0 : p.probe_offsets[q], j_hi = p.R > 0 ? p.R : p.probe_offsets[q + 1];
+    for (long long j = j_lo; j < j_hi; ++j) {
+        const long long slot = p.R > 0 ? j * p.Q + q : p.probe_slot[j];
         if (slot < 0) continue;  // invalid probe
         const unsigned long long* src = p.part_key + (size_t)slot * k;
         for (int e0 = 0; e0 < k; e0 += 32) {

@@ -330,6 +330,49 @@ def centroid_features(q, centroids, mean=None, scale=None, device=0):
     return out
 
 
+class KnnIndex:
+    """Base vectors resident on the device for exact kNN: faiss.IndexFlat{L2,IP}(d) + .add(x) + .search(q, k) as
+    compute_knn.cpp:208-244 / utils.py:293-310 / LIRA_largescale.py:225-229 use it (global ids, best first)."""
+
+    def __init__(self, base, metric="L2", device=0):
+        C.require_gpu()
+        base = C.f32(base)
+        self.ntotal, self.dim, self.device = base.shape[0], base.shape[1], device
+        self._h = ctypes.c_void_p()
+        C.check(C.lib().lira_knn_create(C.ptr(base, C.c_f32p), base.shape[0], base.shape[1], _metric_code(metric), device,
+                                        ctypes.byref(self._h)))
+
+    def search(self, query, k):
+        query = C.f32(query).reshape(-1, self.dim)
+        D = np.empty((query.shape[0], k), np.float32)
+        I = np.empty((query.shape[0], k), np.int64)
+        C.check(C.lib().lira_knn_search(self._h, C.ptr(query, C.c_f32p), query.shape[0], int(k), C.ptr(D, C.c_f32p),
+                                        C.ptr(I, C.c_i64p)))
+        return D, I
+
+    def set_use_tensor_cores(self, enable=True):
+        C.check(C.lib().lira_knn_set_use_tensor_cores(self._h, int(bool(enable))))
+
+    @property
+    def last_path(self) -> str:
+        return {0: "cuda-core", 1: "tensor-core", 2: "mixed"}.get(int(C.lib().lira_knn_last_path(self._h)), "?")
+
+    @property
+    def last_redo(self) -> int:
+        return int(C.lib().lira_knn_last_redo(self._h))
+
+    def close(self):
+        if self._h is not None:
+            C.lib().lira_knn_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def knn(base, query, k, metric="L2", device=0):
     """Exact kNN (compute_knn.cpp:208-259 / utils.py:293-310). Returns (D[Q,k], I[Q,k] int64)."""
     C.require_gpu()

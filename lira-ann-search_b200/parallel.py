@@ -51,10 +51,10 @@ def stripe_csr(list_offsets, list_ids, rank, world):
     off = np.asarray(list_offsets, np.int64)
     ids = np.asarray(list_ids)
     B = len(off) - 1
-    pos = np.arange(off[-1]) - np.repeat(off[:-1], np.diff(off))
+    lst = np.repeat(np.arange(B), np.diff(off))      # list of every entry (empty lists, also trailing ones, simply do not occur)
+    pos = np.arange(off[-1]) - off[:-1][lst]
     keep = pos % world == rank
-    sizes = np.add.reduceat(keep.astype(np.int64), off[:-1]) if off[-1] > 0 else np.zeros(B, np.int64)
-    sizes[np.diff(off) == 0] = 0
+    sizes = np.bincount(lst[keep], minlength=B).astype(np.int64)
     new_off = np.zeros(B + 1, np.int64)
     np.cumsum(sizes, out=new_off[1:])
     return new_off, ids[keep]

@@ -62,7 +62,8 @@ def _tuning_rows(all_outputs, knn_distr_id, found_aknn_id, search_time, cmp_dist
     qq = np.arange(all_outputs.shape[0])[:, None, None]
     rows = []
     for thr in thresholds:
-        probed = all_outputs > thr  # LIRA_smallscale.py:206
+        # LIRA_smallscale.py:206: all_outputs is a torch fp32 tensor there, so the comparison runs in fp32
+        probed = all_outputs > np.float32(thr)
         nprobe = probed.sum(1)
         cmp_ = (np.asarray(cmp_distr_all) * probed).sum(1)
         hit = (in_found & probed[qq, safe]).any(-1)  # [Q, k]: id found in >= 1 probed bucket

@@ -137,9 +137,11 @@ def compute_data_knn(x_data, cfg, data_path="/data/vector_datasets", device=0):
     knn = np.zeros((n, cfg.k), np.int32)
     batch = min(10000, n)  # utils.py:301
     metric = "inner_product" if cfg.dis_metric == "inner_product" else "L2"
-    for a in range(0, n, batch * 10):
-        _, ids = engine.knn(x_data, x_data[a:a + batch * 10], cfg.k + 1, metric, device)
-        knn[a:a + batch * 10] = ids[:, 1:cfg.k + 1]
+    index = engine.KnnIndex(x_data, metric, device)   # index.add(x_data): uploaded once (utils.py:294-298)
+    for a in range(0, n, batch):
+        _, ids = index.search(x_data[a:a + batch], cfg.k + 1)
+        knn[a:a + batch] = ids[:, 1:cfg.k + 1]
+    index.close()
     print(f"KNN computation completed in {time.time() - t0:.2f}s")
     np.save(npy, knn)
     return knn

@@ -8,7 +8,7 @@
  *
  * Pinning status: the reference ships no golden vectors or unit tests.
  *   - The C++ twin of the query phase (search.cpp) IS compiled unmodified into
- *     oracle/_ref/search_ref and tests/test_oracle_vs_ref.py checks this file against its
+ *     oracle/_ref/search_ref and tests/test_oracle_golden.py checks this file against its
  *     per-threshold recall / nprobe / cmp output, and tests/golden/ holds outputs produced
  *     by importing the reference's own Python (utils.py, LIRA_smallscale.py,
  *     model_probing.py) -- see oracle/make_golden.py.
@@ -215,8 +215,9 @@ ORACLE_API void oracle_mlp_forward(const float* x_dist, const float* x_vec, long
  * mode 1: C++      -- scores[q,b] >= thr, and if none: argmax (first max) (search.cpp:448-466)
  * mode 2: top-n    -- the nprobe = (int)value best scores, ties to the lower partition id
  *                     (utils.py:512 all_outputs[q].topk(probeM)); ids emitted best-first.
- * scores are fp32 (model output). thr is passed as double: Python compares the fp32 score
- * with a float64 np.arange value; for mode 1 pass (double)(float)thr.
+ * scores are fp32 (model output). The threshold is compared in fp32 in both callers: all_outputs is a
+ * torch fp32 tensor, and `tensor > np.float64(thr)` is evaluated in the tensor's dtype (checked against
+ * torch here: torch.tensor([float32(0.1)]) > np.float64(0.1) is False); search.cpp's thr is a float.
  * probe_offsets[Q+1], probe_ids[capacity Q*B] are written; returns total count. */
 ORACLE_API long oracle_select(const float* scores, long Q, long B, int mode, double value,
                               long* probe_offsets, int* probe_ids) {
@@ -227,7 +228,8 @@ ORACLE_API long oracle_select(const float* scores, long Q, long B, int mode, dou
         if (mode == 0 || mode == 1) {
             long before = total;
             for (long b = 0; b < B; ++b) {
-                int hit = (mode == 0) ? ((double)s[b] > value) : ((double)s[b] >= value);
+                const float thr = (float)value;
+                int hit = (mode == 0) ? (s[b] > thr) : (s[b] >= thr);
                 if (hit) probe_ids[total++] = (int)b;
             }
             if (mode == 1 && total == before) {

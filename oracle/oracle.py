@@ -295,7 +295,7 @@ def query_tuning_rows(all_outputs, knn_ids, member, found_aknn_id, cmp_distr_all
     knn_ids = np.asarray(knn_ids)
     rows = []
     for thr in thresholds:
-        probed = all_outputs > thr  # fp32 scores vs fp64 threshold, as np.where(all_outputs[i] > threshold)
+        probed = all_outputs > np.float32(thr)  # torch fp32 tensor vs scalar: compared in fp32 (LIRA_smallscale.py:206)
         nprobe = probed.sum(1)
         cmp_ = (cmp_distr_all * probed).sum(1)
         rec = np.zeros(Q)

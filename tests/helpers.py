@@ -60,3 +60,23 @@ def assert_topk_equiv(D, I, D_ref, I_ref, q, base, metric, rtol=RTOL):
     for qi in np.unique(np.nonzero(diff)[0]):
         row = I[qi][I[qi] >= 0]
         assert len(set(row.tolist())) == len(row), "duplicate id in a result row"
+
+
+def merge_ranks_numpy(D_all, I_all, k, dedup=True):
+    """[R,Q,k] per-rank top-k lists -> [Q,k]: ascending (score, id), an id counted once."""
+    R, Q, _ = D_all.shape
+    D_out = np.full((Q, k), np.inf, np.float32)
+    I_out = np.full((Q, k), -1, np.int64)
+    for q in range(Q):
+        cand = sorted({(float(D_all[r, q, j]), int(I_all[r, q, j])) for r in range(R) for j in range(D_all.shape[2])
+                       if I_all[r, q, j] >= 0})
+        seen, w = set(), 0
+        for dd, ii in cand:
+            if dedup and ii in seen:
+                continue
+            seen.add(ii)
+            D_out[q, w], I_out[q, w] = dd, ii
+            w += 1
+            if w == k:
+                break
+    return D_out, I_out

@@ -15,26 +15,6 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _merge_ranks_numpy(D_all, I_all, k, dedup=True):
-    """[R,Q,k] -> [Q,k]: ascending (score, id), an id counted once."""
-    R, Q, _ = D_all.shape
-    D_out = np.full((Q, k), np.inf, np.float32)
-    I_out = np.full((Q, k), -1, np.int64)
-    for q in range(Q):
-        cand = sorted({(float(D_all[r, q, j]), int(I_all[r, q, j])) for r in range(R) for j in range(D_all.shape[2])
-                       if I_all[r, q, j] >= 0})
-        seen, w = set(), 0
-        for dd, ii in cand:
-            if dedup and ii in seen:
-                continue
-            seen.add(ii)
-            D_out[q, w], I_out[q, w] = dd, ii
-            w += 1
-            if w == k:
-                break
-    return D_out, I_out
-
-
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -43,7 +23,7 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle as O
-    from helpers import synth
+    from helpers import merge_ranks_numpy as _merge_ranks_numpy, synth
     from lira_ann_search_b200.parallel import stripe_assignment
     O.set_num_threads(2)
     x_d, x_q = synth(3000, 16, 40, seed=5, integer=True)
@@ -106,3 +86,11 @@ def test_stripes_partition_every_list():
         for b in range(B):
             merged = np.sort(np.concatenate([o[1][o[0][b]:o[0][b + 1]] for o in o2]))
             assert np.array_equal(merged, ids[off[b]:off[b + 1]])
+    # empty lists, also trailing ones, are legal (the reference skips empty buckets)
+    off_e = np.array([0, 3, 5, 5, 5], np.int64)
+    ids_e = np.arange(5, dtype=np.int32)
+    for world in (1, 2, 3):
+        got = [stripe_csr(off_e, ids_e, r, world) for r in range(world)]
+        assert all(len(o[0]) == 5 and o[0][-1] == len(o[1]) for o in got)
+        assert np.array_equal(np.sort(np.concatenate([o[1] for o in got])), ids_e)
+        assert all(o[0][3] == o[0][2] == o[0][4] for o in got)
