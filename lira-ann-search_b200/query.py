@@ -169,28 +169,18 @@ def search_sweep(index: LiraIndex, model, x_q, gt_ids, k, thresholds=None, mode=
 # ---------------------------------------------------------------------------------------------
 # redundancy assignment -- LIRA_smallscale.py:77-97 / LIRA_largescale.py:51-72
 # ---------------------------------------------------------------------------------------------
-def mul_partition_by_model(data_partition_score, data_predicts, xd_id_sorted_pre, data_2_bkt, cluster_cnts, cluster_ids,
-                           begin, end):
-    """The reference's per-point Python loop, vectorised (same arguments, same in-place effects on `data_2_bkt`,
-    `cluster_cnts` and `cluster_ids`, same append order inside every `cluster_ids[c]`).
+def _as_numpy(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
-    For each point t of xd_id_sorted_pre[begin:end] (LIRA_smallscale.py:79-97): partitions ranked by score, descending;
-    n_actual = min(n_mul - 1, #partitions predicted for t); with `loc` the rank of t's current partition:
-      loc >= n_actual            -> the n_actual best go to columns 1..n_actual             (current partition kept in column 0)
-      else, n_eff == n_actual    -> the n_actual best replace columns 0..n_actual-1
-      else                       -> the n_actual + 1 best replace columns 0..n_actual
-    and t is appended to every chosen partition other than its current one. Equal scores are ranked by partition id
-    (torch.argsort leaves their order unspecified)."""
-    score = data_partition_score.detach().cpu().numpy() if hasattr(data_partition_score, "detach") else np.asarray(data_partition_score)
-    pred = data_predicts.detach().cpu().numpy() if hasattr(data_predicts, "detach") else np.asarray(data_predicts)
-    order = xd_id_sorted_pre.detach().cpu().numpy() if hasattr(xd_id_sorted_pre, "detach") else np.asarray(xd_id_sorted_pre)
-    t = np.asarray(order[begin:end], np.int64)
+
+def _mul_partition_rows(score_rows, pred_rows, t, data_2_bkt, cluster_cnts, cluster_ids):
+    """Core of both drivers' redundancy assignment, vectorised: score_rows[i] / pred_rows[i] belong to point t[i]."""
     if t.size == 0:
         return
     n_mul = data_2_bkt.shape[1]
-    top = np.argsort(-score[t], axis=1, kind="stable")[:, :n_mul]          # the n_mul best partitions of every point
+    top = np.argsort(-score_rows, axis=1, kind="stable")[:, :n_mul]       # the n_mul best partitions of every point
     width = top.shape[1]
-    n_eff = (pred[t] != 0).sum(1)
+    n_eff = (pred_rows != 0).sum(1)
     n_act = np.minimum(n_mul - 1, n_eff)
     cur = np.asarray(data_2_bkt[t, 0], np.int64)
     hit = top == cur[:, None]
@@ -212,3 +202,29 @@ def mul_partition_by_model(data_partition_score, data_predicts, xd_id_sorted_pre
     for c, ids in zip(part_s[np.r_[0, cuts]] if part_s.size else [], np.split(pts_s, cuts) if part_s.size else []):
         cluster_ids[int(c)].extend(int(x) for x in ids)
 
+
+def mul_partition_by_model(data_partition_score, data_predicts, xd_id_sorted_pre, data_2_bkt, cluster_cnts, cluster_ids,
+                           begin, end):
+    """The reference's per-point Python loop, vectorised (same arguments, same in-place effects on `data_2_bkt`,
+    `cluster_cnts` and `cluster_ids`, same append order inside every `cluster_ids[c]`).
+
+    For each point t of xd_id_sorted_pre[begin:end] (LIRA_smallscale.py:79-97): partitions ranked by score, descending;
+    n_actual = min(n_mul - 1, #partitions predicted for t); with `loc` the rank of t's current partition:
+      loc >= n_actual            -> the n_actual best go to columns 1..n_actual             (current partition kept in column 0)
+      else, n_eff == n_actual    -> the n_actual best replace columns 0..n_actual-1
+      else                       -> the n_actual + 1 best replace columns 0..n_actual
+    and t is appended to every chosen partition other than its current one. Equal scores are ranked by partition id
+    (torch.argsort leaves their order unspecified)."""
+    score, pred, order = _as_numpy(data_partition_score), _as_numpy(data_predicts), _as_numpy(xd_id_sorted_pre)
+    t = np.asarray(order[begin:end], np.int64)
+    _mul_partition_rows(score[t], pred[t], t, data_2_bkt, cluster_cnts, cluster_ids)
+
+
+def mul_partition_by_model_large(data_partition_score, data_predicts, global_xd_ids, start_idx, data_2_bkt, cluster_cnts,
+                                 cluster_ids):
+    """LIRA_largescale.py:51-72: the same rule for one batch of the full data -- row i of the score / predict matrices is
+    point global_xd_ids[i] = start_idx + i. Vectorised, same in-place effects and append order as the reference loop."""
+    score, pred = _as_numpy(data_partition_score), _as_numpy(data_predicts)
+    t = np.asarray(_as_numpy(global_xd_ids), np.int64)
+    local = t - int(start_idx)
+    _mul_partition_rows(score[local], pred[local], t, data_2_bkt, cluster_cnts, cluster_ids)

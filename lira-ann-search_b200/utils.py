@@ -114,6 +114,15 @@ def get_scaled_dist(x_d, x_q, kmeans, n_bkt, cfg, device=0, return_data=True):
     return d_scaled, q_scaled
 
 
+def get_scaled_dist_data(x_d, kmeans, n_bkt, device=0):
+    """Standardised centroid distances of one batch of data rows with a scaler fitted ON THAT BATCH (utils.py:182-215,
+    called once per 1 000 000-row redundancy batch at LIRA_largescale.py:323): every batch is standardised with its own
+    mean / std, not with the scaler the model was trained with -- reproduced as the reference does it."""
+    scaler = _fit_scaler(x_d, kmeans, n_bkt, device)
+    return engine.centroid_features(x_d, kmeans.centroids, scaler.mean_.astype(np.float32), scaler.scale_.astype(np.float32),
+                                    device)
+
+
 # ---------------------------------------------------------------------------------------------
 # ground truth / self-kNN (a11) -- utils.py:223-319
 # ---------------------------------------------------------------------------------------------
@@ -266,6 +275,14 @@ def create_flat_indexes(x_d, xd_id_bkts, cfg, dis_metric: str = "L2", device=0):
 
 def create_inner_indexes(x_d, cluster_ids, cfg, device=0):
     return create_flat_indexes(x_d, cluster_ids, cfg, dis_metric=cfg.dis_metric, device=device)
+
+
+def get_idle_gpu():
+    """Index of the GPU with the least memory in use (utils.py:90-96 asks nvidia-smi; NVML is the library behind it)."""
+    import pynvml
+    pynvml.nvmlInit()
+    used = [pynvml.nvmlDeviceGetMemoryInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).used for i in range(pynvml.nvmlDeviceGetCount())]
+    return int(np.argmin(used))
 
 
 def per_query(all_outputs, knn_distr_cnt_query, cluster_cnts, n_bkt, cfg, nq_test=100, recall_target=0.98):

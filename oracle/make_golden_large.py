@@ -146,6 +146,7 @@ def main():
             for idx, cid in enumerate(single.flatten()):
                 cluster_ids[cid].append(idx)
             out["assign_full"] = single.flatten().astype(np.int32)
+            out["labels_query_sub"] = labels_query.astype(np.uint8)
             knn_query = gt[:, :cfg.k]
             cnt_q, ids_q = U.get_knn_distr_redundancy(knn_query, data_2_bkt, cfg)
 
@@ -160,6 +161,7 @@ def main():
 
             # :320-329 full redundancy, in batches with their OWN scaler (utils.py:182-215)
             first = True
+            score_all = np.zeros((n_d, B), np.float32)
             for start_idx in range(0, n_d, BATCH_RED):
                 end_idx = min(start_idx + BATCH_RED, n_d)
                 xd_batch = x_d[start_idx:end_idx]
@@ -169,11 +171,11 @@ def main():
                 tl = DataLoader(TensorDataset(torch.tensor(dist_b, dtype=torch.float32), torch.tensor(xd_batch, dtype=torch.float32)),
                                 batch_size=cfg.batch_size, shuffle=False)
                 data_predicts, data_score = MP.model_infer(model, tl, device)
-                if first:
-                    out["score_batch0"] = data_score.numpy().astype(np.float32)
-                    first = False
+                score_all[start_idx:end_idx] = data_score.numpy()
+                first = False
                 S.mul_partition_by_model(data_score, data_predicts, np.arange(start_idx, end_idx), start_idx, data_2_bkt,
                                          cluster_cnts, cluster_ids)
+            out["score_all"] = score_all
             out["d2b1"] = data_2_bkt.astype(np.int32)
             out["cnts1"] = np.asarray(cluster_cnts, np.int64)
             out["lists1_off"], out["lists1_ids"] = csr(cluster_ids)
