@@ -140,6 +140,13 @@ int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d,
  * fp16 shadow copy are made once at create, every search only moves its query batch. */
 int lira_knn_create(const float* base, int64_t N, int d, int metric, int device, lira_knn_t** out);
 int lira_knn_search(lira_knn_t* h, const float* query, int64_t Q, int k, float* D, int64_t* I);
+/* The same over DEVICE memory: the base d_base[N, ld] (ld % 4 == 0, padding columns zero, 16-byte aligned) is adopted, not
+ * copied, and must outlive the handle; queries and results are device pointers (the 10 000-row batches of
+ * compute_knn.cpp:228-244 without a host round trip; also the K-Means assignment step of utils.py:325, where the base is
+ * the centroid table and k = 1). */
+int lira_knn_create_dev(const float* d_base, int64_t ld, int64_t N, int d, int metric, int device, lira_knn_t** out);
+int lira_knn_search_dev(lira_knn_t* h, const float* d_query, int64_t ldq, int64_t Q, int k, float* d_D, int64_t* d_I,
+                        void* stream);
 int lira_knn_free(lira_knn_t* h);
 int64_t lira_knn_ntotal(const lira_knn_t* h);
 int lira_knn_set_use_tensor_cores(lira_knn_t* h, int enable);

@@ -51,6 +51,8 @@ SIGNATURES = {
     "lira_knn": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_int, c_int, c_int, c_int, c_f32p, c_i64p]),
     "lira_knn_create": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "lira_knn_search": (c_int, [c_vp, c_f32p, c_i64, c_int, c_f32p, c_i64p]),
+    "lira_knn_create_dev": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "lira_knn_search_dev": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     "lira_knn_free": (c_int, [c_vp]),
     "lira_knn_ntotal": (c_i64, [c_vp]),
     "lira_knn_set_use_tensor_cores": (c_int, [c_vp, c_int]),

@@ -1622,6 +1622,7 @@ struct lira_knn_index {
     int device = 0, d = 0, ds = 0, metric = 0;
     long long N = 0, seg = 0;
     int last_path = 0;           // 0 = CUDA cores, 1 = tensor cores, 2 = mixed (some batches of the last search on each)
+    const float* base = nullptr; // [N, ds] on the device: dbase (uploaded by lira_knn_create) or the caller's memory (lira_knn_create_dev)
     DevBuf dbase, dids;
     lira_index_t* index = nullptr;
 };
@@ -1654,6 +1655,28 @@ static int knn_set_segments(lira_knn_index* kn, long long seg) {
 
 extern "C" {
 
+static int knn_finish_create(lira_knn_index* kn) {
+    const long long N = kn->N;
+    cudaStream_t st0 = nullptr;
+    LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+    int r = kn->dids.ensure((size_t)N * 4);
+    if (!r) {
+        iota_i32_kernel<<<grid_for(N, 256), 256, 0, st0>>>(kn->dids.as<int>(), N);
+        g_launches.fetch_add(1);
+    }
+    cudaError_t e = cudaStreamSynchronize(st0);
+    cudaStreamDestroy(st0);
+    if (r) return r;
+    LIRA_CUDA_OK(e);
+    const long long seg = 8192;
+    const int nseg = (int)((N + seg - 1) / seg);
+    std::vector<int64_t> off(nseg + 1);
+    for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
+    if (int r2 = lira_index_create_dev(kn->base, kn->ds, kn->d, off.data(), kn->dids.as<int>(), nseg, kn->metric, kn->device, &kn->index)) return r2;
+    kn->seg = seg;
+    return 0;
+}
+
 int lira_knn_create(const float* base, int64_t N, int d, int metric, int device, lira_knn_t** out) {
     LIRA_REQUIRE(out && base && N >= 1 && d >= 1, "bad argument");
     LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per handle");
@@ -1665,24 +1688,29 @@ int lira_knn_create(const float* base, int64_t N, int d, int metric, int device,
         cudaStream_t st0 = nullptr;
         LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
         int r = upload_rows(kn->dbase, base, N, d, kn->ds, st0);
-        if (!r) r = kn->dids.ensure((size_t)N * 4);
-        if (!r) {
-            iota_i32_kernel<<<grid_for(N, 256), 256, 0, st0>>>(kn->dids.as<int>(), N);
-            g_launches.fetch_add(1);
-        }
         cudaError_t e = cudaStreamSynchronize(st0);
         cudaStreamDestroy(st0);
         if (r) return r;
         LIRA_CUDA_OK(e);
-        const long long seg = 8192;
-        const int nseg = (int)((N + seg - 1) / seg);
-        std::vector<int64_t> off(nseg + 1);
-        for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
-        if (int r2 = lira_index_create_dev(kn->dbase.as<float>(), kn->ds, d, off.data(), kn->dids.as<int>(), nseg, metric, device, &kn->index)) return r2;
-        kn->seg = seg;
-        return 0;
+        kn->base = kn->dbase.as<float>();
+        return knn_finish_create(kn);
     };
     const int rc = body();
+    if (rc) { lira_knn_free(kn); return rc; }
+    *out = kn;
+    return 0;
+}
+
+int lira_knn_create_dev(const float* d_base, int64_t ld, int64_t N, int d, int metric, int device, lira_knn_t** out) {
+    LIRA_REQUIRE(out && d_base && N >= 1 && d >= 1, "bad argument");
+    LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31 per handle");
+    LIRA_REQUIRE(ld >= d && (ld % 4) == 0 && ((uintptr_t)d_base & 15) == 0, "device base needs ld % 4 == 0 and 16-byte alignment");
+    LIRA_REQUIRE(metric == LIRA_METRIC_L2 || metric == LIRA_METRIC_IP, "metric must be LIRA_METRIC_L2 or LIRA_METRIC_IP");
+    if (int rc = check_device(device)) return rc;
+    lira_knn_index* kn = new lira_knn_index();
+    kn->device = device; kn->d = d; kn->ds = (int)ld; kn->metric = metric; kn->N = N;
+    kn->base = d_base;
+    const int rc = knn_finish_create(kn);
     if (rc) { lira_knn_free(kn); return rc; }
     *out = kn;
     return 0;
@@ -1707,10 +1735,9 @@ int lira_knn_set_use_tensor_cores(lira_knn_t* kn, int enable) {
     return 0;
 }
 
-int lira_knn_search(lira_knn_t* kn, const float* query, int64_t Q, int k, float* D, int64_t* I) {
-    LIRA_REQUIRE(kn && kn->index && query && D && I && Q >= 0, "bad argument");
-    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
-    LIRA_CUDA_OK(cudaSetDevice(kn->device));
+// one search over device queries; host_q != nullptr: the batches are uploaded from there (d_q ignored) and the results copied back
+static int knn_search_impl(lira_knn_t* kn, const float* host_q, const float* d_q, long long ldq, int64_t Q, int k, float* D, int64_t* I,
+                           cudaStream_t st_user) {
     lira_index* h = kn->index;
     const int d = kn->d, ds = kn->ds;
     // k <= 16 on a large base: long segments (the in-kernel compaction keeps their candidate regions small), i.e. 8x fewer
@@ -1718,29 +1745,48 @@ int lira_knn_search(lira_knn_t* kn, const float* query, int64_t Q, int k, float*
     const long long seg = (k <= 16 && kn->N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
     if (int rc = knn_set_segments(kn, seg)) return rc;
     const int nseg = h->B;
-    cudaStream_t st = h->stream;
+    cudaStream_t st = st_user ? st_user : h->stream;
     Workspace& ws = h->ws;
     int redo_total = 0, n_tc = 0, n_batches = 0;
     const long long max_pairs = 4ll << 20;   // (query, segment) pairs per batch: bounds the per-pair workspaces (1 KiB each on the tensor-core path)
     const long long qb = std::max<long long>(1, std::min<long long>(std::max<int64_t>(Q, 1), max_pairs / nseg));
     for (long long q0 = 0; q0 < Q; q0 += qb) {
         const long long nq = std::min<long long>(qb, Q - q0);
-        if (int r3 = upload_rows(ws.q, query + q0 * d, nq, d, ds, st)) return r3;
         ProbeSpec ps;
         ps.kind = 2;
-        if (int r3 = ws.D.ensure((size_t)nq * k * 4)) return r3;
-        if (int r3 = ws.I.ensure((size_t)nq * k * 8)) return r3;
-        if (int r3 = search_core(h, ws.q.as<float>(), ds, nq, ps, k, 1, ws.D.as<float>(), ws.I.as<long long>(), nullptr, nullptr, st)) return r3;
+        if (host_q) {
+            if (int r3 = upload_rows(ws.q, host_q + q0 * d, nq, d, ds, st)) return r3;
+            if (int r3 = ws.D.ensure((size_t)nq * k * 4)) return r3;
+            if (int r3 = ws.I.ensure((size_t)nq * k * 8)) return r3;
+            if (int r3 = search_core(h, ws.q.as<float>(), ds, nq, ps, k, 1, ws.D.as<float>(), ws.I.as<long long>(), nullptr, nullptr, st)) return r3;
+            LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)q0 * k, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)q0 * k, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        } else {
+            if (int r3 = search_core(h, d_q + q0 * ldq, ldq, nq, ps, k, 1, D + (size_t)q0 * k, (long long*)I + (size_t)q0 * k, nullptr, nullptr, st)) return r3;
+        }
         redo_total += h->last_redo;
         n_tc += h->last_path == 1;
         ++n_batches;
-        LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)q0 * k, ws.D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-        LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)q0 * k, ws.I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-        LIRA_CUDA_OK(cudaStreamSynchronize(st));
     }
     h->last_redo = redo_total;
     kn->last_path = n_tc == 0 ? 0 : (n_tc == n_batches ? 1 : 2);
     return 0;
+}
+
+int lira_knn_search(lira_knn_t* kn, const float* query, int64_t Q, int k, float* D, int64_t* I) {
+    LIRA_REQUIRE(kn && kn->index && query && D && I && Q >= 0, "bad argument");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_CUDA_OK(cudaSetDevice(kn->device));
+    return knn_search_impl(kn, query, nullptr, 0, Q, k, D, I, nullptr);
+}
+
+int lira_knn_search_dev(lira_knn_t* kn, const float* d_query, int64_t ldq, int64_t Q, int k, float* d_D, int64_t* d_I, void* stream) {
+    LIRA_REQUIRE(kn && kn->index && d_query && d_D && d_I && Q >= 0, "bad argument");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_REQUIRE(ldq >= kn->d && (ldq % 4) == 0 && ((uintptr_t)d_query & 15) == 0, "device queries need ld % 4 == 0 and 16-byte alignment");
+    LIRA_CUDA_OK(cudaSetDevice(kn->device));
+    return knn_search_impl(kn, nullptr, d_query, ldq, Q, k, d_D, d_I, (cudaStream_t)stream);
 }
 
 int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d, int k, int metric, int device,

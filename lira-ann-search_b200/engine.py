@@ -336,9 +336,17 @@ class KnnIndex:
 
     def __init__(self, base, metric="L2", device=0):
         C.require_gpu()
+        self._h = ctypes.c_void_p()
+        if hasattr(base, "data_ptr"):   # torch CUDA tensor [N, d] (row stride % 4 == 0): adopted, not copied
+            if not base.is_cuda or base.dtype.__str__() != "torch.float32" or base.stride(1) != 1:
+                raise ValueError("device base must be a float32 CUDA tensor with unit column stride")
+            self.ntotal, self.dim, self.device = base.shape[0], base.shape[1], base.device.index
+            self._keep = base
+            C.check(C.lib().lira_knn_create_dev(base.data_ptr(), base.stride(0), base.shape[0], base.shape[1], _metric_code(metric),
+                                                self.device, ctypes.byref(self._h)))
+            return
         base = C.f32(base)
         self.ntotal, self.dim, self.device = base.shape[0], base.shape[1], device
-        self._h = ctypes.c_void_p()
         C.check(C.lib().lira_knn_create(C.ptr(base, C.c_f32p), base.shape[0], base.shape[1], _metric_code(metric), device,
                                         ctypes.byref(self._h)))
 
@@ -349,6 +357,17 @@ class KnnIndex:
         C.check(C.lib().lira_knn_search(self._h, C.ptr(query, C.c_f32p), query.shape[0], int(k), C.ptr(D, C.c_f32p),
                                         C.ptr(I, C.c_i64p)))
         return D, I
+
+    def search_dev(self, d_query, k, out=None, stream=None):
+        """torch CUDA queries [Q, d] -> (D[Q,k] float32, I[Q,k] int64) CUDA tensors; no host round trip."""
+        import torch
+        Q = d_query.shape[0]
+        if out is None:
+            out = (torch.empty((Q, k), dtype=torch.float32, device=d_query.device),
+                   torch.empty((Q, k), dtype=torch.int64, device=d_query.device))
+        C.check(C.lib().lira_knn_search_dev(self._h, d_query.data_ptr(), d_query.stride(0), Q, int(k), out[0].data_ptr(),
+                                            out[1].data_ptr(), _stream_handle(d_query.device, stream)))
+        return out
 
     def set_use_tensor_cores(self, enable=True):
         C.check(C.lib().lira_knn_set_use_tensor_cores(self._h, int(bool(enable))))
