@@ -573,21 +573,24 @@ def run_reference(args, world, log):
 # ---------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
-def timed_steps(step, args, stream, flush, index, dist, clocks, rank):
+def timed_steps(step, args, stream, flush, index, dist, clocks, rank, sync_step):
     """W untimed warm-up steps, then exactly K steps: per-step CUDA events on `stream`, L2 flushed between steps (outside the
-    events), barrier + synchronize on both sides, max over ranks."""
+    events), barrier + synchronize on both sides, max over ranks. `step` only ENQUEUES a batch (lira_probe_search_enqueue_dev
+    [+ the NCCL all-gather and the merge]): consecutive steps queue up behind each other on the stream like the batches of a
+    serving loop, and lira_index_finish checks every batch's status words after the loop. Kernel-level timings come from
+    three extra, individually synchronised steps (`sync_step`) after the timed region."""
     import torch
+    import lira_ann_search_b200 as L
     for _ in range(args.warmup):
         flush.zero_()
         step()
+    index.finish()
     torch.cuda.synchronize()
-    import lira_ann_search_b200 as L
     launches0 = L.launch_count()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    tms = []
     clocks.mark_begin()
     t_wall = time.perf_counter()
     res = None
@@ -596,8 +599,7 @@ def timed_steps(step, args, stream, flush, index, dist, clocks, rank):
         ev[i][0].record(stream)
         res = step()
         ev[i][1].record(stream)
-        ev[i][1].synchronize()
-        tms.append(index.last_timing())
+    index.finish()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -609,6 +611,12 @@ def timed_steps(step, args, stream, flush, index, dist, clocks, rank):
         t = torch.tensor([total_ms], device=flush.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+    tms = []
+    for _ in range(3):
+        flush.zero_()
+        sync_step()
+        torch.cuda.synchronize()
+        tms.append(index.last_timing())
     return res, total_ms, wall, launches, tms
 
 
@@ -723,13 +731,17 @@ def run_sift1m(args, rank, world, local, dist, log):
 
     def step():
         nonlocal out
-        out = index.probe_search_dev(model, d_q, L.SELECT_GT, thr, k, True, out=out)
+        out = index.probe_search_enqueue_dev(model, d_q, L.SELECT_GT, thr, k, True, out=out)
         return gather_merge(out[0], out[1])
+
+    def sync_step():
+        nonlocal out
+        out = index.probe_search_dev(model, d_q, L.SELECT_GT, thr, k, True, out=out)
 
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    (D, I), total_ms, wall, launches, tms = timed_steps(step, args, stream, flush, index, dist, clocks, rank)
+    (D, I), total_ms, wall, launches, tms = timed_steps(step, args, stream, flush, index, dist, clocks, rank, sync_step)
     clk = clocks.stop() if rank == 0 else None
     rec = recall_at(I.cpu().numpy(), gt, k)
 
@@ -999,8 +1011,9 @@ def run_shard(args, rank, world, local, dist, log):
         return out[0], out[1]
 
     def step():
-        D, I = local_step()
-        return gather_merge(D, I)
+        nonlocal out
+        out = index.probe_search_enqueue_dev(model, x_q, L.SELECT_GT, thr, k, True, out=out)
+        return gather_merge(out[0], out[1])
 
     # one rank's share alone (no collective): what a single GPU needs for a 12.5 M-vector dataset
     for _ in range(3):
@@ -1022,7 +1035,7 @@ def run_shard(args, rank, world, local, dist, log):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    (D, I), total_ms, wall, launches, tms = timed_steps(step, args, stream, flush, index, dist, clocks, rank)
+    (D, I), total_ms, wall, launches, tms = timed_steps(step, args, stream, flush, index, dist, clocks, rank, local_step)
     clk = clocks.stop() if rank == 0 else None
     Ih = I.cpu().numpy()
     rec = recall_at(Ih, gt, k)

@@ -124,6 +124,24 @@ int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t 
 int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q,
                           int mode, double value, int k, int dedup, float* d_D, int64_t* d_I,
                           int32_t* d_nprobe, int64_t* d_cmp, void* stream);
+/* The same call split in two so that consecutive batches pipeline (search.cpp answers its queries one after the other,
+ * search.cpp:421-517; a server answers a stream of batches):
+ *   lira_probe_search_enqueue_dev  launches the whole query phase of the batch on the stream and returns without waiting;
+ *   lira_index_finish              waits for every batch enqueued on the handle and checks their status words. The fused
+ *                                  tensor-core flow is optimistic (fp16-exact batch, at most nprobe_cap partitions per query,
+ *                                  no candidate-region overflow); a batch for which that did not hold is answered again here
+ *                                  through the checked path, into the same output buffers. Results are valid after finish.
+ * Host-buffer form with two staging slots: submit(slot) copies the queries in (pinned or pageable source) on a copy
+ * stream, enqueues the batch and the copy of its results into pinned memory on a second copy stream; wait(slot) returns
+ * the results in the caller's arrays. With submit(i+1) issued before wait(i), the copies of one batch overlap the
+ * kernels of the other. */
+int lira_probe_search_enqueue_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q,
+                                  int mode, double value, int k, int dedup, float* d_D, int64_t* d_I,
+                                  int32_t* d_nprobe, int64_t* d_cmp, void* stream);
+int lira_index_finish(lira_index_t* h);
+int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, int64_t Q, int mode,
+                             double value, int k, int dedup, int slot);
+int lira_probe_search_wait(lira_index_t* h, int slot, float* D, int64_t* I, int32_t* nprobe, int64_t* cmp);
 /* search with scores already on the device (threshold replay of query_tuning, LIRA_smallscale.py:199-220) */
 int lira_select_search_dev(lira_index_t* h, const float* d_scores, int64_t lds, const float* d_q,
                            int64_t ldq, int64_t Q, int mode, double value, int k, int dedup, float* d_D,
@@ -168,6 +186,9 @@ int64_t lira_launch_count(void);
 int lira_index_last_timing(const lira_index_t* h, float* scan_ms, float* total_ms, int64_t* scan_bytes,
                            int64_t* scan_pairs);
 int lira_index_set_timing(lira_index_t* h, int enable);
+/* device time of ALL kernels of the last scan -- seed pass + filter pass + refine on the tensor-core path (the scan as
+ * SURVEY.md 8d defines it: probed entries in, de-duplicated top-k out); equals scan_ms on the CUDA-core path */
+int lira_index_last_scan_total_ms(const lira_index_t* h, float* scan_total_ms);
 /* The online search (lira_search*, lira_probe_search*, lira_select_search*) has two implementations of the list
  * scan with the same results: fp32 CUDA cores (always valid) and tcgen05 tensor cores, taken for batches of
  * >= 256 queries and d <= 1024 (256 < d: both operands stream) in one of two modes decided when the index is created:

@@ -47,6 +47,10 @@ SIGNATURES = {
     "lira_model_scores": (c_int, [c_vp, c_f32p, c_i64, c_f32p, c_f32p]),
     "lira_probe_search": (c_int, [c_vp, c_vp, c_f32p, c_i64, c_int, ctypes.c_double, c_int, c_int, c_f32p, c_i64p, c_i32p, c_i64p]),
     "lira_probe_search_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, ctypes.c_double, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lira_probe_search_enqueue_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, ctypes.c_double, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lira_index_finish": (c_int, [c_vp]),
+    "lira_probe_search_submit": (c_int, [c_vp, c_vp, c_f32p, c_i64, c_int, ctypes.c_double, c_int, c_int, c_int]),
+    "lira_probe_search_wait": (c_int, [c_vp, c_int, c_f32p, c_i64p, c_i32p, c_i64p]),
     "lira_select_search_dev": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, ctypes.c_double, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lira_knn": (c_int, [c_f32p, c_i64, c_f32p, c_i64, c_int, c_int, c_int, c_int, c_f32p, c_i64p]),
     "lira_knn_create": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
@@ -63,6 +67,7 @@ SIGNATURES = {
     "lira_launch_count": (c_i64, []),
     "lira_index_last_timing": (c_int, [c_vp, c_f32p, c_f32p, c_i64p, c_i64p]),
     "lira_index_set_timing": (c_int, [c_vp, c_int]),
+    "lira_index_last_scan_total_ms": (c_int, [c_vp, c_f32p]),
     "lira_index_set_use_tensor_cores": (c_int, [c_vp, c_int]),
     "lira_index_last_path": (c_int, [c_vp]),
     "lira_index_last_redo": (c_int, [c_vp]),

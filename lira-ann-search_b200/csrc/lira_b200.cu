@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <thread>
 #include <mutex>
 #include <numeric>
@@ -17,6 +18,7 @@
 #include "probe_kernels.cuh"
 #include "tc_scan_kernels.cuh"
 #include "tc_dense_kernels.cuh"
+#include "fused_probe_kernels.cuh"
 
 namespace lira {
 
@@ -155,6 +157,26 @@ struct Workspace {
 
 using namespace lira;
 
+// a batch that was enqueued without waiting for its status words (lira_probe_search_enqueue_dev / _submit): everything
+// lira_index_finish needs to check it and, in the rare cases the optimistic run is void, to answer it again
+struct PendingBatch {
+    cudaEvent_t ev = nullptr;      // recorded behind the copy of the status words (and, for host batches, of the results)
+    int* h_flags = nullptr;        // pinned [4]: not exact in fp16 / queries left for the exact path / probe set truncated / --
+    lira_model* m = nullptr;
+    const float* d_q = nullptr;
+    long long ldq = 0, Q = 0;
+    int mode = 0;
+    double value = 0;
+    int k = 0, dedup = 1;
+    float* d_D = nullptr;
+    long long* d_I = nullptr;
+    int* d_nprobe = nullptr;
+    long long* d_cmp = nullptr;
+    cudaStream_t st = nullptr;
+    bool enqueued = false;         // false: the batch did not qualify for the fused flow and nothing was launched
+    int slot = -1;                 // host-buffer batches (lira_probe_search_submit): staging slot
+};
+
 struct lira_index {
     int device = 0, B = 0, d = 0, ds = 0, metric = 0;
     long long E = 0;
@@ -167,6 +189,23 @@ struct lira_index {
     CUtensorMap tmap;
     cudaStream_t stream = nullptr;
     Workspace ws, ws_seed;
+    int* h_flags = nullptr;      // pinned: the four status words of a tensor-core batch land here (no pageable staging on the way back)
+    struct HostSlot {                            // lira_probe_search_submit / _wait: one batch of host queries in flight
+        DevBuf q, D, I, nprobe, cmp;
+        void* pin_in = nullptr;                  // pinned copy of the queries when the caller's array is pageable
+        size_t pin_in_cap = 0;
+        void* pin_out = nullptr;                 // pinned landing area of the results
+        size_t pin_out_cap = 0;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+        PendingBatch pb;
+        bool busy = false, sync_done = false;
+        const float* user_q = nullptr;
+        size_t oI = 0, oC = 0, oN = 0;
+    } slots[2];
+    cudaStream_t st_in = nullptr, st_out = nullptr;   // copy streams of the submit / wait pipeline
+    std::deque<PendingBatch> pending;            // enqueued, not yet checked (oldest first)
+    std::vector<int*> flag_pool;                 // free pinned status slots
+    std::vector<cudaEvent_t> event_pool;         // free events (timing disabled)
     void* h_stage = nullptr;     // pinned host staging for results (D2H into pageable user buffers is staged by the driver otherwise,
     size_t h_stage_cap = 0;      //   synchronously and in small pieces)
     DevBuf stats;                // {E_p, pairs} of the last timed scan (copied out of ws.n_items before it is reused)
@@ -187,8 +226,9 @@ struct lira_index {
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
     int last_redo = 0;           // queries of the last tensor-core batch redone on the CUDA cores
     bool timing = false, timing_pending = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float last_scan_ms = 0.f, last_total_ms = 0.f;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0,1] filter kernel, [2,3] whole search, [4,5] seed + filter + refine
+    float last_scan_ms = 0.f, last_total_ms = 0.f, last_scan_total_ms = 0.f;
+    bool scan_total_valid = false;
     long long last_scan_bytes = 0, last_scan_pairs = 0, last_Q = 0;
     int last_k = 0;
     int num_sms = 148;
@@ -203,6 +243,8 @@ struct lira_model {
     int out_dim[6], in_dim[6], in_ld[6];
     CUtensorMap tm_cent, tm_w[6];
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;                 // vector_net runs here, concurrently with the centroid features and distance_net
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = 148;
     DevBuf feats, h1, cat, h2, h5, scores, q;
     // tensor-core front end (tc_dense_kernels.cuh): error-free hi / lo splits of the static operands ...
@@ -243,6 +285,7 @@ static int init_kernels(int device) {
     rc |= set_smem(tc_dense_kernel<TD_EPI_FEATURE>, TD_SMEM_BYTES);
     rc |= set_smem(tc_dense_kernel<TD_EPI_BIAS_RELU>, TD_SMEM_BYTES);
     rc |= set_smem(tc_dense_kernel<TD_EPI_BIAS_SIGMOID>, TD_SMEM_BYTES);
+    rc |= set_smem(tc_dense_kernel<TD_EPI_SELECT>, TD_SMEM_BYTES);
     if (device < 64) done_dev[device] = (rc == 0);
     return rc;
 }
@@ -321,28 +364,59 @@ static int launch_tc_dense(const float* a_h, const float* a_l, long long M, int 
     return 0;
 }
 
-static int model_forward_tc(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
-                            float* d_feats_out, long long ldf_out, cudaStream_t st) {
-    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0 && (lds % 4) == 0, "queries / scores must be 16-byte aligned with ld % 4 == 0");
-    LIRA_REQUIRE(!d_feats_out || (ldf_out % 4) == 0, "feats output needs a row stride that is a multiple of 4");
-    const size_t Qs = (size_t)Q;
-    const int ds = m->ds, B = m->B, Bp = m->Bp;
+// selection fused into the last layer (tc_dense_kernel<TD_EPI_SELECT>): where the probe lists go
+struct FusedSelect {
+    int* sel;
+    int* nsel;
+    int* list_count;
+    unsigned long long* rowbest;
+    int cap, mode;
+    float thr;
+};
+
+static int model_ensure_tc(lira_model* m, long long Q) {
+    const size_t Qs = (size_t)std::max<long long>(Q, 1);
     for (DevBuf* b : {&m->qch, &m->qcl, &m->qrh, &m->qrl})
-        if (int rc = b->ensure(Qs * ds * 4)) return rc;
+        if (int rc = b->ensure(Qs * m->ds * 4)) return rc;
     if (int rc = m->qn.ensure(Qs * 4)) return rc;
     for (DevBuf* b : {&m->fh, &m->fl})
-        if (int rc = b->ensure(Qs * Bp * 4)) return rc;
+        if (int rc = b->ensure(Qs * m->Bp * 4)) return rc;
     for (DevBuf* b : {&m->h1h, &m->h1l, &m->cath, &m->catl, &m->h2h, &m->h2l, &m->h5h, &m->h5l})
         if (int rc = b->ensure(Qs * 128 * 4)) return rc;
+    return 0;
+}
+
+// prepped: the hi / lo splits of the queries and |q'|^2 are already in m->qch .. m->qn (prep_queries_kernel);
+// fs != null: the last layer selects instead of writing scores (d_scores unused)
+static int model_forward_tc(lira_model* m, const float* d_q, long long ldq, long long Q, float* d_scores, long long lds,
+                            float* d_feats_out, long long ldf_out, cudaStream_t st, bool prepped = false, const FusedSelect* fs = nullptr) {
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0 && (lds % 4) == 0, "queries / scores must be 16-byte aligned with ld % 4 == 0");
+    LIRA_REQUIRE(!d_feats_out || (ldf_out % 4) == 0, "feats output needs a row stride that is a multiple of 4");
+    const int ds = m->ds, B = m->B, Bp = m->Bp;
+    if (int rc = model_ensure_tc(m, Q)) return rc;
     const int num_sms = m->num_sms;
     const int warps = 8;
     const int sgrid = (int)((Q + warps - 1) / warps);
-    // queries: centred split (+ |q'|^2) for the distance features, raw split for vector_net
-    split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, m->mu, m->qch.as<float>(), m->qcl.as<float>(), ds, m->qn.as<float>());
-    LIRA_LAUNCH_CHECK();
-    split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, nullptr, m->qrh.as<float>(), m->qrl.as<float>(), ds, nullptr);
-    LIRA_LAUNCH_CHECK();
+    if (!prepped) {
+        // queries: centred split (+ |q'|^2) for the distance features, raw split for vector_net
+        split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, m->mu, m->qch.as<float>(), m->qcl.as<float>(), ds, m->qn.as<float>());
+        LIRA_LAUNCH_CHECK();
+        split_rows_kernel<<<sgrid, warps * 32, 0, st>>>(d_q, ldq, m->d, Q, nullptr, m->qrh.as<float>(), m->qrl.as<float>(), ds, nullptr);
+        LIRA_LAUNCH_CHECK();
+    }
     TdParams tp;
+    // vector_net (model_probing.py:19-24) depends on the raw queries only: it runs on a second stream next to the centroid
+    // features and distance_net, and joins before fc
+    cudaStream_t sv = (m->side && !getenv("LIRA_NO_SIDE_STREAM")) ? m->side : st;
+    if (sv != st) {
+        LIRA_CUDA_OK(cudaEventRecord(m->ev_fork, st));
+        LIRA_CUDA_OK(cudaStreamWaitEvent(sv, m->ev_fork, 0));
+    }
+    tp = TdParams{(int)Q, 128, m->d, m->h2h.as<float>(), m->h2l.as<float>(), nullptr, 128, 0, 0, m->bias[2], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->qrh.as<float>(), m->qrl.as<float>(), Q, m->d, ds, m->tm_wh[2], m->tm_wl[2], 128, tp, num_sms, sv)) return rc;
+    tp = TdParams{(int)Q, 64, 128, m->cath.as<float>(), m->catl.as<float>(), nullptr, 128, 0, 64, m->bias[3], nullptr, nullptr, nullptr};
+    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->h2h.as<float>(), m->h2l.as<float>(), Q, 128, 128, m->tm_wh[3], m->tm_wl[3], 64, tp, num_sms, sv)) return rc;
+    if (sv != st) LIRA_CUDA_OK(cudaEventRecord(m->ev_join, sv));
     // K0: ||q - c_b||_2, standardised (utils.py:98-118,142-167; search.cpp:220-250)
     tp = TdParams{(int)Q, B, ds, m->fh.as<float>(), m->fl.as<float>(), d_feats_out, Bp, (long)ldf_out, 0,
                   m->cn, m->mean, m->scale, m->qn.as<float>()};
@@ -352,14 +426,17 @@ static int model_forward_tc(lira_model* m, const float* d_q, long long ldq, long
     if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->fh.as<float>(), m->fl.as<float>(), Q, B, Bp, m->tm_wh[0], m->tm_wl[0], 128, tp, num_sms, st)) return rc;
     tp = TdParams{(int)Q, 64, 128, m->cath.as<float>(), m->catl.as<float>(), nullptr, 128, 0, 0, m->bias[1], nullptr, nullptr, nullptr};
     if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->h1h.as<float>(), m->h1l.as<float>(), Q, 128, 128, m->tm_wh[1], m->tm_wl[1], 64, tp, num_sms, st)) return rc;
-    // vector_net (model_probing.py:19-24)
-    tp = TdParams{(int)Q, 128, m->d, m->h2h.as<float>(), m->h2l.as<float>(), nullptr, 128, 0, 0, m->bias[2], nullptr, nullptr, nullptr};
-    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->qrh.as<float>(), m->qrl.as<float>(), Q, m->d, ds, m->tm_wh[2], m->tm_wl[2], 128, tp, num_sms, st)) return rc;
-    tp = TdParams{(int)Q, 64, 128, m->cath.as<float>(), m->catl.as<float>(), nullptr, 128, 0, 64, m->bias[3], nullptr, nullptr, nullptr};
-    if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->h2h.as<float>(), m->h2l.as<float>(), Q, 128, 128, m->tm_wh[3], m->tm_wl[3], 64, tp, num_sms, st)) return rc;
+    if (sv != st) LIRA_CUDA_OK(cudaStreamWaitEvent(st, m->ev_join, 0));
     // fc (model_probing.py:26-31): cat -> 128 -> B, sigmoid
     tp = TdParams{(int)Q, 128, 128, m->h5h.as<float>(), m->h5l.as<float>(), nullptr, 128, 0, 0, m->bias[4], nullptr, nullptr, nullptr};
     if (int rc = launch_tc_dense<TD_EPI_BIAS_RELU>(m->cath.as<float>(), m->catl.as<float>(), Q, 128, 128, m->tm_wh[4], m->tm_wl[4], 128, tp, num_sms, st)) return rc;
+    if (fs) {
+        tp = TdParams{(int)Q, B, 128, nullptr, nullptr, nullptr, 0, 0, 0, m->bias[5], nullptr, nullptr, nullptr};
+        tp.sel = fs->sel; tp.nsel = fs->nsel; tp.list_count = fs->list_count; tp.rowbest = fs->rowbest;
+        tp.sel_cap = fs->cap; tp.sel_mode = fs->mode; tp.sel_thr = fs->thr;
+        if (int rc = launch_tc_dense<TD_EPI_SELECT>(m->h5h.as<float>(), m->h5l.as<float>(), Q, 128, 128, m->tm_wh[5], m->tm_wl[5], B, tp, num_sms, st)) return rc;
+        return 0;
+    }
     tp = TdParams{(int)Q, B, 128, nullptr, nullptr, d_scores, 0, (long)lds, 0, m->bias[5], nullptr, nullptr, nullptr};
     if (int rc = launch_tc_dense<TD_EPI_BIAS_SIGMOID>(m->h5h.as<float>(), m->h5l.as<float>(), Q, 128, 128, m->tm_wh[5], m->tm_wl[5], B, tp, num_sms, st)) return rc;
     return 0;
@@ -593,7 +670,7 @@ static int simt_scan(lira_index* h, Workspace& ws, const float* d_q, long long l
     sp.k = k;
     sp.store_local = store_local;
     sp.max_rows = max_rows;
-    if (timed && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    if (timed && h->timing) { LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st)); h->scan_total_valid = false; }
     if (int rc = launch_scan(h, sp, k, st)) return rc;
     if (timed && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     return 0;
@@ -623,6 +700,119 @@ static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows o
 static constexpr int TC_SEED_ROWS_MAIN = 2048;   // seed pass on the filter's own work items: first rows of every probed list (0 = all; measured best)
 static constexpr int TC_SEED_ROWS_TC = 0;     // tensor-core seed (k <= 16): rows of each of the two best probed lists (0 = all: the pass streams
                                               // (nearly) every list once anyway, and whole lists halve the survivors of the filter pass)
+
+struct TcStage {   // one tensor-core batch after the grouping: what the seed / filter / refine launches need
+    long long Q = 0, P = 0;          // P: (upper bound of the) number of (query, list) pairs -- sizes the candidate regions
+    const long long* po = nullptr;   // probe offsets of the queries (refine)
+    int k = 0, dedup = 1;
+    const float* d_q = nullptr;
+    long long ldq = 0;
+    float* d_D = nullptr;
+    long long* d_I = nullptr;
+    int* redo_count = nullptr;       // device counter of queries left for the exact path
+    const CUtensorMap* tmap_q = nullptr;
+    float margin_c = 0.f, margin_abs = 0.f;
+    int* seed_counter = nullptr;     // zeroed ticket counters of the two passes
+    int* filter_counter = nullptr;
+};
+
+// approximate mode: |accumulator - exact| <= M(q) = margin_c sqrt(sigma^2 |q|^2) + margin_abs (units of the scaled copy):
+// operand rounding (2^-11 relative each, 5 % slack), fp32 accumulation inside the tensor core (2^-21 per term, generous),
+// fp16 subnormal flushing of tiny components, and the (hi, lo) representation of sigma^2 |v|^2
+static void tc_margins(const lira_index* h, float* margin_c, float* margin_abs) {
+    *margin_c = 0.f;
+    *margin_abs = 0.f;
+    if (h->tc_mode != 2) return;
+    const bool is_ip = h->metric == LIRA_METRIC_IP;
+    const float W = h->tc_sigma * h->tc_vmax, sd = std::sqrt((float)h->d);
+    const float per = 1.05f * 0.0009765625f + (float)h->d16 * 4.76837158e-7f;
+    *margin_c = W * ((is_ip ? 1.0f : 2.0f) * per + sd * 1.1920929e-7f);
+    *margin_abs = W * sd * 5.9604645e-8f + (is_ip ? 0.0f : W * W * 9.5367432e-7f);
+}
+
+// seed pass on the filter's own work items (ws.thr must hold +inf): see tc_search
+static int tc_seed_main(lira_index* h, Workspace& ws, const TcStage& sg, cudaStream_t st) {
+    TcParams sp;
+    sp.group_queries = ws.group_queries.as<int>();
+    sp.list_offsets = h->d_offsets;
+    sp.items = ws.items.as<ScanItem>();
+    sp.n_items = ws.n_items.as<int>();
+    sp.work_counter = sg.seed_counter;
+    sp.nk = (h->d16 + TC_KH - 1) / TC_KH;
+    sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_MAIN;
+    sp.exp = 0;
+    sp.margin_c = sg.margin_c;
+    sp.margin_abs = sg.margin_abs;
+    sp.qn_scale = h->tc_sigma * h->tc_sigma;
+    sp.qnorm = ws.qnorm.as<float>();
+    sp.thr = ws.thr.as<uint32_t>();
+    sp.cand_key = nullptr;
+    sp.cand_count = nullptr;
+    sp.cap = 0;
+    sp.trace = nullptr;
+    sp.k = sg.k;
+    sp.is_ip = h->metric == LIRA_METRIC_IP;
+    if (getenv("LIRA_TC_NO_SEED")) return 0;
+    tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+// filter on the tensor cores + refine: ws.thr holds the bounds, the queries sit in ws.gq in group order
+static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cudaStream_t st) {
+    const long long Q = sg.Q, P = sg.P;
+    const int k = sg.k;
+    const bool approx = h->tc_mode == 2;
+    // one private candidate region per (pair, column part); every valid pair's owner writes its count
+    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
+    if (int rc = ws.cand_key.ensure((size_t)P * TC_PARTS * cap * 8)) return rc;
+    if (int rc = ws.cand_count.ensure((size_t)P * TC_PARTS * 4)) return rc;
+    TcParams tp;
+    tp.group_queries = ws.group_queries.as<int>();
+    tp.list_offsets = h->d_offsets;
+    tp.items = ws.items.as<ScanItem>();
+    tp.n_items = ws.n_items.as<int>();
+    tp.work_counter = sg.filter_counter;
+    tp.nk = (h->d16 + TC_KH - 1) / TC_KH;
+    tp.max_rows = 0;
+    tp.qnorm = ws.qnorm.as<float>();
+    tp.thr = ws.thr.as<uint32_t>();
+    tp.cand_key = ws.cand_key.as<unsigned long long>();
+    tp.cand_count = ws.cand_count.as<int>();
+    tp.cap = cap;
+    tp.k = k;
+    tp.is_ip = h->metric == LIRA_METRIC_IP;
+    tp.margin_c = sg.margin_c;
+    tp.margin_abs = sg.margin_abs;
+    tp.qn_scale = h->tc_sigma * h->tc_sigma;
+    tp.trace = nullptr;
+    tp.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) : 0;
+    if (getenv("LIRA_TC_TRACE")) {   // debug: per-chunk clock stamps of CTA 0 -> CSV
+        if (int rc = ws.trace.ensure(((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8)) return rc;
+        LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, ((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8, st));
+        tp.trace = ws.trace.as<long long>();
+    }
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    LIRA_LAUNCH_CHECK();
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
+    // ---- refine ----
+    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), cap, sg.po, ws.probe_slot.as<int>(), h->ids, k,
+                    (int)Q, sg.dedup, h->metric == LIRA_METRIC_IP, sg.d_D, sg.d_I, ws.redo.as<int>(), sg.redo_count,
+                    h->vecs, (long long)h->ds, sg.d_q, sg.ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, sg.margin_c, sg.margin_abs,
+                    1.0f / (h->tc_sigma * h->tc_sigma)};
+    const int warps = 8;
+    if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    LIRA_LAUNCH_CHECK();
+    if (h->timing) { LIRA_CUDA_OK(cudaEventRecord(h->ev[5], st)); h->scan_total_valid = true; }
+    return 0;
+}
+
+static void tc_dump_trace(lira_index* h, Workspace& ws, const char* trace_path);
+static void tc_debug_stats(lira_index* h, Workspace& ws, long long Q, long long P, int n_redo);
 
 // The online query path on the tensor cores (tc_scan_kernels.cuh). *done = true when results were produced
 // for every query whose ws.redo flag is 0; *n_redo counts the queries (flag 1) whose candidate buffer
@@ -680,16 +870,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // L2: the gathered fp16 query rows carry the factor 2 of  s = 2 q.v - |v|^2  (exact: integers of <= 11 bits, doubled)
     const bool is_ip = h->metric == LIRA_METRIC_IP;
     const float qscale = (is_ip ? 1.0f : 2.0f) * h->tc_sigma;
-    // approximate mode: |accumulator - exact| <= M(q) = margin_c sqrt(sigma^2 |q|^2) + margin_abs (units of the scaled copy):
-    // operand rounding (2^-11 relative each, 5 % slack), fp32 accumulation inside the tensor core (2^-21 per term, generous),
-    // fp16 subnormal flushing of tiny components, and the (hi, lo) representation of sigma^2 |v|^2
     float margin_c = 0.f, margin_abs = 0.f;
-    if (approx) {
-        const float W = h->tc_sigma * h->tc_vmax, sd = std::sqrt((float)h->d);
-        const float per = 1.05f * 0.0009765625f + (float)h->d16 * 4.76837158e-7f;
-        margin_c = W * ((is_ip ? 1.0f : 2.0f) * per + sd * 1.1920929e-7f);
-        margin_abs = W * sd * 5.9604645e-8f + (is_ip ? 0.0f : W * W * 9.5367432e-7f);
-    }
+    tc_margins(h, &margin_c, &margin_abs);
     int* d_ok = approx ? ws.flags.as<int>() : nullptr;
     Workspace& sw = h->ws_seed;
     // ---- queries in group order (one TMA box per tile) ----
@@ -707,31 +889,11 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     if (seed_on_main) {
         fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u /* f32_to_ordered(+inf) */);
         LIRA_LAUNCH_CHECK();
-        TcParams sp;
-        sp.group_queries = ws.group_queries.as<int>();
-        sp.list_offsets = h->d_offsets;
-        sp.items = ws.items.as<ScanItem>();
-        sp.n_items = ws.n_items.as<int>();
-        sp.work_counter = ws.n_items.as<int>() + 1;
-        sp.nk = nk;
-        sp.max_rows = getenv("LIRA_TC_SEED_ROWS") ? atoi(getenv("LIRA_TC_SEED_ROWS")) : TC_SEED_ROWS_MAIN;
-        sp.exp = 0;
-        sp.margin_c = margin_c;
-        sp.margin_abs = margin_abs;
-        sp.qn_scale = h->tc_sigma * h->tc_sigma;
-        sp.qnorm = ws.qnorm.as<float>();
-        sp.thr = ws.thr.as<uint32_t>();
-        sp.cand_key = nullptr;
-        sp.cand_count = nullptr;
-        sp.cap = 0;
-        sp.trace = nullptr;
-        sp.k = k;
-        sp.is_ip = h->metric == LIRA_METRIC_IP;
-        if (!getenv("LIRA_TC_NO_SEED")) {
-            tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
-            LIRA_LAUNCH_CHECK();
-            LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.as<int>() + 1, 0, 4, st));   // the filter pass takes its tickets from 0 again
-        }
+        TcStage ss;
+        ss.k = k; ss.tmap_q = &tmap_q; ss.margin_c = margin_c; ss.margin_abs = margin_abs;
+        ss.seed_counter = ws.n_items.as<int>() + 2;   // (prepare_groups zeroes the whole control block)
+        if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));
+        if (int rc = tc_seed_main(h, ws, ss, st)) return rc;
     } else if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
@@ -805,53 +967,15 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                                                                 ws.top1.as<int>(), (int)Q, k, ws.thr.as<uint32_t>());
         LIRA_LAUNCH_CHECK();
     }
-    // ---- filter on the tensor cores ----
-    // one private candidate region per (pair, column part); every valid pair's owner writes its count
-    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
-    if (int rc = ws.cand_key.ensure((size_t)P * TC_PARTS * cap * 8)) return rc;
-    if (int rc = ws.cand_count.ensure((size_t)P * TC_PARTS * 4)) return rc;
-    TcParams tp;
-    tp.group_queries = ws.group_queries.as<int>();
-    tp.list_offsets = h->d_offsets;
-    tp.items = ws.items.as<ScanItem>();
-    tp.n_items = ws.n_items.as<int>();
-    tp.work_counter = ws.n_items.as<int>() + 1;
-    tp.nk = nk;
-    tp.max_rows = 0;
-    tp.qnorm = ws.qnorm.as<float>();
-    tp.thr = ws.thr.as<uint32_t>();
-    tp.cand_key = ws.cand_key.as<unsigned long long>();
-    tp.cand_count = ws.cand_count.as<int>();
-    tp.cap = cap;
-    tp.k = k;
-    tp.is_ip = h->metric == LIRA_METRIC_IP;
-    tp.margin_c = margin_c;
-    tp.margin_abs = margin_abs;
-    tp.qn_scale = h->tc_sigma * h->tc_sigma;
-    tp.trace = nullptr;
-    tp.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) : 0;
-    const char* trace_path = getenv("LIRA_TC_TRACE");   // debug: per-chunk clock stamps of CTA 0 -> CSV
-    if (trace_path) {
-        if (int rc = ws.trace.ensure(((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8)) return rc;
-        LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, ((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4) * 8, st));
-        tp.trace = ws.trace.as<long long>();
-    }
-    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
-    if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
-    else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
-    LIRA_LAUNCH_CHECK();
-    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
-    // ---- refine ----
-    RefineParams rp{ws.cand_key.as<unsigned long long>(), ws.cand_count.as<int>(), cap, po, ws.probe_slot.as<int>(), h->ids, k,
-                    (int)Q, dedup, h->metric == LIRA_METRIC_IP, d_D, d_I, ws.redo.as<int>(), ws.flags.as<int>() + 1,
-                    h->vecs, (long long)h->ds, d_q, ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, margin_c, margin_abs,
-                    1.0f / (h->tc_sigma * h->tc_sigma)};
-    const int warps = 8;
-    if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    LIRA_LAUNCH_CHECK();
-    int fl[4] = {1, 0, 0, 0};
+    if (!seed_on_main && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));   // (the other seeds' own grouping is not part of the scan time)
+    TcStage sg;
+    sg.Q = Q; sg.P = P; sg.po = po; sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq; sg.d_D = d_D; sg.d_I = d_I;
+    sg.redo_count = ws.flags.as<int>() + 1; sg.tmap_q = &tmap_q; sg.margin_c = margin_c; sg.margin_abs = margin_abs;
+    sg.filter_counter = ws.n_items.as<int>() + 1;
+    if (int rc = tc_filter_refine(h, ws, sg, st)) return rc;
+    const char* trace_path = getenv("LIRA_TC_TRACE");
+    if (!h->h_flags) LIRA_CUDA_OK(cudaHostAlloc((void**)&h->h_flags, 64, cudaHostAllocDefault));
+    int* fl = h->h_flags;
     LIRA_CUDA_OK(cudaMemcpyAsync(fl, ws.flags.p, 16, cudaMemcpyDeviceToHost, st));
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     LIRA_REQUIRE(fl[3] == 0, "probed list id out of range");
@@ -864,7 +988,15 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         *n_redo = 0;
         return 0;
     }
-    if (trace_path) {
+    if (trace_path) tc_dump_trace(h, ws, trace_path);
+    if (getenv("LIRA_DEBUG")) tc_debug_stats(h, ws, Q, P, *n_redo);
+    h->last_path = 1;
+    h->last_redo = *n_redo;
+    *done = true;
+    return 0;
+}
+
+static void tc_dump_trace(lira_index* h, Workspace& ws, const char* trace_path) {
         std::vector<long long> tr((size_t)TC_TRACE_ROLES * TC_TRACE_CHUNKS + TC_TRACE_CTAS * 4 + (size_t)TC_TRACE_CTAS * TC_TRACE_ITEMS * 4);
         cudaMemcpy(tr.data(), ws.trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
         if (FILE* f = fopen(trace_path, "w")) {
@@ -893,8 +1025,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                 }
             fclose(f);
         }
-    }
-    if (getenv("LIRA_DEBUG")) {
+}
+
+static void tc_debug_stats(lira_index* h, Workspace& ws, long long Q, long long P, int n_redo) {
         std::vector<uint32_t> th((size_t)Q);
         cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
         long long n_inf = 0;
@@ -907,18 +1040,41 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         long long tot = 0;
         for (int c : cc) tot += c;
         fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, part) p50 %d p99 %d max %d; redo %d\n",
-                Q, P, (double)tot / Q, sorted[P * TC_PARTS / 2], sorted[(size_t)(P * TC_PARTS * 0.99)], sorted[P * TC_PARTS - 1], *n_redo);
+                Q, P, (double)tot / Q, sorted[P * TC_PARTS / 2], sorted[(size_t)(P * TC_PARTS * 0.99)], sorted[P * TC_PARTS - 1], n_redo);
+}
+
+// exact CUDA-core path: the whole batch (done = false), or only the queries the tensor-core pass flagged in ws.redo
+static int exact_fallback(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k, int dedup,
+                          float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st, bool done) {
+    const int* mask = done ? h->ws.redo.as<int>() : nullptr;
+    if (!done) h->last_path = 0;
+    const long long* po = nullptr;
+    long long P = 0;
+    if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, done ? nullptr : d_cmp, &P, &po, st, mask, !done)) return rc;
+    if (Q == 0) return 0;
+    Workspace& ws = h->ws;
+    MergeParams mp;
+    mp.part_key = ws.part_key.as<unsigned long long>();
+    mp.probe_offsets = po;
+    mp.probe_slot = ws.probe_slot.as<int>();
+    mp.k = k;
+    mp.Q = (int)Q;
+    mp.dedup = dedup;
+    mp.out_dist = d_D;
+    mp.out_ids = d_I;
+    mp.is_ip = h->metric == LIRA_METRIC_IP;
+    mp.mask = mask;
+    if (int rc = launch_merge(mp, st)) return rc;
+    if (d_nprobe && !done) {
+        copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
+        LIRA_LAUNCH_CHECK();
     }
-    h->last_path = 1;
-    h->last_redo = *n_redo;
-    *done = true;
     return 0;
 }
 
 static int search_core(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k,
                        int dedup, float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st) {
     LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
-    long long P = 0;
     h->last_Q = Q;
     h->last_k = k;
     h->last_redo = 0;
@@ -931,34 +1087,127 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
         if (!done && retry)
             if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st)) return rc;
     }
-    if (!done || n_redo > 0) {
-        // exact CUDA-core path: the whole batch, or only the queries the tensor-core pass flagged
-        const int* mask = done ? h->ws.redo.as<int>() : nullptr;
-        if (!done) h->last_path = 0;
-        const long long* po = nullptr;
-        if (int rc = run_grouped_scan(h, d_q, ldq, Q, ps, k, /*store_local=*/0, done ? nullptr : d_cmp, &P, &po, st, mask, !done)) return rc;
-        if (Q == 0) return 0;
-        Workspace& ws = h->ws;
-        MergeParams mp;
-        mp.part_key = ws.part_key.as<unsigned long long>();
-        mp.probe_offsets = po;
-        mp.probe_slot = ws.probe_slot.as<int>();
-        mp.k = k;
-        mp.Q = (int)Q;
-        mp.dedup = dedup;
-        mp.out_dist = d_D;
-        mp.out_ids = d_I;
-        mp.is_ip = h->metric == LIRA_METRIC_IP;
-        mp.mask = mask;
-        if (int rc = launch_merge(mp, st)) return rc;
-        if (d_nprobe && !done) {
-            copy_nprobe_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.nsel.as<int>(), d_nprobe, (int)Q);
-            LIRA_LAUNCH_CHECK();
-        }
-    }
+    if (!done || n_redo > 0)
+        if (int rc = exact_fallback(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, st, done)) return rc;
     if (h->timing) {
         LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
         h->timing_pending = true;
+    }
+    return 0;
+}
+
+// The whole query phase of one batch with the front end fused (fused_probe_kernels.cuh): prep -> model forward whose last
+// layer selects -> finish_select -> scatter_queries -> seed -> filter -> refine; no host round trip before the final
+// status read. Takes the batch only when the tensor-core scan with in-kernel tightening serves it (k <= 16, >= 256
+// queries, threshold selection); *done = false (and nothing written) otherwise, or when the optimistic assumptions did
+// not hold (batch not exact in fp16, or more than nprobe_cap partitions selected for a query even after raising the cap).
+// On success ws.probe_offsets / ws.probe_ids hold the probe sets as a CSR (the exact redo of flagged queries uses it).
+static bool fused_eligible(const lira_index* h, const lira_model* m, long long Q, int mode, int k) {
+    return h->use_tc && m->use_tc && h->tc_ok && Q >= 256 && k <= TC_KMAX_TIGHTEN && mode != LIRA_SELECT_TOPN && !getenv("LIRA_NO_FUSED") &&
+           Q * (long long)std::min(h->B, h->nprobe_cap) <= (4ll << 20);
+}
+
+// Enqueues the fused flow of one batch on `st` (every launch, no host wait) and the copy of its four status words into
+// `h_flags` (pinned). The caller decides when to wait: fused_status() reads the words once the stream has passed them.
+static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long long ldq, long long Q, int mode, double value,
+                         int k, int dedup, float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st, int* h_flags) {
+    LIRA_REQUIRE(mode == LIRA_SELECT_GT || mode == LIRA_SELECT_GE_ARGMAX, "unknown selection mode");
+    LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
+    const int B = h->B;
+    const bool approx = h->tc_mode == 2;
+    Workspace& ws = h->ws;
+    const int cap = std::min(B, h->nprobe_cap);
+    const long long P = Q * (long long)cap;   // bound: sizes the per-pair buffers
+    if (int rc = model_ensure_tc(m, Q)) return rc;
+    for (DevBuf* b : {&ws.qnorm, &ws.thr, &ws.redo})
+        if (int rc = b->ensure((size_t)Q * 4)) return rc;
+    if (int rc = ws.nsel.ensure((size_t)(Q + 1) * 4)) return rc;
+    if (int rc = ws.top1.ensure((size_t)(Q + 1) * 8)) return rc;        // per-query argmax keys of the selection
+    if (int rc = ws.sel.ensure((size_t)P * 4)) return rc;
+    if (int rc = ws.probe_ids.ensure((size_t)P * 4 + 64)) return rc;
+    if (int rc = ws.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
+    if (int rc = ws.group_offsets.ensure((size_t)(B + 1) * 8)) return rc;
+    if (int rc = ws.list_count.ensure((size_t)(B + 1) * 4)) return rc;
+    if (int rc = ws.cursor.ensure((size_t)(B + 1) * 4)) return rc;
+    if (int rc = ws.n_items.ensure(128)) return rc;
+    if (int rc = ws.group_queries.ensure((size_t)P * 4)) return rc;
+    if (int rc = ws.probe_slot.ensure((size_t)P * 4)) return rc;
+    if (int rc = ws.items.ensure(((size_t)P / 8 + B + 1) * sizeof(ScanItem))) return rc;
+    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
+    // control block: [0] work items, [1] filter tickets, [2] seed tickets, +64 B {E_p, pairs}, +96 B status words:
+    // [24] batch not exact in fp16, [25] queries left for the exact path, [26] a probe set was truncated
+    LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.p, 0, 128, st));
+    int* ctl = ws.n_items.as<int>();
+    int* fl_dev = ctl + 24;
+    PrepParams pp{d_q, (long)ldq, m->d, m->ds, Q, m->mu, m->qch.as<float>(), m->qcl.as<float>(), m->qn.as<float>(),
+                  m->qrh.as<float>(), m->qrl.as<float>(), ws.qnorm.as<float>(), approx ? nullptr : fl_dev, ws.thr.as<uint32_t>(),
+                  ws.nsel.as<int>(), ws.top1.as<unsigned long long>(), ws.list_count.as<int>(), ws.cursor.as<int>(), B};
+    const int warps = 8;
+    const int qgrid = (int)((Q + warps - 1) / warps);
+    prep_queries_kernel<<<qgrid, warps * 32, 0, st>>>(pp);
+    LIRA_LAUNCH_CHECK();
+    FusedSelect fs{ws.sel.as<int>(), ws.nsel.as<int>(), ws.list_count.as<int>(), ws.top1.as<unsigned long long>(), cap,
+                   mode == LIRA_SELECT_GE_ARGMAX ? 1 : 0, (float)value};
+    if (int rc = model_forward_tc(m, d_q, ldq, Q, nullptr, 0, nullptr, 0, st, /*prepped=*/true, &fs)) return rc;
+    FinishSelectParams fp{ws.nsel.as<int>(), ws.sel.as<int>(), cap, fs.mode, ws.top1.as<unsigned long long>(), ws.list_count.as<int>(),
+                          (int)Q, B, ws.probe_offsets.as<long long>(), ws.group_offsets.as<long long>(), fl_dev + 2, h->d_list_order,
+                          h->d_offsets, TC_M, ws.items.as<ScanItem>(), ctl, (unsigned long long*)((char*)ws.n_items.p + 64)};
+    finish_select_kernel<<<1, 1024, 0, st>>>(fp);
+    LIRA_LAUNCH_CHECK();
+    if (int rc = save_stats(h, ws, st)) return rc;
+    const bool is_ip = h->metric == LIRA_METRIC_IP;
+    const float qscale = (is_ip ? 1.0f : 2.0f) * h->tc_sigma;
+    ScatterQueriesParams sc{d_q, (long)ldq, h->ds, ws.sel.as<int>(), ws.nsel.as<int>(), cap, ws.probe_offsets.as<long long>(),
+                            ws.group_offsets.as<long long>(), h->d_offsets, ws.cursor.as<int>(), ws.group_queries.as<int>(),
+                            ws.probe_slot.as<int>(), ws.probe_ids.as<int>(), ws.gq.as<__half>(), h->d16, qscale, approx ? fl_dev : nullptr,
+                            d_nprobe, d_cmp, (int)Q};
+    scatter_queries_kernel<<<qgrid, warps * 32, 0, st>>>(sc);
+    LIRA_LAUNCH_CHECK();
+    CUtensorMap tmap_q;
+    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
+    TcStage sg;
+    sg.Q = Q; sg.P = P; sg.po = ws.probe_offsets.as<long long>(); sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq;
+    sg.d_D = d_D; sg.d_I = d_I; sg.redo_count = fl_dev + 1; sg.tmap_q = &tmap_q;
+    tc_margins(h, &sg.margin_c, &sg.margin_abs);
+    sg.seed_counter = ctl + 2;
+    sg.filter_counter = ctl + 1;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));
+    if (int rc = tc_seed_main(h, ws, sg, st)) return rc;
+    if (int rc = tc_filter_refine(h, ws, sg, st)) return rc;
+    LIRA_CUDA_OK(cudaMemcpyAsync(h_flags, fl_dev, 16, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+// The whole query phase of one batch with the front end fused (fused_probe_kernels.cuh): prep -> model forward whose last
+// layer selects -> finish_select -> scatter_queries -> seed -> filter -> refine, then ONE host wait for the status words.
+// Takes the batch only when the tensor-core scan with in-kernel tightening serves it (k <= 16, >= 256 queries, threshold
+// selection); *done = false otherwise, or when the optimistic assumptions did not hold (batch not exact in fp16, or more
+// than nprobe_cap partitions selected for a query even after raising the cap: the caller's unfused flow answers).
+// On success ws.probe_offsets / ws.probe_ids hold the probe sets as a CSR (the exact redo of flagged queries uses it).
+static int fused_probe_search(lira_index* h, lira_model* m, const float* d_q, long long ldq, long long Q, int mode, double value,
+                              int k, int dedup, float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, cudaStream_t st,
+                              bool* done, int* n_redo) {
+    *done = false;
+    *n_redo = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (!fused_eligible(h, m, Q, mode, k)) return 0;
+        if (!h->h_flags) LIRA_CUDA_OK(cudaHostAlloc((void**)&h->h_flags, 64, cudaHostAllocDefault));
+        int* fl = h->h_flags;
+        if (int rc = fused_enqueue(h, m, d_q, ldq, Q, mode, value, k, dedup, d_D, d_I, d_nprobe, d_cmp, st, fl)) return rc;
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        if (getenv("LIRA_TC_TRACE")) tc_dump_trace(h, h->ws, getenv("LIRA_TC_TRACE"));
+        if (fl[0] != 0) return 0;                       // batch not exact in fp16 (or out of fp16 range): the unfused flow decides
+        if (fl[2] != 0) {                               // a query selected more than the cap: raise it, once more
+            if (h->nprobe_cap >= h->B) return 0;
+            h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4);
+            continue;
+        }
+        if (getenv("LIRA_DEBUG")) tc_debug_stats(h, h->ws, Q, Q * (long long)std::min(h->B, h->nprobe_cap), fl[1]);
+        *n_redo = fl[1];
+        h->last_path = 1;
+        h->last_redo = fl[1];
+        *done = true;
+        return 0;
     }
     return 0;
 }
@@ -968,6 +1217,9 @@ static int finish_timing(lira_index* h) {
     h->timing_pending = false;
     LIRA_CUDA_OK(cudaEventSynchronize(h->ev[3]));
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_scan_ms, h->ev[0], h->ev[1]));
+    h->last_scan_total_ms = h->last_scan_ms;
+    if (h->scan_total_valid) LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_scan_total_ms, h->ev[4], h->ev[5]));
+    h->scan_total_valid = false;
     LIRA_CUDA_OK(cudaEventElapsedTime(&h->last_total_ms, h->ev[2], h->ev[3]));
     unsigned long long stats[2] = {0, 0};
     if (h->stats.p) LIRA_CUDA_OK(cudaMemcpy(stats, h->stats.p, 16, cudaMemcpyDeviceToHost));
@@ -1238,6 +1490,19 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->vaug);
     cudaFree(h->vecs16);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (PendingBatch& pb : h->pending) { if (pb.h_flags) cudaFreeHost(pb.h_flags); if (pb.ev) cudaEventDestroy(pb.ev); }
+    for (int* p : h->flag_pool) cudaFreeHost(p);
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    for (auto& sl : h->slots) {
+        for (DevBuf* b : {&sl.q, &sl.D, &sl.I, &sl.nprobe, &sl.cmp}) b->release();
+        if (sl.pin_in) cudaFreeHost(sl.pin_in);
+        if (sl.pin_out) cudaFreeHost(sl.pin_out);
+        if (sl.pb.enqueued) { cudaFreeHost(sl.pb.h_flags); cudaEventDestroy(sl.pb.ev); }
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_done, sl.ev_out}) if (e) cudaEventDestroy(e);
+    }
+    if (h->st_in) cudaStreamDestroy(h->st_in);
+    if (h->st_out) cudaStreamDestroy(h->st_out);
     cudaFree(h->aaug);
     h->ws.release();
     h->ws_seed.release();
@@ -1281,6 +1546,15 @@ int lira_index_last_timing(const lira_index_t* hc, float* scan_ms, float* total_
     if (total_ms) *total_ms = h->last_total_ms;
     if (scan_bytes) *scan_bytes = h->last_scan_bytes;
     if (scan_pairs) *scan_pairs = h->last_scan_pairs;
+    return 0;
+}
+
+int lira_index_last_scan_total_ms(const lira_index_t* hc, float* scan_total_ms) {
+    LIRA_REQUIRE(hc && scan_total_ms, "null argument");
+    lira_index_t* h = const_cast<lira_index_t*>(hc);
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    if (int rc = finish_timing(h)) return rc;
+    *scan_total_ms = h->last_scan_total_ms;
     return 0;
 }
 
@@ -1409,6 +1683,9 @@ int lira_model_create(const float* centroids, const float* scaler_mean, const fl
     };
     do {
         if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = 2; break; }
+        if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaStreamCreate failed"); rc = 2; break; }
         if ((rc = up(&m->centroids, centroids, B, d, m->ds))) break;
         if ((rc = make_tmap(&m->tm_cent, m->centroids, B, m->ds, m->ds))) break;
         if (scaler_mean && scaler_scale) {
@@ -1481,6 +1758,9 @@ int lira_model_free(lira_model_t* m) {
     if (!m) return 0;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     cudaFree(m->centroids); cudaFree(m->mean); cudaFree(m->scale);
     for (int l = 0; l < 6; ++l) { cudaFree(m->W[l]); cudaFree(m->bias[l]); cudaFree(m->W_h[l]); cudaFree(m->W_l[l]); }
     cudaFree(m->mu); cudaFree(m->cent_h); cudaFree(m->cent_l); cudaFree(m->cn);
@@ -1568,6 +1848,28 @@ int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, in
     LIRA_REQUIRE(h->device == m->device && h->B == m->B && h->d == m->d, "index and model disagree on device / B / d");
     LIRA_CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    // fused front end (selection inside the last layer, no scores in HBM) where the tensor-core scan serves the batch
+    h->last_Q = Q;
+    h->last_k = k;
+    h->last_redo = 0;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
+    bool done = false;
+    int n_redo = 0;
+    if (int rc = fused_probe_search(h, m, d_q, ldq, Q, mode, value, k, dedup, d_D, (long long*)d_I, d_nprobe, (long long*)d_cmp, st, &done, &n_redo)) return rc;
+    if (done) {
+        if (n_redo > 0) {   // queries whose candidate regions overflowed: exact CUDA-core scan of their probe sets
+            ProbeSpec ps;
+            ps.kind = 1; ps.d_probe_offsets = h->ws.probe_offsets.as<long long>(); ps.d_probe_ids = h->ws.probe_ids.as<int>();
+            ps.P = Q * (long long)std::min(h->B, h->nprobe_cap);
+            if (int rc = exact_fallback(h, d_q, ldq, Q, ps, k, dedup, d_D, (long long*)d_I, nullptr, nullptr, st, true)) return rc;
+        }
+        if (h->timing) {
+            LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
+            h->timing_pending = true;
+        }
+        return 0;
+    }
     if (int rc = h->ws.scores.ensure((size_t)std::max<int64_t>(Q, 1) * m->Bp * 4)) return rc;
     if (int rc = model_forward(m, d_q, ldq, Q, h->ws.scores.as<float>(), m->Bp, nullptr, 0, st)) return rc;
     return lira_select_search_dev(h, h->ws.scores.as<float>(), m->Bp, d_q, ldq, Q, mode, value, k, dedup, d_D, d_I,
@@ -1613,6 +1915,187 @@ int lira_probe_search(lira_index_t* h, lira_model_t* m, const float* q, int64_t 
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     return finish_timing(h);
+}
+
+// ---- asynchronous forms: enqueue now, check later ------------------------------------------------------------------------
+namespace lira {
+static int take_flags_and_event(lira_index* h, int** fl, cudaEvent_t* ev) {
+    if (h->flag_pool.empty()) {
+        int* p = nullptr;
+        LIRA_CUDA_OK(cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault));
+        h->flag_pool.push_back(p);
+    }
+    if (h->event_pool.empty()) {
+        cudaEvent_t e;
+        LIRA_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->event_pool.push_back(e);
+    }
+    *fl = h->flag_pool.back(); h->flag_pool.pop_back();
+    *ev = h->event_pool.back(); h->event_pool.pop_back();
+    return 0;
+}
+// waits for one enqueued batch and reads its status words: *ok = false when the optimistic run is void (not exact in
+// fp16, a truncated probe set, or queries left for the exact path) and the batch has to be answered again
+static int settle(lira_index* h, PendingBatch& pb, bool* ok) {
+    *ok = true;
+    if (!pb.enqueued) return 0;
+    LIRA_CUDA_OK(cudaEventSynchronize(pb.ev));
+    const int* fl = pb.h_flags;
+    if (fl[2] != 0 && h->nprobe_cap < h->B) h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4);
+    *ok = fl[0] == 0 && fl[1] == 0 && fl[2] == 0;
+    if (*ok) { h->last_path = 1; h->last_redo = 0; }
+    h->flag_pool.push_back(pb.h_flags);
+    h->event_pool.push_back(pb.ev);
+    pb.enqueued = false;
+    return 0;
+}
+}  // namespace lira
+
+int lira_probe_search_enqueue_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q, int mode,
+                                  double value, int k, int dedup, float* d_D, int64_t* d_I, int32_t* d_nprobe, int64_t* d_cmp,
+                                  void* stream) {
+    LIRA_REQUIRE(h && m && d_q && d_D && d_I, "null argument");
+    LIRA_REQUIRE(h->device == m->device && h->B == m->B && h->d == m->d, "index and model disagree on device / B / d");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (!fused_eligible(h, m, Q, mode, k))   // nothing to defer: the synchronous call answers
+        return lira_probe_search_dev(h, m, d_q, ldq, Q, mode, value, k, dedup, d_D, d_I, d_nprobe, d_cmp, stream);
+    PendingBatch pb;
+    if (int rc = take_flags_and_event(h, &pb.h_flags, &pb.ev)) return rc;
+    pb.m = m; pb.d_q = d_q; pb.ldq = ldq; pb.Q = Q; pb.mode = mode; pb.value = value; pb.k = k; pb.dedup = dedup;
+    pb.d_D = d_D; pb.d_I = (long long*)d_I; pb.d_nprobe = d_nprobe; pb.d_cmp = (long long*)d_cmp; pb.st = st;
+    h->last_Q = Q;
+    h->last_k = k;
+    if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
+    if (int rc = fused_enqueue(h, m, d_q, ldq, Q, mode, value, k, dedup, d_D, (long long*)d_I, d_nprobe, (long long*)d_cmp, st, pb.h_flags)) return rc;
+    LIRA_CUDA_OK(cudaEventRecord(pb.ev, st));
+    if (h->timing) {
+        LIRA_CUDA_OK(cudaEventRecord(h->ev[3], st));
+        h->timing_pending = true;
+    }
+    pb.enqueued = true;
+    h->pending.push_back(pb);
+    return 0;
+}
+
+int lira_index_finish(lira_index_t* h) {
+    LIRA_REQUIRE(h, "null index");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    while (!h->pending.empty()) {
+        PendingBatch pb = h->pending.front();
+        h->pending.pop_front();
+        bool ok = true;
+        if (int rc = settle(h, pb, &ok)) return rc;
+        if (!ok)   // rare: answer the batch again through the checked path (its inputs and outputs are the caller's, still valid)
+            if (int rc = lira_probe_search_dev(h, pb.m, pb.d_q, pb.ldq, pb.Q, pb.mode, pb.value, pb.k, pb.dedup, pb.d_D, (int64_t*)pb.d_I,
+                                               pb.d_nprobe, (int64_t*)pb.d_cmp, pb.st)) return rc;
+    }
+    return 0;
+}
+
+int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, int64_t Q, int mode, double value, int k,
+                             int dedup, int slot) {
+    LIRA_REQUIRE(h && m && q && Q >= 0, "null argument");
+    LIRA_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    LIRA_REQUIRE(h->device == m->device && h->B == m->B && h->d == m->d, "index and model disagree on device / B / d");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    lira_index::HostSlot& s = h->slots[slot];
+    LIRA_REQUIRE(!s.busy, "slot still holds a batch: call lira_probe_search_wait first");
+    if (!h->st_in) {
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+    }
+    if (!s.ev_in) {
+        LIRA_CUDA_OK(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        LIRA_CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        LIRA_CUDA_OK(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    const size_t Qs = (size_t)std::max<int64_t>(Q, 1);
+    s.pb = PendingBatch();
+    s.pb.m = m; s.pb.Q = Q; s.pb.mode = mode; s.pb.value = value; s.pb.k = k; s.pb.dedup = dedup; s.pb.slot = slot;
+    s.user_q = q;
+    s.busy = true;
+    s.sync_done = false;
+    if (h->ds != h->d || Q == 0 || !fused_eligible(h, m, Q, mode, k)) return 0;   // answered synchronously in wait()
+    if (int rc = s.q.ensure(Qs * h->ds * 4)) return rc;
+    if (int rc = s.D.ensure(Qs * k * 4)) return rc;
+    if (int rc = s.I.ensure(Qs * k * 8)) return rc;
+    if (int rc = s.nprobe.ensure(Qs * 4)) return rc;
+    if (int rc = s.cmp.ensure(Qs * 8)) return rc;
+    const size_t bq = (size_t)Q * h->d * 4;
+    const size_t bD = (size_t)Q * k * 4, bI = (size_t)Q * k * 8, bC = (size_t)Q * 8, bN = (size_t)Q * 4;
+    s.oI = (bD + 255) & ~(size_t)255; s.oC = s.oI + ((bI + 255) & ~(size_t)255); s.oN = s.oC + ((bC + 255) & ~(size_t)255);
+    const size_t total = s.oN + bN;
+    if (total > s.pin_out_cap) {
+        if (s.pin_out) cudaFreeHost(s.pin_out);
+        s.pin_out = nullptr; s.pin_out_cap = 0;
+        LIRA_CUDA_OK(cudaHostAlloc(&s.pin_out, total + total / 4, cudaHostAllocDefault));
+        s.pin_out_cap = total + total / 4;
+    }
+    // queries: through a pinned staging buffer of this handle, filled by two host threads. A pageable cudaMemcpyAsync would be
+    // staged by the driver synchronously and in small pieces; and a caller's own pinned array is not necessarily the faster
+    // source either (measured on this pool: pages pinned by another allocator, possibly on the other NUMA node, upload at
+    // less than half the rate of this buffer), so LIRA_DIRECT_PINNED=1 is needed to copy straight from it
+    cudaPointerAttributes attr;
+    const bool pageable = cudaPointerGetAttributes(&attr, q) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    const void* src = q;
+    if (pageable || !getenv("LIRA_DIRECT_PINNED")) {
+        if (bq > s.pin_in_cap) {
+            if (s.pin_in) cudaFreeHost(s.pin_in);
+            s.pin_in = nullptr; s.pin_in_cap = 0;
+            LIRA_CUDA_OK(cudaHostAlloc(&s.pin_in, bq + bq / 4, cudaHostAllocDefault));
+            s.pin_in_cap = bq + bq / 4;
+        }
+        const size_t half = (bq / 2) & ~(size_t)63;
+        std::thread t2([&]() { memcpy((char*)s.pin_in + half, (const char*)q + half, bq - half); });
+        memcpy(s.pin_in, q, half);
+        t2.join();
+        src = s.pin_in;
+    }
+    LIRA_CUDA_OK(cudaMemcpyAsync(s.q.p, src, bq, cudaMemcpyHostToDevice, h->st_in));
+    LIRA_CUDA_OK(cudaEventRecord(s.ev_in, h->st_in));
+    cudaStream_t st = h->stream;
+    LIRA_CUDA_OK(cudaStreamWaitEvent(st, s.ev_in, 0));
+    if (int rc = take_flags_and_event(h, &s.pb.h_flags, &s.pb.ev)) return rc;
+    h->last_Q = Q;
+    h->last_k = k;
+    if (int rc = fused_enqueue(h, m, s.q.as<float>(), h->ds, Q, mode, value, k, dedup, s.D.as<float>(), s.I.as<long long>(), s.nprobe.as<int>(),
+                               s.cmp.as<long long>(), st, s.pb.h_flags)) return rc;
+    LIRA_CUDA_OK(cudaEventRecord(s.ev_done, st));
+    LIRA_CUDA_OK(cudaStreamWaitEvent(h->st_out, s.ev_done, 0));
+    char* sg = (char*)s.pin_out;
+    LIRA_CUDA_OK(cudaMemcpyAsync(sg, s.D.p, bD, cudaMemcpyDeviceToHost, h->st_out));
+    LIRA_CUDA_OK(cudaMemcpyAsync(sg + s.oI, s.I.p, bI, cudaMemcpyDeviceToHost, h->st_out));
+    LIRA_CUDA_OK(cudaMemcpyAsync(sg + s.oC, s.cmp.p, bC, cudaMemcpyDeviceToHost, h->st_out));
+    LIRA_CUDA_OK(cudaMemcpyAsync(sg + s.oN, s.nprobe.p, bN, cudaMemcpyDeviceToHost, h->st_out));
+    LIRA_CUDA_OK(cudaEventRecord(s.pb.ev, h->st_out));
+    s.pb.enqueued = true;
+    return 0;
+}
+
+int lira_probe_search_wait(lira_index_t* h, int slot, float* D, int64_t* I, int32_t* nprobe, int64_t* cmp) {
+    LIRA_REQUIRE(h && D && I, "null argument");
+    LIRA_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    LIRA_CUDA_OK(cudaSetDevice(h->device));
+    lira_index::HostSlot& s = h->slots[slot];
+    LIRA_REQUIRE(s.busy, "no batch was submitted to this slot");
+    s.busy = false;
+    bool ok = false;
+    if (s.pb.enqueued) {
+        if (int rc = settle(h, s.pb, &ok)) return rc;
+    }
+    const PendingBatch& pb = s.pb;
+    if (!ok)   // not eligible for the fused flow, or its optimistic run was void: the synchronous call answers
+        return lira_probe_search(h, pb.m, s.user_q, pb.Q, pb.mode, pb.value, pb.k, pb.dedup, D, I, nprobe, cmp);
+    const char* sg = (const char*)s.pin_out;
+    memcpy(D, sg, (size_t)pb.Q * pb.k * 4);
+    memcpy(I, sg + s.oI, (size_t)pb.Q * pb.k * 8);
+    if (cmp) memcpy(cmp, sg + s.oC, (size_t)pb.Q * 8);
+    if (nprobe) memcpy(nprobe, sg + s.oN, (size_t)pb.Q * 4);
+    return 0;
 }
 
 // ---- exact kNN: the base is resident behind a handle, cut into segments that play the role of lists --------

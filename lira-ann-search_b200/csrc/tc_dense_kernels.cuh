@@ -21,7 +21,7 @@
 
 namespace lira {
 
-enum { TD_EPI_FEATURE = 0, TD_EPI_BIAS_RELU = 1, TD_EPI_BIAS_SIGMOID = 2 };
+enum { TD_EPI_FEATURE = 0, TD_EPI_BIAS_RELU = 1, TD_EPI_BIAS_SIGMOID = 2, TD_EPI_SELECT = 3 };
 
 static constexpr int TD_THREADS = 320;   // warp 0 TMA, warp 1 TMEM + MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 static constexpr int TD_EPI_WARPS = 8;
@@ -40,6 +40,16 @@ struct TdParams {
     const float* v1;         // FEATURE: scaler mean [N] (may be null)
     const float* v2;         // FEATURE: scaler scale [N]
     const float* rown;       // FEATURE: |q'|^2 [M]
+    // SELECT (the last layer fused with the partition selection: the scores never leave the SM): a score that passes the
+    // threshold appends its partition to the query's probe list (slot from atomicAdd on nsel[m]) and counts in the
+    // per-partition histogram; entries past sel_cap are dropped (nsel keeps counting: the caller sees the truncation)
+    int* sel;                // [M, sel_cap] selected partitions, in arrival order
+    int* nsel;               // [M] zeroed before the launch
+    int* list_count;         // [N] zeroed before the launch
+    unsigned long long* rowbest;   // [M] zeroed: (score bits << 32 | ~partition) maximum = first argmax (sel_mode 1 only)
+    int sel_cap;
+    int sel_mode;            // 0: score > thr (LIRA_smallscale.py:206)   1: score >= thr, argmax recorded (search.cpp:448-466)
+    float sel_thr;
 };
 
 // MUFU.SQRT: max relative error 2^-22 (the reference's own two feature paths differ by more: fp64 cdist vs fp32 loop)
@@ -166,6 +176,44 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
             mbar_wait(&t_full[acc], (it >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_N;
+            if constexpr (EPI == TD_EPI_SELECT) {
+                const bool row_ok = m < p.M;
+                float best = -1.0f;
+                int best_n = 0;
+#pragma unroll 1
+                for (int g = half * 2; g < half * 2 + 2; ++g) {
+                    uint32_t r[32];
+                    tc_ld32_async(taddr + g * 32, r);
+                    tc_ld_wait(r);
+                    // pass 1 (ALU only): which of the 32 columns pass; pass 2: ONE returning atomic reserves the thread's slots in the
+                    // query's probe list (a returning atomic per hit would put a global round trip on every hit of the warp)
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const int c = g * 32 + u;
+                        const int n = n0 + c;
+                        const float v = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(r[u]) + vec_s[c])));   // same sigmoid as TD_EPI_BIAS_SIGMOID
+                        const bool ok = row_ok && n < p.N;
+                        if (p.sel_mode == 1 && ok && v > best) { best = v; best_n = n; }
+                        const bool hit = ok && (p.sel_mode == 0 ? v > p.sel_thr : v >= p.sel_thr);
+                        mask |= hit ? (1u << u) : 0u;
+                    }
+                    if (mask) {
+                        int pos = atomicAdd(p.nsel + m, __popc(mask));
+                        while (mask) {
+                            const int n = n0 + g * 32 + __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            if (pos < p.sel_cap) {
+                                p.sel[(size_t)m * p.sel_cap + pos] = n;
+                                atomicAdd(p.list_count + n, 1);
+                            }
+                            ++pos;
+                        }
+                    }
+                }
+                if (p.sel_mode == 1 && row_ok && best >= 0.0f)
+                    atomicMax(p.rowbest + m, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_n));
+            } else {
 #pragma unroll 1
             for (int g = half * 2; g < half * 2 + 2; ++g) {
                 uint32_t r[32];
@@ -209,6 +257,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
                         }
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();

@@ -178,6 +178,47 @@ class LiraIndex:
                                               npb.data_ptr(), cmp_.data_ptr(), st))
         return out
 
+    def probe_search_enqueue_dev(self, model, d_q, mode, value, k, dedup=True, out=None, stream=None):
+        """probe_search_dev without the host wait: the batch is launched and the call returns. The outputs are valid (in stream
+        order) once `finish()` has been called -- it checks the status words of every enqueued batch and answers the rare
+        batch whose optimistic run was void again."""
+        import torch
+        Q = d_q.shape[0]
+        if out is None:
+            out = (torch.empty((Q, k), dtype=torch.float32, device=d_q.device),
+                   torch.empty((Q, k), dtype=torch.int64, device=d_q.device),
+                   torch.empty((Q,), dtype=torch.int32, device=d_q.device),
+                   torch.empty((Q,), dtype=torch.int64, device=d_q.device))
+        D, I, npb, cmp_ = out
+        st = _stream_handle(d_q.device, stream)
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((d_q, out))   # the tensors must outlive the batch
+        C.check(C.lib().lira_probe_search_enqueue_dev(self._h, model._h, d_q.data_ptr(), d_q.stride(0), Q, int(mode),
+                                                      float(value), int(k), int(bool(dedup)), D.data_ptr(), I.data_ptr(),
+                                                      npb.data_ptr(), cmp_.data_ptr(), st))
+        return out
+
+    def finish(self):
+        C.check(C.lib().lira_index_finish(self._h))
+        self._inflight = []
+
+    def probe_search_submit(self, model, q, mode, value, k, dedup=True, slot=0):
+        """Host queries in, asynchronously: returns at once; `probe_search_wait(slot)` delivers the results."""
+        q = C.f32(q).reshape(-1, self.dim)
+        self._slots = getattr(self, "_slots", {})
+        self._slots[slot] = (q, q.shape[0], int(k))   # the array must stay alive until wait()
+        C.check(C.lib().lira_probe_search_submit(self._h, model._h, C.ptr(q, C.c_f32p), q.shape[0], int(mode), float(value),
+                                                 int(k), int(bool(dedup)), int(slot)))
+
+    def probe_search_wait(self, slot=0, out=None):
+        _, Q, k = self._slots.pop(slot)
+        if out is None:
+            out = (np.empty((Q, k), np.float32), np.empty((Q, k), np.int64), np.empty(Q, np.int32), np.empty(Q, np.int64))
+        D, I, npb, cmp_ = out
+        C.check(C.lib().lira_probe_search_wait(self._h, int(slot), C.ptr(D, C.c_f32p), C.ptr(I, C.c_i64p), C.ptr(npb, C.c_i32p),
+                                               C.ptr(cmp_, C.c_i64p)))
+        return out
+
     def select_search_dev(self, d_scores, d_q, mode, value, k, dedup=True, out=None, stream=None):
         import torch
         Q = d_q.shape[0]
@@ -237,8 +278,10 @@ class LiraIndex:
         nbytes, pairs = ctypes.c_int64(), ctypes.c_int64()
         C.check(C.lib().lira_index_last_timing(self._h, ctypes.byref(scan_ms), ctypes.byref(total_ms),
                                                ctypes.byref(nbytes), ctypes.byref(pairs)))
+        trio = ctypes.c_float()
+        C.check(C.lib().lira_index_last_scan_total_ms(self._h, ctypes.byref(trio)))
         return {"scan_ms": scan_ms.value, "total_ms": total_ms.value, "scan_bytes": nbytes.value,
-                "scan_pairs": pairs.value}
+                "scan_pairs": pairs.value, "scan_total_ms": trio.value}
 
 
 class ListView:

@@ -445,6 +445,97 @@ def test_select_without_round_trip_truncation_and_inexact_batches(L):
     assert_topk_equiv(a[0], a[1], D_ref, I_ref, xq_f, x_d, O.L2)
 
 
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_fused_front_end_matches_unfused_flow(L, metric, monkeypatch):
+    """lira_probe_search: the fused front end (selection inside the last layer's epilogue, scatter that writes the fp16 query
+    rows, no scores in HBM) against the unfused flow (scores -> select_kernel -> scans -> scatter -> gather) on the same
+    model: identical ids, distances, nprobe and cmp. Covers score > thr and score >= thr + argmax (with queries that select
+    nothing), a threshold that selects more than the optimistic 64 partitions per query (the cap is raised and the batch
+    runs again), and a ragged batch size."""
+    rng = np.random.RandomState(11)
+    B, d, k = 100, 64, 10
+    x_d, x_q = synth(30000, d, 777, seed=9, integer=True)
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    shapes = [(128, B), (128,), (64, 128), (64,), (128, d), (128,), (64, 128), (64,), (128, 128), (128,), (B, 128), (B,)]
+    w = [(rng.randn(*s) * (0.5 / np.sqrt(s[-1]) if len(s) == 2 else 0.1)).astype(np.float32) for s in shapes]
+    w[4] = (w[4] / 128.0).astype(np.float32)   # raw vectors are O(100): keep vector_net's activations O(1)
+    cent = x_d[rng.choice(len(x_d), B, replace=False)]
+    f = O.features_cpp(x_d[:2000], cent, None, None)
+    mean = f.mean(0).astype(np.float32)
+    scale = f.std(0).astype(np.float32)
+    model = L.LiraModel.from_arrays(cent, mean, scale, w)
+    s = model.scores(x_q)
+    lo, hi = float(np.quantile(s, 0.2)), float(np.quantile(s.max(1), 0.5))
+    for mode, value in [(L.SELECT_GT, float(np.quantile(s, 0.9))), (L.SELECT_GE_ARGMAX, hi), (L.SELECT_GT, lo), (L.SELECT_GE_ARGMAX, float(np.quantile(s, 0.95)))]:
+        monkeypatch.delenv("LIRA_NO_FUSED", raising=False)
+        a = index.probe_search(model, x_q, mode, value, k)
+        assert index.last_path == "tensor-core"
+        monkeypatch.setenv("LIRA_NO_FUSED", "1")
+        b = index.probe_search(model, x_q, mode, value, k)
+        assert index.last_path == "tensor-core"
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        # and against the oracle's scan of the same probe sets (selection replayed on the library's own scores)
+        sel = (s > np.float32(value)) if mode == L.SELECT_GT else (s >= np.float32(value))
+        if mode == L.SELECT_GE_ARGMAX:
+            none = ~sel.any(1)
+            sel[none, s[none].argmax(1)] = True
+        edge = np.abs(s - np.float32(value)) < 1e-6   # (scores are recomputed per call bit-identically; still, skip exact edges)
+        rows = ~edge.any(1)
+        poff = np.zeros(len(x_q) + 1, np.int64)
+        np.cumsum(sel.sum(1), out=poff[1:])
+        pids = np.nonzero(sel)[1].astype(np.int32)
+        I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 1)
+        assert np.array_equal(a[1][rows], I_ref[rows]) and np.array_equal(a[3][rows], cmp_ref[rows])
+        assert np.array_equal(a[2][rows], sel.sum(1)[rows])
+    monkeypatch.delenv("LIRA_NO_FUSED", raising=False)
+
+
+def test_asynchronous_forms_match_the_synchronous_call(L):
+    """lira_probe_search_enqueue_dev + lira_index_finish and lira_probe_search_submit / _wait against lira_probe_search on the
+    same batches: several batches in flight, a batch whose optimistic run is void (more than 64 partitions selected: answered
+    again by finish / wait), a real-valued batch on an integer index, and a batch too small for the fused flow."""
+    import torch
+    rng = np.random.RandomState(21)
+    B, d, k = 100, 64, 10
+    x_d, x_q = synth(30000, d, 600, seed=13, integer=True)
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(x_d, cl)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    shapes = [(128, B), (128,), (64, 128), (64,), (128, d), (128,), (64, 128), (64,), (128, 128), (128,), (B, 128), (B,)]
+    w = [(rng.randn(*s) * (0.5 / np.sqrt(s[-1]) if len(s) == 2 else 0.1)).astype(np.float32) for s in shapes]
+    w[4] = (w[4] / 128.0).astype(np.float32)
+    cent = x_d[rng.choice(len(x_d), B, replace=False)]
+    f = O.features_cpp(x_d[:2000], cent, None, None)
+    model = L.LiraModel.from_arrays(cent, f.mean(0).astype(np.float32), f.std(0).astype(np.float32), w)
+    s = model.scores(x_q)
+    thr_small, thr_big = float(np.quantile(s, 0.9)), float(np.quantile(s, 0.2))   # ~10 / ~80 partitions per query
+    batches = [(x_q, thr_small), (x_q[:300], thr_small), (x_q, thr_big), ((x_q + 0.25).astype(np.float32), thr_small), (x_q[:100], thr_small)]
+    ref = [index.probe_search(model, q, L.SELECT_GT, t, k) for q, t in batches]
+    index2 = L.LiraIndex.from_csr(x_d, off, ids, O.L2)   # fresh handle: the partition cap starts at 64 again
+    dev = torch.device("cuda:0")
+    # device form: everything enqueued, one finish
+    outs = [index2.probe_search_enqueue_dev(model, torch.as_tensor(q, device=dev), L.SELECT_GT, t, k) for q, t in batches]
+    index2.finish()
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        for x, y in zip(o, r):
+            assert np.array_equal(x.cpu().numpy(), y)
+    # host form: two slots, submit(i + 1) before wait(i)
+    index3 = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    got = []
+    index3.probe_search_submit(model, batches[0][0], L.SELECT_GT, batches[0][1], k, slot=0)
+    for i in range(len(batches)):
+        if i + 1 < len(batches):
+            index3.probe_search_submit(model, batches[i + 1][0], L.SELECT_GT, batches[i + 1][1], k, slot=(i + 1) & 1)
+        got.append(index3.probe_search_wait(slot=i & 1))
+    for o, r in zip(got, ref):
+        for x, y in zip(o, r):
+            assert np.array_equal(x, y)
+
+
 # ---------------------------------------------------------------------------------------------
 # tensor-core (tcgen05, error-compensated TF32) forward of the probing model vs the fp32 CUDA-core kernels
 # ---------------------------------------------------------------------------------------------
