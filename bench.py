@@ -838,7 +838,7 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
     res = {}
     n_rep = 3 + max(6, min(args.steps, 20))
     pipelined = hasattr(index, "probe_search_submit") and gather_merge is None
-    res["api"] = "lira_probe_search_submit / lira_probe_search_wait, two batches in flight" if pipelined else "lira_probe_search"
+    res["api"] = "lira_probe_search_submit / lira_probe_search_wait, three batches in flight" if pipelined else "lira_probe_search"
     for name, q_host in (("pinned_s", pin_q.numpy()), ("pageable_s", np.array(x_q, copy=True))):
         outs = [None, None]
         ts = []
@@ -847,14 +847,17 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
         if dist is not None:
             dist.barrier()
         if pipelined:
-            # steady state: submit(i+1) before wait(i); period = time between consecutive completed batches
+            # steady state with two batches ahead: submit(i + 2) before wait(i); the period between completed batches is timed
+            outs = [None] * 4
             index.probe_search_submit(model, q_host, L.SELECT_GT, thr, k, True, slot=0)
+            index.probe_search_submit(model, q_host, L.SELECT_GT, thr, k, True, slot=1)
             for i in range(n_rep):
                 t0 = time.perf_counter()
-                index.probe_search_submit(model, q_host, L.SELECT_GT, thr, k, True, slot=(i + 1) & 1)
-                outs[i & 1] = index.probe_search_wait(slot=i & 1, out=outs[i & 1])
+                index.probe_search_submit(model, q_host, L.SELECT_GT, thr, k, True, slot=(i + 2) & 3)
+                outs[i & 3] = index.probe_search_wait(slot=i & 3, out=outs[i & 3])
                 ts.append(time.perf_counter() - t0)
-            outs[n_rep & 1] = index.probe_search_wait(slot=n_rep & 1, out=outs[n_rep & 1])
+            for i in (n_rep, n_rep + 1):
+                outs[i & 3] = index.probe_search_wait(slot=i & 3, out=outs[i & 3])
             ids = outs[0][1]
         else:
             host_out = None

@@ -131,7 +131,7 @@ int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, in
  *                                  tensor-core flow is optimistic (fp16-exact batch, at most nprobe_cap partitions per query,
  *                                  no candidate-region overflow); a batch for which that did not hold is answered again here
  *                                  through the checked path, into the same output buffers. Results are valid after finish.
- * Host-buffer form with two staging slots: submit(slot) copies the queries in (pinned or pageable source) on a copy
+ * Host-buffer form with four staging slots (slot in [0, 4)): submit(slot) copies the queries in (pinned or pageable source) on a copy
  * stream, enqueues the batch and the copy of its results into pinned memory on a second copy stream; wait(slot) returns
  * the results in the caller's arrays. With submit(i+1) issued before wait(i), the copies of one batch overlap the
  * kernels of the other. */

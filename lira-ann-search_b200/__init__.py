@@ -10,6 +10,7 @@ from .engine import KnnIndex, LiraIndex, LiraModel, ListView, centroid_features,
 from .model_probing import MLP_2_Input, model_evaluate, model_infer, model_train
 from .query import (cpp_thresholds, get_cmp_recall, mul_partition_by_model, mul_partition_by_model_large, query_tuning,
                     query_tuning_large, recall_at_k, search_sweep)
+from .drivers import Config, LargeConfig, cal_metrics, parse_config, run_largescale, run_smallscale
 from .utils import (build_kmeans_index, compute_data_knn, create_flat_indexes, create_inner_indexes,
                     fprint, get_dist_cid, get_idle_gpu, get_knn_distr_redundancy, get_knn_labels_data_only,
                     get_scaled_dist, get_scaled_dist_data, load_data, per_query, read_xvecs, write_xvecs)

@@ -133,7 +133,7 @@ struct FinishSelectParams {
     int Q, B;
     long long* probe_offsets;       // [Q + 1]
     long long* group_offsets;       // [B + 1]
-    int* trunc_flag;                // set when a query selected more than cap partitions
+    int* trunc_flag;                // set when a query selected more than cap partitions; trunc_flag[1] <- the largest such count
     const int* list_order;          // [B] lists by size, descending
     const long long* list_offsets;  // [B + 1]
     int tile;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
     // without any selection its argmax (mode 1, search.cpp:456-466), which also enters the partition histogram
     block_exclusive_scan_1024([&](int q) {
         int n = p.nsel[q];
-        if (n > p.cap) { n = p.cap; *p.trunc_flag = 1; }
+        if (n > p.cap) { atomicMax(p.trunc_flag + 1, n); n = p.cap; *p.trunc_flag = 1; }
         if (n == 0 && p.mode == 1) {
             const int b = (int)(0xFFFFFFFFu - (uint32_t)(p.rowbest[q] & 0xFFFFFFFFull));
             p.sel[(size_t)q * p.cap] = b;

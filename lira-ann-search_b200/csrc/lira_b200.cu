@@ -173,6 +173,7 @@ struct PendingBatch {
     int* d_nprobe = nullptr;
     long long* d_cmp = nullptr;
     cudaStream_t st = nullptr;
+    int cap = 0;                   // partitions-per-query cap the batch ran with
     bool enqueued = false;         // false: the batch did not qualify for the fused flow and nothing was launched
     int slot = -1;                 // host-buffer batches (lira_probe_search_submit): staging slot
 };
@@ -201,7 +202,7 @@ struct lira_index {
         bool busy = false, sync_done = false;
         const float* user_q = nullptr;
         size_t oI = 0, oC = 0, oN = 0;
-    } slots[2];
+    } slots[4];
     cudaStream_t st_in = nullptr, st_out = nullptr;   // copy streams of the submit / wait pipeline
     std::deque<PendingBatch> pending;            // enqueued, not yet checked (oldest first)
     std::vector<int*> flag_pool;                 // free pinned status slots
@@ -1102,6 +1103,14 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
 // queries, threshold selection); *done = false (and nothing written) otherwise, or when the optimistic assumptions did
 // not hold (batch not exact in fp16, or more than nprobe_cap partitions selected for a query even after raising the cap).
 // On success ws.probe_offsets / ws.probe_ids hold the probe sets as a CSR (the exact redo of flagged queries uses it).
+// a batch that ran with `ran_with` partitions per query at most saw a query selecting `seen_max`: the next ones get room for it
+// (several truncated batches may be in flight: only the first to be checked moves the cap)
+static void raise_nprobe_cap(lira_index* h, int ran_with, int seen_max) {
+    if (ran_with < h->nprobe_cap) return;
+    const int want = std::max(ran_with + 32, (seen_max + 31) / 32 * 32);
+    h->nprobe_cap = std::min(h->B, want);
+}
+
 static bool fused_eligible(const lira_index* h, const lira_model* m, long long Q, int mode, int k) {
     return h->use_tc && m->use_tc && h->tc_ok && Q >= 256 && k <= TC_KMAX_TIGHTEN && mode != LIRA_SELECT_TOPN && !getenv("LIRA_NO_FUSED") &&
            Q * (long long)std::min(h->B, h->nprobe_cap) <= (4ll << 20);
@@ -1135,7 +1144,7 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     if (int rc = ws.items.ensure(((size_t)P / 8 + B + 1) * sizeof(ScanItem))) return rc;
     if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
     // control block: [0] work items, [1] filter tickets, [2] seed tickets, +64 B {E_p, pairs}, +96 B status words:
-    // [24] batch not exact in fp16, [25] queries left for the exact path, [26] a probe set was truncated
+    // [24] batch not exact in fp16, [25] queries left for the exact path, [26] a probe set was truncated, [27] largest selection of a query
     LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.p, 0, 128, st));
     int* ctl = ws.n_items.as<int>();
     int* fl_dev = ctl + 24;
@@ -1199,7 +1208,7 @@ static int fused_probe_search(lira_index* h, lira_model* m, const float* d_q, lo
         if (fl[0] != 0) return 0;                       // batch not exact in fp16 (or out of fp16 range): the unfused flow decides
         if (fl[2] != 0) {                               // a query selected more than the cap: raise it, once more
             if (h->nprobe_cap >= h->B) return 0;
-            h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4);
+            raise_nprobe_cap(h, h->nprobe_cap, fl[3]);
             continue;
         }
         if (getenv("LIRA_DEBUG")) tc_debug_stats(h, h->ws, Q, Q * (long long)std::min(h->B, h->nprobe_cap), fl[1]);
@@ -1941,7 +1950,7 @@ static int settle(lira_index* h, PendingBatch& pb, bool* ok) {
     if (!pb.enqueued) return 0;
     LIRA_CUDA_OK(cudaEventSynchronize(pb.ev));
     const int* fl = pb.h_flags;
-    if (fl[2] != 0 && h->nprobe_cap < h->B) h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4);
+    if (fl[2] != 0) raise_nprobe_cap(h, pb.cap, fl[3]);
     *ok = fl[0] == 0 && fl[1] == 0 && fl[2] == 0;
     if (*ok) { h->last_path = 1; h->last_redo = 0; }
     h->flag_pool.push_back(pb.h_flags);
@@ -1965,6 +1974,7 @@ int lira_probe_search_enqueue_dev(lira_index_t* h, lira_model_t* m, const float*
     if (int rc = take_flags_and_event(h, &pb.h_flags, &pb.ev)) return rc;
     pb.m = m; pb.d_q = d_q; pb.ldq = ldq; pb.Q = Q; pb.mode = mode; pb.value = value; pb.k = k; pb.dedup = dedup;
     pb.d_D = d_D; pb.d_I = (long long*)d_I; pb.d_nprobe = d_nprobe; pb.d_cmp = (long long*)d_cmp; pb.st = st;
+    pb.cap = std::min(h->B, h->nprobe_cap);
     h->last_Q = Q;
     h->last_k = k;
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[2], st));
@@ -1997,7 +2007,7 @@ int lira_index_finish(lira_index_t* h) {
 int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, int64_t Q, int mode, double value, int k,
                              int dedup, int slot) {
     LIRA_REQUIRE(h && m && q && Q >= 0, "null argument");
-    LIRA_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    LIRA_REQUIRE(slot >= 0 && slot < 4, "slot must be in [0, 4)");
     LIRA_REQUIRE(h->device == m->device && h->B == m->B && h->d == m->d, "index and model disagree on device / B / d");
     LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
     LIRA_CUDA_OK(cudaSetDevice(h->device));
@@ -2015,6 +2025,7 @@ int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, i
     const size_t Qs = (size_t)std::max<int64_t>(Q, 1);
     s.pb = PendingBatch();
     s.pb.m = m; s.pb.Q = Q; s.pb.mode = mode; s.pb.value = value; s.pb.k = k; s.pb.dedup = dedup; s.pb.slot = slot;
+    s.pb.cap = std::min(h->B, h->nprobe_cap);
     s.user_q = q;
     s.busy = true;
     s.sync_done = false;
@@ -2034,7 +2045,7 @@ int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, i
         LIRA_CUDA_OK(cudaHostAlloc(&s.pin_out, total + total / 4, cudaHostAllocDefault));
         s.pin_out_cap = total + total / 4;
     }
-    // queries: through a pinned staging buffer of this handle, filled by two host threads. A pageable cudaMemcpyAsync would be
+    // queries: through a pinned staging buffer of this handle. A pageable cudaMemcpyAsync would be
     // staged by the driver synchronously and in small pieces; and a caller's own pinned array is not necessarily the faster
     // source either (measured on this pool: pages pinned by another allocator, possibly on the other NUMA node, upload at
     // less than half the rate of this buffer), so LIRA_DIRECT_PINNED=1 is needed to copy straight from it
@@ -2049,10 +2060,7 @@ int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, i
             LIRA_CUDA_OK(cudaHostAlloc(&s.pin_in, bq + bq / 4, cudaHostAllocDefault));
             s.pin_in_cap = bq + bq / 4;
         }
-        const size_t half = (bq / 2) & ~(size_t)63;
-        std::thread t2([&]() { memcpy((char*)s.pin_in + half, (const char*)q + half, bq - half); });
-        memcpy(s.pin_in, q, half);
-        t2.join();
+        memcpy(s.pin_in, q, bq);
         src = s.pin_in;
     }
     LIRA_CUDA_OK(cudaMemcpyAsync(s.q.p, src, bq, cudaMemcpyHostToDevice, h->st_in));
@@ -2078,7 +2086,7 @@ int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, i
 
 int lira_probe_search_wait(lira_index_t* h, int slot, float* D, int64_t* I, int32_t* nprobe, int64_t* cmp) {
     LIRA_REQUIRE(h && D && I, "null argument");
-    LIRA_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    LIRA_REQUIRE(slot >= 0 && slot < 4, "slot must be in [0, 4)");
     LIRA_CUDA_OK(cudaSetDevice(h->device));
     lira_index::HostSlot& s = h->slots[slot];
     LIRA_REQUIRE(s.busy, "no batch was submitted to this slot");

@@ -100,7 +100,7 @@ def _fit_scaler(x_d, kmeans, n_bkt, device, batch=65536):
     return _Scaler(mean, scale)
 
 
-def get_scaled_dist(x_d, x_q, kmeans, n_bkt, cfg, device=0, return_data=True):
+def get_scaled_dist(x_d, x_q, kmeans, n_bkt, cfg=None, device=0, return_data=True):
     """-> (distances_data_scaled [n_d,B] f32, distances_query_scaled [n_q,B] f32); side effect: writes
     {pth_log}/{file_name}_scaler_mean.npy / _scaler_scale.npy (utils.py:120-180).
     return_data=False skips materialising the n_d x B matrix (query phase only)."""
@@ -108,9 +108,10 @@ def get_scaled_dist(x_d, x_q, kmeans, n_bkt, cfg, device=0, return_data=True):
     mean32, scale32 = scaler.mean_.astype(np.float32), scaler.scale_.astype(np.float32)
     q_scaled = engine.centroid_features(x_q, kmeans.centroids, mean32, scale32, device)
     d_scaled = engine.centroid_features(x_d, kmeans.centroids, mean32, scale32, device) if return_data else None
-    os.makedirs(cfg.pth_log, exist_ok=True)
-    np.save(os.path.join(cfg.pth_log, f"{cfg.file_name}_scaler_mean.npy"), mean32)
-    np.save(os.path.join(cfg.pth_log, f"{cfg.file_name}_scaler_scale.npy"), scale32)
+    if cfg is not None:   # (LIRA_largescale.py:258 calls without cfg, which the reference's signature does not allow)
+        os.makedirs(cfg.pth_log, exist_ok=True)
+        np.save(os.path.join(cfg.pth_log, f"{cfg.file_name}_scaler_mean.npy"), mean32)
+        np.save(os.path.join(cfg.pth_log, f"{cfg.file_name}_scaler_scale.npy"), scale32)
     return d_scaled, q_scaled
 
 
@@ -167,6 +168,12 @@ class Kmeans:
         self.d, self.k, self.niter, self.verbose, self.seed, self.device = d, k, niter, verbose, seed, device
         self.centroids = None
 
+    @property
+    def index(self):
+        """faiss.Kmeans.index: a flat L2 index over the centroids; `.search(x, 1)` is the partition assignment the
+        reference uses (utils.py:325, LIRA_largescale.py:294). Exact kNN on the GPU (engine.KnnIndex)."""
+        return _CentroidIndex(self)
+
     @staticmethod
     def assign(x_t, c_t, chunk=262144):
         import torch
@@ -197,6 +204,27 @@ class Kmeans:
                 c[~nz] = x_t[idx]
         self.centroids = c.cpu().numpy()
         return self
+
+
+class _CentroidIndex:
+    def __init__(self, km):
+        self.km = km
+
+    @property
+    def ntotal(self):
+        return len(self.km.centroids)
+
+    def search(self, x, k):
+        dev = self.km.device
+        dev_i = int(str(dev).split(":")[1]) if ":" in str(dev) else 0
+        x = np.ascontiguousarray(x, np.float32)
+        idx = engine.KnnIndex(np.ascontiguousarray(self.km.centroids, np.float32), "L2", dev_i)
+        D = np.empty((len(x), k), np.float32)
+        I = np.empty((len(x), k), np.int64)
+        for a in range(0, len(x), 1 << 20):
+            D[a:a + (1 << 20)], I[a:a + (1 << 20)] = idx.search(x[a:a + (1 << 20)], k)
+        idx.close()
+        return D, I
 
 
 def build_kmeans_index(x_data, n_bkt, device="cuda:0"):

@@ -164,3 +164,37 @@ def test_threshold_is_compared_in_fp32():
     assert pids.tolist() == [1]
     poff, pids = O.select(s, O.SELECT_GE_ARGMAX, 0.1)
     assert pids.tolist() == [0, 1]
+
+
+def test_cal_metrics_and_configs_match_the_reference(golden):
+    """drivers.cal_metrics against the metrics table the reference's own cal_metrics (LIRA_smallscale.py:99-143) produced in
+    the large-scale golden run, and the Config name / argv conventions of both drivers."""
+    import torch
+    import lira_ann_search_b200 as L
+    z = golden("toy_large")
+    B, k = int(z["n_bkt"]), int(z["k"])
+    xs = z["x_d"][z["sub_idx"]]
+    d2 = ((xs[:, None, :].astype(np.float64) - z["centroids"][None].astype(np.float64)) ** 2).sum(-1)
+    d2b_sub = np.full((len(xs), 2), -1)
+    d2b_sub[:, 0] = d2.argmin(1)
+
+    class C:
+        n_bkt = B
+    _, ids_q = L.get_knn_distr_redundancy(z["knn_query_sub"], d2b_sub, C)
+    df = L.cal_metrics(torch.as_tensor(z["all_predicts"]), torch.as_tensor(z["all_targets"]), 7, ids_q, None, None,
+                       float(z["loss_test"]), knn=k)
+    assert list(df.columns) == ["Epoch", "Accuracy", "Hit Rate", "nprobe predict", "nprobe target", "KNN Recall", "KNN Computations", "Loss"]
+    ref = z["metrics"][-1]
+    assert np.allclose(df.to_numpy(np.float64)[0, 1:], ref[1:], atol=2e-4)
+    df2 = L.cal_metrics(torch.as_tensor(z["all_predicts"]), torch.as_tensor(z["all_targets"]), 8, ids_q, None, df, 0.5, knn=k)
+    assert len(df2) == 2 and list(df2.columns) == list(df.columns)
+    # Config conventions (LIRA_smallscale.py:44-75)
+    c = L.parse_config(L.Config, ["--dataset", "sift", "--n_bkt", "1024", "--k", "10", "--dis_metric", "dot"])
+    assert c.dis_metric == "inner_product" and c.pth_log == "./logs/sift/ML_kmeans_RE_FLAT/"
+    assert c.file_name == "sift-k=10-ML_kmeans=1024_FLAT_Metric=inner_product_ReType=model_ReRatio=0.03"
+    assert c.df_name == c.file_name + ".csv" and c.log_name == c.file_name + ".txt"
+    with pytest.raises(ValueError):
+        L.parse_config(L.Config, ["--n_bkt", "64", "--k", "10"])
+    cl = L.parse_config(L.LargeConfig, [])
+    assert cl.dis_metric == "L2" and cl.k == 100 and cl.n_bkt == 1024 and cl.batch_size == 512 and cl.n_epoch == 30
+    assert cl.file_name == "deep50M-k=100-ML_kmeans=1024_FLAT_ReType=model"
