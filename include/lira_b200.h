@@ -171,6 +171,45 @@ int lira_knn_set_use_tensor_cores(lira_knn_t* h, int enable);
 int lira_knn_last_path(const lira_knn_t* h); /* last search: 0 CUDA cores, 1 tensor cores, 2 some batches on each */
 int lira_knn_last_redo(const lira_knn_t* h); /* queries of the last search answered again by the exact CUDA-core scan */
 
+/* ---- a12: IVF-approximate self-kNN (compute_knn.cpp:158-203) ------------------------------------------------------
+ * faiss::IndexIVFFlat(quantizer = IndexFlatL2(d), d, nlist): train (K-Means, lira_kmeans_train), add (every vector to the list
+ * of its nearest centroid), search with `nprobe`: the k best of each base vector inside its nprobe nearest lists, exact
+ * distances, best first (-1 padded). D[N,k], I[N,k] host. The caller drops column 0 (the vector itself) as
+ * compute_knn.cpp:254-259 does. */
+int lira_knn_ivf(const float* base, int64_t N, int d, int k, int nlist, int nprobe, uint64_t seed, int device, float* D,
+                 int64_t* I);
+
+/* ---- f2 / f3: index build (the callers in front of the query path) ----------------------------------------------
+ * faiss.Kmeans(d, B, niter=20).train(x) as build_kmeans_index uses it (utils.py:321-324): at most 256 points per centroid
+ * take part (random subset, `seed`), centroids start from B random points (or init_centroids[B,d] when given), `niter` Lloyd
+ * iterations, an empty cluster is re-seeded by splitting the largest one. Assignment = exact nearest centroid on the kNN path
+ * (ties to the lower id), update = segmented mean on the device. centroids_out[B,d] host. The assignment of the full data
+ * (kmeans.index.search(x, 1): utils.py:325, LIRA_largescale.py:294) is lira_knn_* with the centroid table as base, k = 1.
+ * _dev: rows d_x[n, ld] on the device (ld % 4 == 0, padding zero); d_centroids[B, ldc] is the result and, with init_given,
+ * the start; otherwise d_init_rows[B] (int64) names the rows of d_x the centroids start from. */
+int lira_kmeans_train(const float* x, int64_t n, int d, int B, int niter, uint64_t seed, const float* init_centroids,
+                      int device, float* centroids_out);
+int lira_kmeans_train_dev(const float* d_x, int64_t ld, int64_t n, int d, int B, int niter, int init_given,
+                          float* d_centroids, int64_t ldc, const int64_t* d_init_rows, int device, void* stream);
+/* get_dist_cid (+ StandardScaler.transform) with everything on the device: d_out[Q, ldo] (ldo % 4 == 0). */
+int lira_centroid_features_dev(const float* d_q, int64_t ldq, int64_t Q, const float* d_centroids, int64_t ldc, int B,
+                               int d, const float* d_mean, const float* d_scale, float* d_out, int64_t ldo, int device,
+                               void* stream);
+/* StandardScaler.fit / partial_fit on the centroid distances of n rows (utils.py:133-168, and per 1 000 000-row batch in
+ * get_scaled_dist_data, utils.py:182-215): fp64 mean and variance per partition; the [n, B] matrix never leaves the device.
+ * mean_out[B], var_out[B] host. Waits for the stream. */
+int lira_feature_stats_dev(const float* d_x, int64_t ld, int64_t n, const float* d_centroids, int64_t ldc, int B, int d,
+                           double* mean_out, double* var_out, int device, void* stream);
+/* mul_partition_by_model (LIRA_smallscale.py:77-97, LIRA_largescale.py:51-72), one warp per point: row i of d_score[n_rows,
+ * lds] (the probing model's outputs) belongs to point d_points[i] (NULL: first + i). With the partitions ranked by score
+ * (equal scores: lower id first), n_eff = #(score > sigma), n_act = min(n_mul - 1, n_eff) and loc = the rank of the point's
+ * current partition d_data_2_bkt[t, 0]:  loc >= n_act -> the n_act best go to columns 1..n_act;  else n_eff == n_act -> they
+ * replace columns 0..n_act-1;  else the n_act + 1 best replace columns 0..n_act. d_data_2_bkt[N, n_mul] int32 is updated in
+ * place; d_added[N, n_mul] (caller presets -1) receives the partitions that newly hold the point, for the caller's
+ * cluster_ids / cluster_cnts bookkeeping. 2 <= n_mul <= 8. */
+int lira_mul_partition_dev(const float* d_score, int64_t lds, int64_t n_rows, int B, float sigma, const int64_t* d_points,
+                           int64_t first, int n_mul, int32_t* d_data_2_bkt, int32_t* d_added, int device, void* stream);
+
 /* ---- multi-GPU merge (e): per-rank top-k lists -> global top-k with id de-duplication ----
  * d_keys_in[R, Q, k]: rank-major gathered (score,id) lists as produced by lira_*_topk_keys_dev /
  * lira_pack_keys_dev; output as lira_search. */

@@ -62,6 +62,12 @@ SIGNATURES = {
     "lira_knn_set_use_tensor_cores": (c_int, [c_vp, c_int]),
     "lira_knn_last_path": (c_int, [c_vp]),
     "lira_knn_last_redo": (c_int, [c_vp]),
+    "lira_knn_ivf": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_int, c_f32p, c_i64p]),
+    "lira_kmeans_train": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, ctypes.c_uint64, c_f32p, c_int, c_f32p]),
+    "lira_kmeans_train_dev": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_int, c_vp]),
+    "lira_centroid_features_dev": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "lira_feature_stats_dev": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), c_int, c_vp]),
+    "lira_mul_partition_dev": (c_int, [c_vp, c_i64, c_i64, c_int, ctypes.c_float, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
     "lira_pack_keys_dev": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
     "lira_merge_ranks_dev": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "lira_launch_count": (c_i64, []),

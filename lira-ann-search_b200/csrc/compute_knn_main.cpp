@@ -7,9 +7,11 @@
 // reads  {data_path}/{dataset}/{dataset}_base.fvecs (or .bvecs)
 // writes {data_path}/{dataset}/knn_cache/{dataset}-data_self_knn{k}-n{n}.bin   (raw int32 [n, k]) and .bin.meta
 //
-// The reference's IVF branch (nprobe != 0) trades accuracy for CPU time; the GPU search is exact at any size, so
-// every nprobe value produces the exact result (method: flat_exact, no _ivf_nprobe suffix). n_threads is accepted
-// and ignored.
+// nprobe as in the reference (compute_knn.cpp:103, 150-203): 0 = exact brute force (lira_knn); any other value = the IVF
+// approximation (lira_knn_ivf: K-Means with the reference's nlist rule, every vector searched in its nprobe nearest lists;
+// negative or absent = the reference's automatic nprobe) and the `_ivf_nprobe{p}` suffix utils.compute_data_knn looks for
+// first (utils.py:245-266). On a B200 the exact search is affordable at any size the reference targets, so `0` is the
+// recommended value. n_threads is accepted and ignored.
 //
 // Not in the reference (opt-in):  compute_knn <dataset> <data_path> <k> --queries
 //   exact ground truth of the QUERY set against the base: reads {dataset}_query.fvecs (or .bvecs) and writes
@@ -17,7 +19,9 @@
 //   utils.load_data (utils.py:54-76) and search.cpp:341-343 read. The reference ships it with the datasets.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -69,13 +73,14 @@ bool exists(const std::string& p) {
 int main(int argc, char** argv) {
     if (argc < 4) {
         std::cout << "Usage: " << argv[0] << " <dataset> <data_path> <k> [nprobe] [n_threads]   |   <dataset> <data_path> <k> --queries" << std::endl;
-        std::cout << "  exact brute-force self-kNN on the GPU (any nprobe gives the exact result)" << std::endl;
+        std::cout << "  nprobe: 0 = exact search on the GPU (recommended), > 0 = IVF approximation, absent / negative = automatic" << std::endl;
         return 1;
     }
     const std::string dataset = argv[1], data_path = argv[2];
     const int k = std::atoi(argv[3]);
     bool query_mode = false;
     for (int a = 4; a < argc; ++a) query_mode |= std::string(argv[a]) == "--queries";
+    const int nprobe_arg = (argc > 4 && !query_mode) ? std::atoi(argv[4]) : -1;   // -1: automatic (compute_knn.cpp:103)
     if (k < 1 || k > (query_mode ? 128 : 127)) { std::cerr << "Error: k must be in [1, " << (query_mode ? 128 : 127) << "]" << std::endl; return 1; }
 
     std::cout << "=== GPU KNN Computation (liblira_b200) ===" << std::endl;
@@ -146,10 +151,28 @@ int main(int argc, char** argv) {
     // k + 1 neighbours of every base vector, column 0 (the vector itself) dropped: compute_knn.cpp:237, 254-259
     std::vector<float> D((size_t)n * (k + 1));
     std::vector<int64_t> I((size_t)n * (k + 1));
+    const bool approximate = nprobe_arg != 0;
+    int n_list = 0, actual_nprobe = 0;
     const double t1 = now_s();
-    if (lira_knn(data.data(), n, data.data(), n, dim, k + 1, LIRA_METRIC_L2, 0, D.data(), I.data()) != 0) {
-        std::cerr << "Error: " << lira_last_error() << std::endl;
-        return 1;
+    if (approximate) {
+        // compute_knn.cpp:160-168 (number of lists) and :190-199 (automatic nprobe)
+        const int root = (int)std::sqrt((double)n);
+        n_list = std::max(1, n < 50000 ? std::min(root, 256) : n < 1000000 ? std::min(root, 1024) : std::min(root, 4096));
+        if (nprobe_arg < 0) actual_nprobe = n < 100000 ? std::min(std::max(n_list / 4, 16), 64) : std::min(std::max(n_list / 8, 32), 128);
+        else actual_nprobe = nprobe_arg;
+        std::cout << "Using IVF index with " << n_list << " clusters" << std::endl;
+        std::cout << "Set nprobe = " << actual_nprobe << " (out of " << n_list << " clusters)" << std::endl;
+        std::cout << "Method: Approximate IVF search" << std::endl;
+        if (lira_knn_ivf(data.data(), n, dim, k + 1, n_list, actual_nprobe, 1234, 0, D.data(), I.data()) != 0) {
+            std::cerr << "Error: " << lira_last_error() << std::endl;
+            return 1;
+        }
+    } else {
+        std::cout << "Method: Exact FLAT search" << std::endl;
+        if (lira_knn(data.data(), n, data.data(), n, dim, k + 1, LIRA_METRIC_L2, 0, D.data(), I.data()) != 0) {
+            std::cerr << "Error: " << lira_last_error() << std::endl;
+            return 1;
+        }
     }
     const double search_time = now_s() - t1;
     std::cout << "Search time: " << search_time << "s" << std::endl;
@@ -160,7 +183,8 @@ int main(int argc, char** argv) {
 
     const std::string cache_dir = dir + "/knn_cache";
     mkdir(cache_dir.c_str(), 0755);
-    const std::string out = cache_dir + "/" + dataset + "-data_self_knn" + std::to_string(k) + "-n" + std::to_string(n) + ".bin";
+    const std::string suffix = approximate ? ("_ivf_nprobe" + std::to_string(actual_nprobe)) : "";
+    const std::string out = cache_dir + "/" + dataset + "-data_self_knn" + std::to_string(k) + "-n" + std::to_string(n) + suffix + ".bin";
     {
         std::ofstream f(out, std::ios::binary);
         if (!f) { std::cerr << "Error: Cannot write " << out << std::endl; return 1; }
@@ -172,7 +196,12 @@ int main(int argc, char** argv) {
         meta << "n: " << n << std::endl;
         meta << "dim: " << dim << std::endl;
         meta << "k: " << k << std::endl;
-        meta << "method: flat_exact" << std::endl;
+        meta << "method: " << (approximate ? "ivf_approximate" : "flat_exact") << std::endl;
+        if (approximate) {
+            meta << "n_clusters: " << n_list << std::endl;
+            meta << "nprobe: " << actual_nprobe << std::endl;
+            meta << "probe_ratio: " << (100.0 * actual_nprobe / n_list) << "%" << std::endl;
+        }
         meta << "read_time: " << read_time << "s" << std::endl;
         meta << "build_time: " << 0.0 << "s" << std::endl;
         meta << "search_time: " << search_time << "s" << std::endl;

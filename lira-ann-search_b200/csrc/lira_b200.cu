@@ -13,12 +13,14 @@
 #include <thread>
 #include <mutex>
 #include <numeric>
+#include <random>
 #include <vector>
 
 #include "probe_kernels.cuh"
 #include "tc_scan_kernels.cuh"
 #include "tc_dense_kernels.cuh"
 #include "fused_probe_kernels.cuh"
+#include "build_kernels.cuh"
 
 namespace lira {
 
@@ -2288,6 +2290,290 @@ int lira_knn(const float* base, int64_t N, const float* query, int64_t Q, int d,
     if (int rc = lira_knn_create(base, N, d, metric, device, &kn)) return rc;
     const int rc = lira_knn_search(kn, query, Q, k, D, I);
     lira_knn_free(kn);
+    return rc;
+}
+
+// ---- build side: K-Means, scaler statistics, redundancy rule --------------------------------------------------
+int lira_kmeans_train_dev(const float* d_x, int64_t ld, int64_t n, int d, int B, int niter, int init_given, float* d_centroids,
+                          int64_t ldc, const int64_t* d_init_rows, int device, void* stream) {
+    LIRA_REQUIRE(d_x && d_centroids && n >= 1 && d >= 1 && B >= 1 && niter >= 0, "bad argument");
+    LIRA_REQUIRE(n >= B, "K-Means needs at least as many points as centroids");
+    LIRA_REQUIRE(ld >= d && (ld % 4) == 0 && ((uintptr_t)d_x & 15) == 0, "device rows need ld % 4 == 0 and 16-byte alignment");
+    LIRA_REQUIRE(ldc >= d && (ldc % 4) == 0 && ((uintptr_t)d_centroids & 15) == 0, "device centroids need ld % 4 == 0 and 16-byte alignment");
+    LIRA_REQUIRE(init_given || d_init_rows, "initial centroids or the rows to take them from are needed");
+    if (int rc = check_device(device)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf sums, counts, assign, dist;
+    const int lds = round_up(d, 4);
+    int rc = 0;
+    auto body = [&]() -> int {
+        if (int r = sums.ensure((size_t)B * lds * 4)) return r;
+        if (int r = counts.ensure((size_t)B * 4)) return r;
+        if (int r = assign.ensure((size_t)n * 8)) return r;
+        if (int r = dist.ensure((size_t)n * 4)) return r;
+        if (!init_given) {   // centroids = the given rows of x (faiss: k points of a random permutation)
+            LIRA_CUDA_OK(cudaMemsetAsync(d_centroids, 0, (size_t)B * ldc * 4, st));
+            gather_rows64_kernel<<<grid_for((long long)B * (ldc / 4), 256), 256, 0, st>>>(d_x, ld, d, (const long long*)d_init_rows, B, d_centroids, (int)ldc);
+            LIRA_LAUNCH_CHECK();
+        }
+        std::vector<int> h_counts(B);
+        std::vector<float> h_cent;
+        for (int it = 0; it < niter; ++it) {
+            // assignment: exact nearest centroid (ties to the lower id), the kNN path with the centroid table as base
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+            lira_knn_t* kn = nullptr;
+            if (int r = lira_knn_create_dev(d_centroids, ldc, B, d, LIRA_METRIC_L2, device, &kn)) return r;
+            int r = lira_knn_search_dev(kn, d_x, ld, n, 1, dist.as<float>(), (int64_t*)assign.p, st);
+            if (!r && cudaStreamSynchronize(st) != cudaSuccess) { set_error("K-Means assignment failed"); r = 2; }
+            lira_knn_free(kn);
+            if (r) return r;
+            // update: segmented mean
+            LIRA_CUDA_OK(cudaMemsetAsync(sums.p, 0, (size_t)B * lds * 4, st));
+            LIRA_CUDA_OK(cudaMemsetAsync(counts.p, 0, (size_t)B * 4, st));
+            kmeans_accumulate_kernel<<<(int)((n + 7) / 8), 256, 0, st>>>(d_x, ld, d, n, assign.as<long long>(), sums.as<float>(), lds, counts.as<int>());
+            LIRA_LAUNCH_CHECK();
+            kmeans_finalize_kernel<<<grid_for((long long)B * d, 256), 256, 0, st>>>(sums.as<float>(), lds, counts.as<int>(), B, d, d_centroids, ldc);
+            LIRA_LAUNCH_CHECK();
+            LIRA_CUDA_OK(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+            // empty clusters: split the currently largest one (faiss clustering: both halves get the centroid, perturbed by
+            // +-1/1024 in alternating dimensions, and the donor's count is halved)
+            bool any_empty = false;
+            for (int b = 0; b < B; ++b) any_empty |= h_counts[b] == 0;
+            if (any_empty) {
+                h_cent.resize((size_t)B * ldc);
+                LIRA_CUDA_OK(cudaMemcpy(h_cent.data(), d_centroids, (size_t)B * ldc * 4, cudaMemcpyDeviceToHost));
+                for (int b = 0; b < B; ++b) {
+                    if (h_counts[b] != 0) continue;
+                    const int donor = (int)(std::max_element(h_counts.begin(), h_counts.end()) - h_counts.begin());
+                    if (h_counts[donor] < 2) break;
+                    const float eps = 1.0f / 1024.0f;
+                    for (int j = 0; j < d; ++j) {
+                        const float c = h_cent[(size_t)donor * ldc + j];
+                        h_cent[(size_t)b * ldc + j] = c * ((j & 1) ? 1.0f - eps : 1.0f + eps);
+                        h_cent[(size_t)donor * ldc + j] = c * ((j & 1) ? 1.0f + eps : 1.0f - eps);
+                    }
+                    h_counts[b] = h_counts[donor] / 2;
+                    h_counts[donor] -= h_counts[b];
+                }
+                LIRA_CUDA_OK(cudaMemcpy(d_centroids, h_cent.data(), (size_t)B * ldc * 4, cudaMemcpyHostToDevice));
+            }
+        }
+        return 0;
+    };
+    rc = body();
+    cudaStreamSynchronize(st);
+    for (DevBuf* b : {&sums, &counts, &assign, &dist}) b->release();
+    return rc;
+}
+
+int lira_kmeans_train(const float* x, int64_t n, int d, int B, int niter, uint64_t seed, const float* init_centroids, int device,
+                      float* centroids_out) {
+    LIRA_REQUIRE(x && centroids_out && n >= 1 && d >= 1 && B >= 1 && niter >= 0, "bad argument");
+    LIRA_REQUIRE(n >= B, "K-Means needs at least as many points as centroids");
+    if (int rc = check_device(device)) return rc;
+    // faiss clustering: at most 256 points per centroid take part (a random subset, selection sampling: one pass, no O(n) memory)
+    std::mt19937_64 rng(seed);
+    const int64_t cap = 256ll * B;
+    const int64_t ns = std::min<int64_t>(n, cap);
+    const int ds = round_up(d, 4);
+    std::vector<float> sample;
+    const float* src = x;
+    if (ns < n || ds != d) {
+        sample.assign((size_t)ns * ds, 0.0f);
+        int64_t need = ns, w = 0;
+        for (int64_t i = 0; i < n && need > 0; ++i) {
+            const uint64_t remaining = (uint64_t)(n - i);
+            if (ns == n || (rng() % remaining) < (uint64_t)need) {
+                memcpy(sample.data() + (size_t)w * ds, x + (size_t)i * d, (size_t)d * 4);
+                ++w;
+                --need;
+            }
+        }
+        src = sample.data();
+    }
+    // initial centroids: B distinct sample rows
+    std::vector<int64_t> rows(ns);
+    std::iota(rows.begin(), rows.end(), 0ll);
+    for (int b = 0; b < B; ++b) std::swap(rows[b], rows[b + (int64_t)(rng() % (uint64_t)(ns - b))]);
+    DevBuf dx, dc, dr;
+    cudaStream_t st = nullptr;
+    auto body = [&]() -> int {
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (int r = dx.ensure((size_t)ns * ds * 4)) return r;
+        if (int r = dc.ensure((size_t)B * ds * 4)) return r;
+        if (int r = dr.ensure((size_t)B * 8)) return r;
+        if (int r = upload_bytes(dx.p, src, (size_t)ns * ds * 4, st)) return r;
+        LIRA_CUDA_OK(cudaMemcpyAsync(dr.p, rows.data(), (size_t)B * 8, cudaMemcpyHostToDevice, st));
+        if (init_centroids) {
+            LIRA_CUDA_OK(cudaMemsetAsync(dc.p, 0, (size_t)B * ds * 4, st));
+            LIRA_CUDA_OK(cudaMemcpy2DAsync(dc.p, (size_t)ds * 4, init_centroids, (size_t)d * 4, (size_t)d * 4, (size_t)B, cudaMemcpyHostToDevice, st));
+        }
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        if (int r = lira_kmeans_train_dev(dx.as<float>(), ds, ns, d, B, niter, init_centroids ? 1 : 0, dc.as<float>(), ds, (const int64_t*)dr.p, device, st)) return r;
+        LIRA_CUDA_OK(cudaMemcpy2DAsync(centroids_out, (size_t)d * 4, dc.p, (size_t)ds * 4, (size_t)d * 4, (size_t)B, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    };
+    const int rc = body();
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (DevBuf* b : {&dx, &dc, &dr}) b->release();
+    return rc;
+}
+
+int lira_centroid_features_dev(const float* d_q, int64_t ldq, int64_t Q, const float* d_centroids, int64_t ldc, int B, int d,
+                               const float* d_mean, const float* d_scale, float* d_out, int64_t ldo, int device, void* stream) {
+    LIRA_REQUIRE(d_q && d_centroids && d_out && B >= 1 && d >= 1 && Q >= 0, "bad argument");
+    LIRA_REQUIRE((d_mean == nullptr) == (d_scale == nullptr), "mean and scale must be given together");
+    LIRA_REQUIRE((ldq % 4) == 0 && (ldc % 4) == 0 && (ldo % 4) == 0 && ((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_centroids & 15) == 0 &&
+                 ((uintptr_t)d_out & 15) == 0, "device matrices need row strides that are multiples of 4 and 16-byte alignment");
+    LIRA_REQUIRE(ldq >= d && ldc >= d && ldo >= B, "row strides too small");
+    if (int rc = check_device(device)) return rc;
+    if (Q == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tm;
+    if (int r = make_tmap(&tm, d_centroids, B, round_up(d, 4), ldc)) return r;
+    const long long chunk = 1ll << 20;
+    for (long long q0 = 0; q0 < Q; q0 += chunk) {
+        const long long nq = std::min<long long>(chunk, Q - q0);
+        DenseParams p{d_q + q0 * ldq, (long)ldq, (int)nq, round_up(d, 4), B, d_out + q0 * ldo, (long)ldo, 0, d_mean, d_scale};
+        if (int r = launch_dense<64, OP_L2, EPI_FEATURE>(tm, p, st)) return r;
+    }
+    return 0;
+}
+
+int lira_feature_stats_dev(const float* d_x, int64_t ld, int64_t n, const float* d_centroids, int64_t ldc, int B, int d,
+                           double* mean_out, double* var_out, int device, void* stream) {
+    LIRA_REQUIRE(d_x && d_centroids && mean_out && var_out && n >= 1 && B >= 1 && d >= 1, "bad argument");
+    if (int rc = check_device(device)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Bp = round_up(B, 4);
+    const long long chunk = std::min<long long>(n, 65536);
+    DevBuf feats, acc;
+    auto body = [&]() -> int {
+        if (int r = feats.ensure((size_t)chunk * Bp * 4)) return r;
+        if (int r = acc.ensure((size_t)2 * B * 8)) return r;
+        LIRA_CUDA_OK(cudaMemsetAsync(acc.p, 0, (size_t)2 * B * 8, st));
+        for (long long a = 0; a < n; a += chunk) {
+            const long long m = std::min<long long>(chunk, n - a);
+            if (int r = lira_centroid_features_dev(d_x + a * ld, ld, m, d_centroids, ldc, B, d, nullptr, nullptr, feats.as<float>(), Bp, device, st)) return r;
+            dim3 grid((B + 31) / 32, (unsigned)std::min<long long>(256, (m + 7) / 8));
+            feature_stats_kernel<<<grid, 256, 0, st>>>(feats.as<float>(), Bp, m, B, acc.as<double>(), acc.as<double>() + B);
+            LIRA_LAUNCH_CHECK();
+        }
+        std::vector<double> h(2 * (size_t)B);
+        LIRA_CUDA_OK(cudaMemcpyAsync(h.data(), acc.p, (size_t)2 * B * 8, cudaMemcpyDeviceToHost, st));
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; ++b) {
+            const double mu = h[b] / (double)n;
+            mean_out[b] = mu;
+            var_out[b] = std::max(h[B + b] / (double)n - mu * mu, 0.0);
+        }
+        return 0;
+    };
+    const int rc = body();
+    cudaStreamSynchronize(st);
+    feats.release();
+    acc.release();
+    return rc;
+}
+
+int lira_mul_partition_dev(const float* d_score, int64_t lds, int64_t n_rows, int B, float sigma, const int64_t* d_points, int64_t first,
+                           int n_mul, int32_t* d_data_2_bkt, int32_t* d_added, int device, void* stream) {
+    LIRA_REQUIRE(d_score && d_data_2_bkt && d_added && n_rows >= 0 && B >= 1, "bad argument");
+    LIRA_REQUIRE(n_mul >= 2 && n_mul <= 8, "n_mul must be in [2, 8]");
+    LIRA_REQUIRE(lds >= B, "score row stride too small");
+    if (int rc = check_device(device)) return rc;
+    if (n_rows == 0) return 0;
+    mul_partition_kernel<<<(int)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_score, (long)lds, n_rows, B, sigma, (const long long*)d_points, first,
+                                                                                 n_mul, d_data_2_bkt, d_added);
+    LIRA_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- a12: IVF-approximate self-kNN (compute_knn.cpp:158-203: IndexIVFFlat(quantizer, d, nlist), train, add, nprobe) ----------
+namespace {
+__global__ void narrow_probe_ids_kernel(const long long* __restrict__ in, long long n, int* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (int)in[i];
+}
+}  // namespace
+
+int lira_knn_ivf(const float* base, int64_t N, int d, int k, int nlist, int nprobe, uint64_t seed, int device, float* D, int64_t* I) {
+    LIRA_REQUIRE(base && D && I && N >= 1 && d >= 1, "bad argument");
+    LIRA_REQUIRE(k >= 1 && k <= 128, "k must be in [1, 128]");
+    LIRA_REQUIRE(nlist >= 1 && nlist <= N && nprobe >= 1, "nlist must be in [1, N] and nprobe >= 1");
+    LIRA_REQUIRE(N < (1ll << 31), "N must be below 2^31");
+    if (int rc = check_device(device)) return rc;
+    nprobe = std::min(nprobe, nlist);
+    const int ds = round_up(d, 4);
+    DevBuf dbase, dcent, dI, dD, dvecs, dids, dpo, dpi, dDo, dIo;
+    lira_knn_t* kc = nullptr;
+    lira_index_t* index = nullptr;
+    cudaStream_t st = nullptr;
+    auto body = [&]() -> int {
+        LIRA_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        // train: K-Means on (a sample of) the base, as IndexIVFFlat::train hands its quantizer to faiss clustering
+        std::vector<float> cent((size_t)nlist * d);
+        if (int r = lira_kmeans_train(base, N, d, nlist, 20, seed, nullptr, device, cent.data())) return r;
+        if (int r = upload_rows(dbase, base, N, d, ds, st)) return r;
+        if (int r = upload_rows(dcent, cent.data(), nlist, d, ds, st)) return r;
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        if (int r = lira_knn_create_dev(dcent.as<float>(), ds, nlist, d, LIRA_METRIC_L2, device, &kc)) return r;
+        // add: every vector goes to the list of its nearest centroid
+        const long long chunk = 1ll << 20;
+        if (int r = dI.ensure((size_t)std::min<long long>(chunk, N) * std::max(nprobe, 1) * 8)) return r;
+        if (int r = dD.ensure((size_t)std::min<long long>(chunk, N) * std::max(nprobe, 1) * 4)) return r;
+        std::vector<long long> a1((size_t)N);
+        for (long long a = 0; a < N; a += chunk) {
+            const long long m = std::min<long long>(chunk, N - a);
+            if (int r = lira_knn_search_dev(kc, dbase.as<float>() + a * ds, ds, m, 1, dD.as<float>(), (int64_t*)dI.p, st)) return r;
+            LIRA_CUDA_OK(cudaMemcpyAsync(a1.data() + a, dI.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        std::vector<int64_t> off((size_t)nlist + 1, 0);
+        for (long long i = 0; i < N; ++i) off[(size_t)a1[i] + 1]++;
+        for (int b = 0; b < nlist; ++b) off[b + 1] += off[b];
+        std::vector<int32_t> ids((size_t)N);
+        {
+            std::vector<int64_t> cur(off.begin(), off.end() - 1);
+            for (long long i = 0; i < N; ++i) ids[(size_t)cur[(size_t)a1[i]]++] = (int32_t)i;   // ids ascending inside a list (add order)
+        }
+        if (int r = dids.ensure((size_t)N * 4)) return r;
+        if (int r = dvecs.ensure((size_t)N * ds * 4)) return r;
+        LIRA_CUDA_OK(cudaMemcpyAsync(dids.p, ids.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<grid_for(N * (ds / 4), 256, 148 * 16), 256, 0, st>>>(dbase.as<float>(), ds, ds, dids.as<int>(), N, dvecs.as<float>(), ds);
+        LIRA_LAUNCH_CHECK();
+        LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        if (int r = lira_index_create_dev(dvecs.as<float>(), ds, d, off.data(), dids.as<int>(), nlist, LIRA_METRIC_L2, device, &index)) return r;
+        // search: the nprobe nearest lists of every vector, exact scan inside them
+        const long long qb = std::max<long long>(256, std::min<long long>(32768, (2ll << 20) / nprobe));
+        if (int r = dI.ensure((size_t)qb * nprobe * 8)) return r;
+        if (int r = dD.ensure((size_t)qb * nprobe * 4)) return r;
+        if (int r = dpo.ensure((size_t)(qb + 1) * 8)) return r;
+        if (int r = dpi.ensure((size_t)qb * nprobe * 4)) return r;
+        if (int r = dDo.ensure((size_t)qb * k * 4)) return r;
+        if (int r = dIo.ensure((size_t)qb * k * 8)) return r;
+        iota_offsets_kernel<<<grid_for(qb + 1, 256), 256, 0, st>>>(dpo.as<long long>(), qb, nprobe);
+        LIRA_LAUNCH_CHECK();
+        for (long long a = 0; a < N; a += qb) {
+            const long long m = std::min<long long>(qb, N - a);
+            const float* q = dbase.as<float>() + a * ds;
+            if (int r = lira_knn_search_dev(kc, q, ds, m, nprobe, dD.as<float>(), (int64_t*)dI.p, st)) return r;
+            narrow_probe_ids_kernel<<<grid_for(m * nprobe, 256), 256, 0, st>>>(dI.as<long long>(), m * nprobe, dpi.as<int>());
+            LIRA_LAUNCH_CHECK();
+            if (int r = lira_search_dev(index, q, ds, m, (const int64_t*)dpo.p, dpi.as<int>(), m * nprobe, k, 0, dDo.as<float>(), (int64_t*)dIo.p, nullptr, st)) return r;
+            LIRA_CUDA_OK(cudaMemcpyAsync(D + (size_t)a * k, dDo.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaMemcpyAsync(I + (size_t)a * k, dIo.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+            LIRA_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    };
+    const int rc = body();
+    if (st) cudaStreamSynchronize(st);
+    if (index) lira_index_free(index);
+    if (kc) lira_knn_free(kc);
+    if (st) cudaStreamDestroy(st);
+    for (DevBuf* b : {&dbase, &dcent, &dI, &dD, &dvecs, &dids, &dpo, &dpi, &dDo, &dIo}) b->release();
     return rc;
 }
 

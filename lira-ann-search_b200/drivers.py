@@ -299,9 +299,7 @@ def run_smallscale(cfg: Config, device_index=None):
 # LIRA_largescale.py:184-354
 # ---------------------------------------------------------------------------------------------
 def run_largescale(cfg: LargeConfig, device_index=None):
-    from .model_probing import model_infer
     import torch
-    from torch.utils.data import DataLoader, TensorDataset
     n_bkt = cfg.n_bkt
     os.makedirs(cfg.pth_log, exist_ok=True)
     fw = open(cfg.pth_log + cfg.log_name, "a", encoding="utf-8")
@@ -382,15 +380,23 @@ def run_largescale(cfg: LargeConfig, device_index=None):
         _, cmp_all, found = query.get_cmp_recall(inner, x_q, cluster_ids, cfg)
         query.query_tuning_large(all_outputs, knn_distr_id_query, found, cmp_all, cfg)
         del inner
+        # every point gets its partitions from the model, in batches (LIRA_largescale.py:319-329). Each batch stays on the device:
+        # scaler statistics of THIS batch (utils.py:182-215) -> standardised centroid distances -> the model's forward (PyTorch,
+        # as model_infer does) -> the redundancy rule (lira_mul_partition_dev); only the partition columns come back
+        cent_dev = torch.as_tensor(np.ascontiguousarray(kmeans.centroids, np.float32), device=device)
+        model.eval()
         for start_idx in range(0, n_d, cfg.batch_redundancy):
             end_idx = min(start_idx + cfg.batch_redundancy, n_d)
-            xd_batch = np.ascontiguousarray(x_d[start_idx:end_idx])
-            dist_b = utils.get_scaled_dist_data(xd_batch, kmeans, n_bkt, device=dev_i)   # scaler fitted on this batch (utils.py:182-215)
-            loader = DataLoader(TensorDataset(torch.tensor(dist_b, dtype=torch.float32), torch.tensor(xd_batch, dtype=torch.float32)),
-                                batch_size=cfg.batch_size, shuffle=False)
-            data_predicts, data_partition_score = model_infer(model, loader, device)
-            query.mul_partition_by_model_large(data_partition_score, data_predicts, np.arange(start_idx, end_idx), start_idx,
-                                               data_2_bkt, cluster_cnts, cluster_ids)
+            x_b = torch.as_tensor(np.ascontiguousarray(x_d[start_idx:end_idx], np.float32), device=device)
+            mean, var = engine.feature_stats_dev(x_b, cent_dev)
+            scale = np.sqrt(var)
+            scale[scale < 10 * np.finfo(np.float64).eps] = 1.0
+            feats = engine.centroid_features_dev(x_b, cent_dev, torch.as_tensor(mean.astype(np.float32), device=device),
+                                                 torch.as_tensor(scale.astype(np.float32), device=device))
+            with torch.no_grad():
+                score = torch.cat([model(feats[a:a + 65536], x_b[a:a + 65536]) for a in range(0, len(x_b), 65536)])
+            query.mul_partition_by_model_large(score, None, np.arange(start_idx, end_idx), start_idx, data_2_bkt, cluster_cnts, cluster_ids)
+            del x_b, feats, score
         _, knn_distr_id_query = utils.get_knn_distr_redundancy(knn_query, data_2_bkt, cfg)
         inner = utils.create_inner_indexes(x_d, cluster_ids, cfg, device=dev_i)
         _, cmp_all, found = query.get_cmp_recall(inner, x_q, cluster_ids, cfg)

@@ -447,5 +447,61 @@ def knn(base, query, k, metric="L2", device=0):
     return D, I
 
 
+def knn_ivf(base, k, nlist, nprobe, seed=1234, device=0):
+    """IVF-approximate self-kNN (compute_knn.cpp:158-203). Returns (D[N,k], I[N,k] int64)."""
+    C.require_gpu()
+    base = C.f32(base)
+    D = np.empty((base.shape[0], k), np.float32)
+    I = np.empty((base.shape[0], k), np.int64)
+    C.check(C.lib().lira_knn_ivf(C.ptr(base, C.c_f32p), base.shape[0], base.shape[1], int(k), int(nlist), int(nprobe), int(seed),
+                                 device, C.ptr(D, C.c_f32p), C.ptr(I, C.c_i64p)))
+    return D, I
+
+
+def kmeans_train(x, n_bkt, niter=20, seed=1234, init_centroids=None, device=0):
+    """faiss.Kmeans(d, k, niter).train(x) -> centroids [k, d] float32 (utils.py:321-324); Lloyd on the device."""
+    C.require_gpu()
+    x = C.f32(x)
+    out = np.empty((n_bkt, x.shape[1]), np.float32)
+    init = None if init_centroids is None else C.f32(init_centroids)
+    C.check(C.lib().lira_kmeans_train(C.ptr(x, C.c_f32p), x.shape[0], x.shape[1], int(n_bkt), int(niter), int(seed),
+                                      C.ptr(init, C.c_f32p), device, C.ptr(out, C.c_f32p)))
+    return out
+
+
+def centroid_features_dev(d_x, d_centroids, d_mean=None, d_scale=None, out=None, stream=None):
+    """get_dist_cid (+ transform) for torch CUDA tensors; returns a CUDA tensor [n, B] (row stride rounded up to 4)."""
+    import torch
+    n, d = d_x.shape
+    B = d_centroids.shape[0]
+    Bp = (B + 3) // 4 * 4
+    if out is None:
+        out = torch.empty((n, Bp), dtype=torch.float32, device=d_x.device)
+    C.check(C.lib().lira_centroid_features_dev(d_x.data_ptr(), d_x.stride(0), n, d_centroids.data_ptr(), d_centroids.stride(0), B, d,
+                                               None if d_mean is None else d_mean.data_ptr(), None if d_scale is None else d_scale.data_ptr(),
+                                               out.data_ptr(), out.stride(0), d_x.device.index, _stream_handle(d_x.device, stream)))
+    return out[:, :B]
+
+
+def feature_stats_dev(d_x, d_centroids, stream=None):
+    """StandardScaler statistics of the centroid distances of the rows of d_x: (mean[B], var[B]) float64 numpy arrays."""
+    B = d_centroids.shape[0]
+    mean, var = np.empty(B, np.float64), np.empty(B, np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    C.check(C.lib().lira_feature_stats_dev(d_x.data_ptr(), d_x.stride(0), d_x.shape[0], d_centroids.data_ptr(), d_centroids.stride(0), B,
+                                           d_x.shape[1], mean.ctypes.data_as(dp), var.ctypes.data_as(dp), d_x.device.index,
+                                           _stream_handle(d_x.device, stream)))
+    return mean, var
+
+
+def mul_partition_dev(d_score, d_data_2_bkt, d_added, first=0, d_points=None, sigma=0.5, stream=None):
+    """The redundancy rule on the device (LIRA_smallscale.py:77-97): d_score [rows, B] float32, d_data_2_bkt [N, n_mul] int32
+    (updated in place), d_added [N, n_mul] int32 preset to -1."""
+    C.check(C.lib().lira_mul_partition_dev(d_score.data_ptr(), d_score.stride(0), d_score.shape[0], d_score.shape[1], float(sigma),
+                                           None if d_points is None else d_points.data_ptr(), int(first), d_data_2_bkt.shape[1],
+                                           d_data_2_bkt.data_ptr(), d_added.data_ptr(), d_score.device.index,
+                                           _stream_handle(d_score.device, stream)))
+
+
 def launch_count() -> int:
     return int(C.lib().lira_launch_count())

@@ -220,11 +220,43 @@ def mul_partition_by_model(data_partition_score, data_predicts, xd_id_sorted_pre
     _mul_partition_rows(score[t], pred[t], t, data_2_bkt, cluster_cnts, cluster_ids)
 
 
+def _append_new_copies(added, t, cluster_cnts, cluster_ids):
+    """added[i, j] = partition newly holding point t[i] in column j (-1: none): the reference's bookkeeping -- counts, and the
+    point appended to every such partition, points in order, columns ascending (LIRA_smallscale.py:94-97)."""
+    rows, cols = np.nonzero(added >= 0)                                     # row-major: points in order, columns ascending
+    part, pts = added[rows, cols].astype(np.int64), t[rows]
+    np.add.at(cluster_cnts, part, 1)
+    by_part = np.argsort(part, kind="stable")
+    part_s, pts_s = part[by_part], pts[by_part]
+    cuts = np.flatnonzero(np.diff(part_s)) + 1
+    for c, ids in zip(part_s[np.r_[0, cuts]] if part_s.size else [], np.split(pts_s, cuts) if part_s.size else []):
+        cluster_ids[int(c)].extend(int(x) for x in ids)
+
+
+def _mul_partition_device(score, t, data_2_bkt, cluster_cnts, cluster_ids):
+    """The same rule evaluated by the library on the device (lira_mul_partition_dev: one warp per point) for scores that are
+    already there: only the [rows, n_mul] partition columns travel."""
+    import torch
+    from . import engine
+    dev = score.device
+    rows = torch.as_tensor(np.ascontiguousarray(data_2_bkt[t], np.int32), device=dev)
+    added = torch.full_like(rows, -1)
+    engine.mul_partition_dev(score.float().contiguous(), rows, added)
+    torch.cuda.synchronize(dev)
+    data_2_bkt[t] = rows.cpu().numpy()
+    _append_new_copies(added.cpu().numpy(), t, cluster_cnts, cluster_ids)
+
+
 def mul_partition_by_model_large(data_partition_score, data_predicts, global_xd_ids, start_idx, data_2_bkt, cluster_cnts,
                                  cluster_ids):
     """LIRA_largescale.py:51-72: the same rule for one batch of the full data -- row i of the score / predict matrices is
-    point global_xd_ids[i] = start_idx + i. Vectorised, same in-place effects and append order as the reference loop."""
-    score, pred = _as_numpy(data_partition_score), _as_numpy(data_predicts)
+    point global_xd_ids[i] = start_idx + i. Vectorised, same in-place effects and append order as the reference loop.
+    A CUDA score tensor takes the device form of the rule (data_predicts is then not needed: it is score > 0.5)."""
     t = np.asarray(_as_numpy(global_xd_ids), np.int64)
+    if getattr(data_partition_score, "is_cuda", False):
+        local = t - int(start_idx)
+        sc = data_partition_score if np.array_equal(local, np.arange(len(t))) else data_partition_score[local.tolist()]
+        return _mul_partition_device(sc, t, data_2_bkt, cluster_cnts, cluster_ids)
+    score, pred = _as_numpy(data_partition_score), _as_numpy(data_predicts)
     local = t - int(start_idx)
     _mul_partition_rows(score[local], pred[local], t, data_2_bkt, cluster_cnts, cluster_ids)

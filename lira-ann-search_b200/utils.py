@@ -2,9 +2,9 @@
 Same function names, argument meaning and return shapes; the arithmetic that the reference hands
 to faiss-cpu / scipy goes to liblira_b200 instead. Citations are into /root/reference/utils.py.
 
-Out of scope here (index construction): training-time label building and the
-redundancy assignment stay numpy/PyTorch as in the reference; a K-Means is provided only because
-synthetic data needs partitions (build_kmeans_index, torch on the GPU).
+Index construction: K-Means runs in the library (lira_kmeans_train: assignment on the kNN path,
+update kernel), the scaler statistics and the redundancy rule have device forms (engine.feature_stats_dev,
+engine.mul_partition_dev); label building stays numpy as in the reference.
 """
 from __future__ import annotations
 
@@ -161,12 +161,17 @@ def compute_data_knn(x_data, cfg, data_path="/data/vector_datasets", device=0):
 # partitions (build side; needed to make synthetic indexes) -- utils.py:321-330
 # ---------------------------------------------------------------------------------------------
 class Kmeans:
-    """faiss.Kmeans stand-in with the fields the reference reads (.centroids, .index): Lloyd on at
-    most 256*k sampled points, niter iterations, L2 assignment. torch on `device` (build side)."""
+    """faiss.Kmeans with the fields the reference reads (.centroids, .index): Lloyd on at most 256 * k sampled points, niter
+    iterations, L2 assignment (utils.py:321-325). Runs in liblira_b200: the assignment step is the exact 1-NN of the kNN path
+    against the centroid table, the update step a segmented mean on the device (lira_kmeans_train)."""
 
     def __init__(self, d, k, niter=20, verbose=False, seed=1234, device="cuda:0"):
         self.d, self.k, self.niter, self.verbose, self.seed, self.device = d, k, niter, verbose, seed, device
         self.centroids = None
+
+    @property
+    def _dev_index(self):
+        return int(str(self.device).split(":")[1]) if ":" in str(self.device) else 0
 
     @property
     def index(self):
@@ -174,35 +179,8 @@ class Kmeans:
         reference uses (utils.py:325, LIRA_largescale.py:294). Exact kNN on the GPU (engine.KnnIndex)."""
         return _CentroidIndex(self)
 
-    @staticmethod
-    def assign(x_t, c_t, chunk=262144):
-        import torch
-        out = torch.empty(x_t.shape[0], dtype=torch.int64, device=x_t.device)
-        c2 = (c_t * c_t).sum(1)[None, :]
-        for a in range(0, x_t.shape[0], chunk):
-            xb = x_t[a:a + chunk]
-            out[a:a + chunk] = ((xb * xb).sum(1)[:, None] + c2 - 2.0 * xb @ c_t.T).argmin(1)
-        return out
-
-    def train(self, x):
-        import torch
-        g = torch.Generator(device="cpu").manual_seed(self.seed)
-        x_t = torch.as_tensor(np.ascontiguousarray(x, np.float32), device=self.device)
-        n = x_t.shape[0]
-        if n > 256 * self.k:
-            x_t = x_t[torch.randperm(n, generator=g)[:256 * self.k].to(self.device)]
-            n = x_t.shape[0]
-        c = x_t[torch.randperm(n, generator=g)[:self.k].to(self.device)].clone()
-        for _ in range(self.niter):
-            a = self.assign(x_t, c)
-            cnt = torch.bincount(a, minlength=self.k).float()
-            s = torch.zeros_like(c).index_add_(0, a, x_t)
-            nz = cnt > 0
-            c[nz] = s[nz] / cnt[nz, None]
-            if (~nz).any():  # re-seed empty clusters from random points
-                idx = torch.randint(0, n, (int((~nz).sum()),), generator=g).to(self.device)
-                c[~nz] = x_t[idx]
-        self.centroids = c.cpu().numpy()
+    def train(self, x, init_centroids=None):
+        self.centroids = engine.kmeans_train(x, self.k, self.niter, self.seed, init_centroids, self._dev_index)
         return self
 
 
@@ -215,8 +193,7 @@ class _CentroidIndex:
         return len(self.km.centroids)
 
     def search(self, x, k):
-        dev = self.km.device
-        dev_i = int(str(dev).split(":")[1]) if ":" in str(dev) else 0
+        dev_i = self.km._dev_index
         x = np.ascontiguousarray(x, np.float32)
         idx = engine.KnnIndex(np.ascontiguousarray(self.km.centroids, np.float32), "L2", dev_i)
         D = np.empty((len(x), k), np.float32)
@@ -229,11 +206,9 @@ class _CentroidIndex:
 
 def build_kmeans_index(x_data, n_bkt, device="cuda:0"):
     """-> (kmeans, data_2_bkt [n,1], cluster_cnts [B], cluster_ids list[B] of id lists) (utils.py:321-330)."""
-    import torch
     n_d, dim = x_data.shape
     kmeans = Kmeans(dim, n_bkt, niter=20, device=device).train(x_data)
-    x_t = torch.as_tensor(np.ascontiguousarray(x_data, np.float32), device=device)
-    a = Kmeans.assign(x_t, torch.as_tensor(kmeans.centroids, device=device)).cpu().numpy()
+    a = kmeans.index.search(x_data, 1)[1].reshape(-1)
     cluster_cnts = np.bincount(a, minlength=n_bkt)
     order = np.argsort(a, kind="stable")
     bounds = np.zeros(n_bkt + 1, np.int64)

@@ -43,6 +43,37 @@ def test_compute_knn_writes_the_reference_cache_files(tmp_path):
     assert r.returncode == 1 and "Cannot find base file" in r.stderr
 
 
+def test_compute_knn_ivf_branch(tmp_path):
+    """compute_knn <ds> <path> <k> <nprobe != 0>: the reference's IVF-approximate branch (compute_knn.cpp:150-203): its nlist rule,
+    the `_ivf_nprobe{p}` suffix utils.compute_data_knn looks for first, the extra .meta keys. Probing every list must give the
+    exact result; a small nprobe a good approximation; no nprobe argument the automatic one (:190-199)."""
+    import lira_ann_search_b200 as L
+    exe = _need("compute_knn")
+    x_d, _ = synth(3000, 24, 1, seed=4, integer=True)
+    ds = tmp_path / "toy"
+    ds.mkdir()
+    L.write_xvecs(str(ds / "toy_base.fvecs"), x_d)
+    _, I_ref = O.knn(x_d, x_d, 11, O.L2, O.F64)
+    nlist = 54                                                     # min(int(sqrt(3000)), 256)
+    for nprobe, arg in ((nlist, [str(nlist)]), (8, ["8", "4"]), (16, [])):   # 16 = min(max(54 // 4, 16), 64): automatic
+        r = subprocess.run([exe, "toy", str(tmp_path), "10"] + arg, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out = ds / "knn_cache" / f"toy-data_self_knn10-n3000_ivf_nprobe{nprobe}.bin"
+        knn = np.fromfile(out, dtype=np.int32).reshape(3000, 10)
+        meta = dict(l.split(": ", 1) for l in open(str(out) + ".meta").read().splitlines())
+        assert meta["method"] == "ivf_approximate" and meta["n_clusters"] == str(nlist) and meta["nprobe"] == str(nprobe)
+        assert meta["probe_ratio"].endswith("%")
+        if nprobe == nlist:
+            assert np.array_equal(knn, I_ref[:, 1:])
+        else:
+            rec = np.mean([len(set(knn[i]) & set(I_ref[i, 1:])) / 10 for i in range(3000)])
+            assert rec > 0.9, rec
+    # utils.compute_data_knn takes the newest *_ivf_nprobe*.bin before anything else (utils.py:245-266)
+    cfg = type("C", (), {"dataset": "toy", "k": 10, "dis_metric": "L2"})
+    got = L.compute_data_knn(x_d, cfg, data_path=str(tmp_path))
+    assert got.shape == (3000, 10) and got.dtype == np.int32
+
+
 def test_compute_knn_query_ground_truth_mode(tmp_path):
     """compute_knn <ds> <path> <k> --queries: exact ground truth of the query set as {ds}_groundtruth.ivecs (the layout
     utils.read_xvecs / search.cpp:read_ivecs read), k = 100 like config 2."""

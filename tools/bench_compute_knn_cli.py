@@ -17,7 +17,7 @@ with tempfile.TemporaryDirectory() as td:
     os.makedirs(os.path.join(td, "syn"))
     L.write_xvecs(os.path.join(td, "syn", "syn_base.fvecs"), x)
     t0 = time.time()
-    r = subprocess.run([os.path.join(root, "bin", "compute_knn"), "syn", td, str(k)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(root, "bin", "compute_knn"), "syn", td, str(k), "0"], capture_output=True, text=True)
     wall = time.time() - t0
     print(r.stdout[-600:], r.stderr[-300:])
     knn = np.fromfile(os.path.join(td, "syn", "knn_cache", f"syn-data_self_knn{k}-n{N}.bin"), dtype=np.int32).reshape(N, k)
