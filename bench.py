@@ -859,21 +859,38 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
             for i in (n_rep, n_rep + 1):
                 outs[i & 3] = index.probe_search_wait(slot=i & 3, out=outs[i & 3])
             ids = outs[0][1]
-        else:
-            host_out = None
+        elif gather_merge is not None:
+            # sharded: pinned / pageable host queries -> device, the batch, the NCCL all-gather + merge, merged results -> host
+            d_q = torch.empty((Q, d), dtype=torch.float32, device=dev)
+            q_t = torch.as_tensor(q_host)
+            D_h = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+            I_h = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+            dev_out = None
             for i in range(n_rep):
                 flush.zero_()
                 torch.cuda.synchronize()
                 if dist is not None:
                     dist.barrier()
                 t0 = time.perf_counter()
-                host_out = index.probe_search(model, q_host, L.SELECT_GT, thr, k, True, out=host_out)
-                Dh, Ih = host_out[0], host_out[1]
-                if gather_merge is not None:
-                    Dg, Ig = gather_merge(torch.as_tensor(Dh, device=dev), torch.as_tensor(Ih, device=dev))
-                    Ih = Ig.cpu().numpy()
+                d_q.copy_(q_t, non_blocking=True)
+                dev_out = index.probe_search_enqueue_dev(model, d_q, L.SELECT_GT, thr, k, True, out=dev_out)
+                Dg, Ig = gather_merge(dev_out[0], dev_out[1])
+                D_h.copy_(Dg, non_blocking=True)
+                I_h.copy_(Ig, non_blocking=True)
+                index.finish()
+                torch.cuda.synchronize()
                 ts.append(time.perf_counter() - t0)
-            ids = Ih
+            ids = I_h.numpy().copy()
+            res["api"] = "host queries -> lira_probe_search_enqueue_dev -> NCCL all-gather + lira_merge_ranks_dev -> host results, one batch at a time"
+        else:
+            host_out = None
+            for i in range(n_rep):
+                flush.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                host_out = index.probe_search(model, q_host, L.SELECT_GT, thr, k, True, out=host_out)
+                ts.append(time.perf_counter() - t0)
+            ids = host_out[1]
         s = float(np.mean(ts[3:]))
         if dist is not None:
             t = torch.tensor([s], device=dev)
@@ -1013,10 +1030,15 @@ def run_shard(args, rank, world, local, dist, log):
         out = index.probe_search_dev(model, x_q, L.SELECT_GT, thr, k, True, out=out)
         return out[0], out[1]
 
+    merged = None
+
     def step():
-        nonlocal out
+        nonlocal out, merged
         out = index.probe_search_enqueue_dev(model, x_q, L.SELECT_GT, thr, k, True, out=out)
-        return gather_merge(out[0], out[1])
+        if dist is not None:
+            merged = allgather_merge(out[0], out[1], k, "L2", dedup=True, device=local, out=merged)
+            return merged
+        return out[0], out[1]
 
     # one rank's share alone (no collective): what a single GPU needs for a 12.5 M-vector dataset
     for _ in range(3):

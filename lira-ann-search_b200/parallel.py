@@ -60,10 +60,25 @@ def stripe_csr(list_offsets, list_ids, rank, world):
     return new_off, ids[keep]
 
 
-def pack_keys(D, I, metric, device):
+_BUF = {}
+
+
+def _buffers(Q, k, world, device):
+    """Grow-only scratch of the merge (keys of this rank, gathered keys) per (shape, device): a step of the serving loop
+    allocates nothing."""
+    import torch
+    key = (Q, k, world, str(device))
+    b = _BUF.get(key)
+    if b is None:
+        b = (torch.empty((Q, k), dtype=torch.int64, device=device), torch.empty((world, Q, k), dtype=torch.int64, device=device))
+        _BUF[key] = b
+    return b
+
+
+def pack_keys(D, I, metric, device, out=None):
     """(D[Q,k] f32, I[Q,k] i64) torch CUDA tensors -> int64 tensor of ordered (score, id) keys."""
     import torch
-    keys = torch.empty(D.shape, dtype=torch.int64, device=D.device)
+    keys = torch.empty(D.shape, dtype=torch.int64, device=D.device) if out is None else out
     from .engine import _stream_handle
     st = _stream_handle(D.device)
     m = C.METRIC_IP if str(metric).lower() in ("1", "ip", "inner_product") else C.METRIC_L2
@@ -71,17 +86,19 @@ def pack_keys(D, I, metric, device):
     return keys
 
 
-def allgather_merge(D, I, k, metric="L2", dedup=True, device=0, group=None):
-    """Per-rank (D, I) -> global top-k on every rank: NCCL all-gather of the packed keys + merge kernel."""
+def allgather_merge(D, I, k, metric="L2", dedup=True, device=0, group=None, out=None):
+    """Per-rank (D, I) -> global top-k on every rank: NCCL all-gather of the packed keys + merge kernel. `out` = (D, I) CUDA
+    tensors of an earlier call are filled in place."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    keys = pack_keys(D.contiguous(), I.contiguous(), metric, device)
-    gathered = torch.empty((world,) + tuple(keys.shape), dtype=torch.int64, device=keys.device)
+    Q = D.shape[0]
+    mine, gathered = _buffers(Q, D.shape[1], world, D.device)
+    keys = pack_keys(D.contiguous(), I.contiguous(), metric, device, out=mine)
     dist.all_gather_into_tensor(gathered, keys, group=group)
-    Q = keys.shape[0]
-    D_out = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
-    I_out = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
+    if out is None:
+        out = (torch.empty((Q, k), dtype=torch.float32, device=keys.device), torch.empty((Q, k), dtype=torch.int64, device=keys.device))
+    D_out, I_out = out
     from .engine import _stream_handle
     st = _stream_handle(keys.device)
     m = C.METRIC_IP if str(metric).lower() in ("1", "ip", "inner_product") else C.METRIC_L2
