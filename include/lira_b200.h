@@ -170,6 +170,7 @@ int64_t lira_knn_ntotal(const lira_knn_t* h);
 int lira_knn_set_use_tensor_cores(lira_knn_t* h, int enable);
 int lira_knn_last_path(const lira_knn_t* h); /* last search: 0 CUDA cores, 1 tensor cores, 2 some batches on each */
 int lira_knn_last_redo(const lira_knn_t* h); /* queries of the last search answered again by the exact CUDA-core scan */
+int lira_knn_last_scan_kind(const lira_knn_t* h); /* kernel family of the last batch, see lira_index_last_scan_kind */
 
 /* ---- a12: IVF-approximate self-kNN (compute_knn.cpp:158-203) ------------------------------------------------------
  * faiss::IndexIVFFlat(quantizer = IndexFlatL2(d), d, nlist): train (K-Means, lira_kmeans_train), add (every vector to the list
@@ -246,6 +247,13 @@ int lira_index_last_redo(const lira_index_t* h); /* queries of the last tensor-c
                                                     overflowed and that were answered by the CUDA-core scan */
 int lira_index_tensor_core_eligible(const lira_index_t* h);
 int lira_index_tensor_core_mode(const lira_index_t* h);
+/* Byte-valued data (mode 1 with every value an integer in [0, 255], d <= 256) additionally qualifies for the integer
+ * tensor-core scan (tcgen05.mma kind::i8 over a one-byte-per-component copy of the rows, int32 accumulators: exact).
+ * It is what exhaustive probe sets (lira_knn*, compute_knn.cpp:208-259) run by default; threshold / top-n / explicit probe
+ * sets use it when LIRA_U8_SEARCH=1 is set in the environment. last_scan_kind: 0 CUDA cores, 1 fp16 tensor-core scan,
+ * 2 byte tensor-core scan. */
+int lira_index_byte_scan_eligible(const lira_index_t* h);
+int lira_index_last_scan_kind(const lira_index_t* h);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lira_knn_set_use_tensor_cores": (c_int, [c_vp, c_int]),
     "lira_knn_last_path": (c_int, [c_vp]),
     "lira_knn_last_redo": (c_int, [c_vp]),
+    "lira_knn_last_scan_kind": (c_int, [c_vp]),
     "lira_knn_ivf": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_int, c_f32p, c_i64p]),
     "lira_kmeans_train": (c_int, [c_f32p, c_i64, c_int, c_int, c_int, ctypes.c_uint64, c_f32p, c_int, c_f32p]),
     "lira_kmeans_train_dev": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_int, c_vp]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "lira_index_set_use_tensor_cores": (c_int, [c_vp, c_int]),
     "lira_index_last_path": (c_int, [c_vp]),
     "lira_index_last_redo": (c_int, [c_vp]),
+    "lira_index_byte_scan_eligible": (c_int, [c_vp]),
+    "lira_index_last_scan_kind": (c_int, [c_vp]),
     "lira_index_tensor_core_eligible": (c_int, [c_vp]),
     "lira_index_tensor_core_mode": (c_int, [c_vp]),
 }

@@ -137,6 +137,7 @@ struct FinishSelectParams {
     const int* list_order;          // [B] lists by size, descending
     const long long* list_offsets;  // [B + 1]
     int tile;
+    int seg_rows;                   // > 0 (byte scan): one item per (query tile group, segment of seg_rows list rows)
     ScanItem* items;
     int* n_items;
     unsigned long long* stats;      // {E_p, pairs}
@@ -168,16 +169,17 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
     __syncthreads();
     for (int base = 0; base < p.B; base += 1024) {
         const int i = base + threadIdx.x;
-        int b = 0, g = 0, cnt = 0;
+        int b = 0, g = 0, cnt = 0, nseg = 1;
         if (i < p.B) {
             b = p.list_order[i];
             g = (int)(p.group_offsets[b + 1] - p.group_offsets[b]);
             cnt = (g + p.tile - 1) / p.tile;
+            const unsigned long long nb = (unsigned long long)(p.list_offsets[b + 1] - p.list_offsets[b]);
             if (g > 0 && p.stats) {
-                const unsigned long long nb = (unsigned long long)(p.list_offsets[b + 1] - p.list_offsets[b]);
                 atomicAdd(p.stats + 0, nb);
                 atomicAdd(p.stats + 1, nb * (unsigned long long)g);
             }
+            if (p.seg_rows > 0) { nseg = (int)((nb + p.seg_rows - 1) / p.seg_rows); if (nseg < 1) nseg = 1; cnt *= nseg; }
         }
         int x = cnt;
 #pragma unroll
@@ -202,12 +204,13 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
         if (i < p.B) {
             const int gb = (int)p.group_offsets[b];
             for (int t = 0; t < cnt; ++t) {
-                const int left = g - t * p.tile;
+                const int tq = t / nseg;
+                const int left = g - tq * p.tile;
                 ScanItem it;
                 it.list = b;
-                it.q_begin = gb + t * p.tile;
+                it.q_begin = gb + tq * p.tile;
                 it.q_count = left < p.tile ? left : p.tile;
-                it.tm = p.tile;
+                it.tm = p.seg_rows > 0 ? t % nseg : p.tile;
                 p.items[at + t] = it;
             }
         }
@@ -235,7 +238,10 @@ struct ScatterQueriesParams {
     __half* gq;                     // [P, d16] fp16(scale q) in group order
     int d16;
     float scale;
-    int* bad_flag;                  // set when a scaled value does not fit fp16 (may be null)
+    int* cand_count;                // byte scan: [P] <- 0 for every valid pair slot (may be null)
+    uint8_t* gq8;                   // byte-valued index: [P, d8] uint8(q) in group order instead of gq (null otherwise)
+    int d8;
+    int* bad_flag;                  // set when a scaled value does not fit fp16 / a value is not an integer in [0, 255] (may be null)
     int* nprobe;                    // [Q] (may be null)
     long long* cmp;                 // [Q] (may be null)
     int Q;
@@ -263,7 +269,17 @@ __global__ void __launch_bounds__(256) scatter_queries_kernel(const ScatterQueri
         pk.y = *reinterpret_cast<uint32_t*>(&h1);
         return pk;
     };
-    if (c0 < p.d16) pk0 = pack(c0);
+    auto pack8 = [&](int c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < p.ds) v = *reinterpret_cast<const float4*>(qr + c);
+        bad |= !(v.x >= 0.f && v.x <= 255.f && v.y >= 0.f && v.y <= 255.f && v.z >= 0.f && v.z <= 255.f && v.w >= 0.f && v.w <= 255.f);
+        return (uint32_t)(int)v.x | ((uint32_t)(int)v.y << 8) | ((uint32_t)(int)v.z << 16) | ((uint32_t)(int)v.w << 24);
+    };
+    uint32_t b0 = 0, b1 = 0;   // this lane's 4 bytes of the first and second 128-byte block of the row
+    if (p.gq8) {
+        if (c0 < p.d8) b0 = pack8(c0);
+        if (c0 + 128 < p.d8) b1 = pack8(c0 + 128);
+    } else if (c0 < p.d16) pk0 = pack(c0);
     long long cmp = 0;
     for (int j0 = 0; j0 < n; j0 += 32) {
         const int j = j0 + lane;
@@ -272,6 +288,7 @@ __global__ void __launch_bounds__(256) scatter_queries_kernel(const ScatterQueri
             const int b = p.sel[(size_t)q * p.cap + j];
             pos = (int)p.group_offsets[b] + atomicAdd(p.cursor + b, 1);
             p.group_queries[pos] = q;
+            if (p.cand_count) p.cand_count[pos] = 0;
             p.probe_slot[po + j] = pos;
             p.probe_ids[po + j] = b;
             cmp += p.list_offsets[b + 1] - p.list_offsets[b];
@@ -279,6 +296,12 @@ __global__ void __launch_bounds__(256) scatter_queries_kernel(const ScatterQueri
         const int cnt = min(32, n - j0);
         for (int jj = 0; jj < cnt; ++jj) {
             const int ps = __shfl_sync(0xffffffffu, pos, jj);
+            if (p.gq8) {
+                uint8_t* dst8 = p.gq8 + (size_t)ps * p.d8;
+                if (c0 < p.d8) *reinterpret_cast<uint32_t*>(dst8 + c0) = b0;
+                if (c0 + 128 < p.d8) *reinterpret_cast<uint32_t*>(dst8 + c0 + 128) = b1;
+                continue;
+            }
             __half* dst = p.gq + (size_t)ps * p.d16;
             if (c0 < p.d16) *reinterpret_cast<uint2*>(dst + c0) = pk0;
             for (int c = c0 + 128; c < p.d16; c += 128) *reinterpret_cast<uint2*>(dst + c) = pack(c);

@@ -18,6 +18,7 @@
 
 #include "probe_kernels.cuh"
 #include "tc_scan_kernels.cuh"
+#include "u8_scan_kernels.cuh"
 #include "tc_dense_kernels.cuh"
 #include "fused_probe_kernels.cuh"
 #include "build_kernels.cuh"
@@ -120,6 +121,25 @@ static int make_tmap_aug(CUtensorMap* m, const void* base, long long rows) {
     return 0;
 }
 
+// rows x cols byte matrix with row stride ld (bytes, % 16 == 0); box = 128 rows x 128 bytes, 128-byte swizzle (u8 scan).
+static int make_tmap_u8(CUtensorMap* m, const void* base, long long rows, int cols, long long ld) {
+    PFN_encodeTiled enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    LIRA_REQUIRE(((uintptr_t)base & 15) == 0 && (ld % 16) == 0, "tensor map: base must be 16-byte aligned, ld % 16 == 0");
+    cuuint64_t dims[2] = {(cuuint64_t)std::max(cols, 1), (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld};
+    cuuint32_t box[2] = {(cuuint32_t)U8_KB, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (u8) failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // grow-only device buffers
 // ---------------------------------------------------------------------------------------------
@@ -146,11 +166,12 @@ struct DevBuf {
 
 struct Workspace {
     DevBuf q, sel, nsel, cmp, list_count, cursor, group_offsets, probe_offsets, group_queries, probe_slot, items,
-        n_items, part_key, D, I, scores, probe_ids, nprobe, top1, thr, gq, cand_key, cand_count, qnorm, flags, redo, trace;
+        n_items, part_key, D, I, scores, probe_ids, nprobe, top1, thr, gq, cand_key, cand_count, qnorm, flags, redo, trace,
+        seed_items, seed_out;
     void release() {
         for (DevBuf* b : {&q, &sel, &nsel, &cmp, &list_count, &cursor, &group_offsets, &probe_offsets, &group_queries,
                           &probe_slot, &items, &n_items, &part_key, &D, &I, &scores, &probe_ids, &nprobe, &top1, &thr, &gq,
-                          &cand_key, &cand_count, &qnorm, &flags, &redo, &trace})
+                          &cand_key, &cand_count, &qnorm, &flags, &redo, &trace, &seed_items, &seed_out})
             b->release();
     }
 };
@@ -223,9 +244,23 @@ struct lira_index {
     bool tc_force_sync = false;  // next tensor-core attempt uses the exact pair count (after a truncated / inexact optimistic run)
     bool tc_ok = false;          // the tensor-core scan can serve this index (tc_mode != 0)
     int tc_mode = 0;             // 1: exact (small integers, bit-identical results); 2: approximate filter + exact re-rank (real-valued data)
+    // byte-valued data (tc_mode 1 with every value in [0, 255], d <= 256): the integer tensor-core scan (u8_scan_kernels.cuh)
+    // streams a one-byte-per-component shadow copy; the fp16 shadow copy is then built only when a batch needs it
+    bool u8_ok = false;
+    bool has16 = false;          // vecs16 / vaug exist
+    bool has8 = false;           // vecs8 / nv_i exist
+    bool prefer_u8 = false;      // exact-kNN handles: the byte copy is the one built at create time
+    uint8_t* vecs8 = nullptr;    // [E + 256, d8]
+    int* nv_i = nullptr;         // [E + 256] |v|^2 (L2) or 0 (IP)
+    int d8 = 0;                  // round_up(d, 16)
+    int u8_max_nseg = 1;         // most row segments (of U8_SEG_ROWS rows) any list is cut into
+    long long u8_nseg_total = 0; // segments of all lists
+    int u8_item_q() const { return (U8_A_KB / ((d8 + U8_KB - 1) / U8_KB)) * U8_M; }   // queries per work item: 512 (d <= 128) or 256
+    CUtensorMap tmap8;
     float tc_sigma = 1.0f;       // power-of-two scale of the fp16 shadow copy
     float tc_vmax = 0.0f;        // largest |v| of the index (mode 2: error margin)
     bool use_tc = true;
+    bool last_u8 = false;        // the last tensor-core batch ran the byte scan
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
     int last_redo = 0;           // queries of the last tensor-core batch redone on the CUDA cores
     bool timing = false, timing_pending = false;
@@ -282,6 +317,10 @@ static int init_kernels(int device) {
     rc |= set_smem(tc_scan_kernel<false, false>, TC_SMEM_BYTES);
     rc |= set_smem(tc_scan_kernel<false, true>, TC_SMEM_BYTES);
     rc |= set_smem(tc_scan_kernel<true, false>, TC_SMEM_BYTES);
+    rc |= set_smem(u8_scan_kernel<true, false>, u8_smem_bytes(true));
+    rc |= set_smem(u8_scan_kernel<false, false>, u8_smem_bytes(false));
+    rc |= set_smem(u8_scan_kernel<true, true>, u8_smem_bytes(true));
+    rc |= set_smem(u8_scan_kernel<false, true>, u8_smem_bytes(false));
     rc |= set_smem(dense_tile_kernel<64, OP_L2, EPI_FEATURE>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<32, OP_DOT, EPI_BIAS_RELU>, DENSE_SMEM_BYTES);
     rc |= set_smem(dense_tile_kernel<64, OP_DOT, EPI_BIAS_SIGMOID>, DENSE_SMEM_BYTES);
@@ -550,7 +589,7 @@ static int launch_merge(const MergeParams& mp, cudaStream_t st) {
 // of (query, list) pairs. `probe_offsets_out` is the CSR the merge must use.
 static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const ProbeSpec& ps, int tile, long long* d_cmp,
                           long long* P_out, const long long** probe_offsets_out, int* extra_flag_host,
-                          const int* d_extra_flag, const int* d_mask, cudaStream_t st, int* d_trunc_flag = nullptr) {
+                          const int* d_extra_flag, const int* d_mask, cudaStream_t st, int* d_trunc_flag = nullptr, int seg_rows = 0) {
     LIRA_REQUIRE(Q >= 0 && Q < (1ll << 31), "Q out of range");
     const int B = h->B;
     const int warps = 8;
@@ -622,7 +661,8 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
     const size_t Ps = (size_t)std::max<long long>(P, 1);
     if (int rc = ws.group_queries.ensure(Ps * 4)) return rc;
     if (int rc = ws.probe_slot.ensure(Ps * 4)) return rc;
-    const size_t max_items = Ps / 8 + B + 1;  // generous: also covers a later re-tiling with a smaller tile
+    size_t max_items = Ps / 8 + B + 1;  // generous: also covers a later re-tiling with a smaller tile
+    if (seg_rows > 0) max_items = std::max(max_items, (Ps / tile + 1) * (size_t)h->u8_max_nseg + (size_t)h->u8_nseg_total + B + 1);
     if (int rc = ws.items.ensure(max_items * sizeof(ScanItem))) return rc;
 
     if (ps.kind == 0) {
@@ -650,7 +690,7 @@ static int prepare_groups(lira_index* h, Workspace& ws, long long Q, const Probe
     }
     build_items_kernel<<<1, 1024, 0, st>>>(h->d_list_order, ws.group_offsets.as<long long>(), h->d_offsets, B, tile,
                                            ws.items.as<ScanItem>(), ws.n_items.as<int>(),
-                                           (unsigned long long*)((char*)ws.n_items.p + 64));
+                                           (unsigned long long*)((char*)ws.n_items.p + 64), seg_rows);
     LIRA_LAUNCH_CHECK();
     return 0;
 }
@@ -699,6 +739,11 @@ static int run_grouped_scan(lira_index* h, const float* d_q, long long ldq, long
     return simt_scan(h, h->ws, d_q, ldq, *P_out, k, store_local, 0, timed, st);
 }
 
+static int ensure_fp16_shadow(lira_index* h);
+static int ensure_u8_shadow(lira_index* h);
+static constexpr int U8_CAPK = 64;            // byte scan: candidate slots per (query, list) pair, k <= 16
+static constexpr int U8_CAPP = 128;           //            ... k > 16 (exhaustive probe sets over base segments)
+static constexpr int U8_SEED_LISTS = 16;      // byte copy, exhaustive probe sets: lists (base segments) the seed pass scans
 static constexpr int TC_SEED_ROWS = 384;      // CUDA-core seed (k > 16): rows of each of the two best probed lists
 static constexpr int TC_SEED_ROWS_MAIN = 2048;   // seed pass on the filter's own work items: first rows of every probed list (0 = all; measured best)
 static constexpr int TC_SEED_ROWS_TC = 0;     // tensor-core seed (k <= 16): rows of each of the two best probed lists (0 = all: the pass streams
@@ -717,7 +762,34 @@ struct TcStage {   // one tensor-core batch after the grouping: what the seed / 
     float margin_c = 0.f, margin_abs = 0.f;
     int* seed_counter = nullptr;     // zeroed ticket counters of the two passes
     int* filter_counter = nullptr;
+    bool u8 = false;                 // byte-valued index and batch: the integer tensor-core scan (u8_scan_kernels.cuh)
+    bool counts_zeroed = false;      // byte scan: the pair counters were zeroed by the front end (fused flow)
+    int seg_rows = U8_SEG_ROWS;      // byte scan: rows of a list per work item (exhaustive probe sets: whole lists)
 };
+
+static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg) {
+    U8Params up;
+    up.group_queries = ws.group_queries.as<int>();
+    up.list_offsets = h->d_offsets;
+    up.items = ws.items.as<ScanItem>();
+    up.n_items = ws.n_items.as<int>();
+    up.work_counter = nullptr;
+    up.nk = (h->d8 + U8_KB - 1) / U8_KB;
+    up.d8 = h->d8;
+    up.seg_rows = sg.seg_rows;
+    up.nv = h->nv_i;
+    up.dbg = ws.n_items.as<int>() + 10;
+    up.qnorm = ws.qnorm.as<float>();
+    up.thr = ws.thr.as<uint32_t>();
+    up.cand_key = nullptr;
+    up.cand_count = nullptr;
+    up.seed_out = nullptr;
+    up.cap = 0;
+    up.k = sg.k;
+    up.is_ip = h->metric == LIRA_METRIC_IP;
+    up.exp = 0;
+    return up;
+}
 
 // approximate mode: |accumulator - exact| <= M(q) = margin_c sqrt(sigma^2 |q|^2) + margin_abs (units of the scaled copy):
 // operand rounding (2^-11 relative each, 5 % slack), fp32 accumulation inside the tensor core (2^-21 per term, generous),
@@ -756,6 +828,15 @@ static int tc_seed_main(lira_index* h, Workspace& ws, const TcStage& sg, cudaStr
     sp.k = sg.k;
     sp.is_ip = h->metric == LIRA_METRIC_IP;
     if (getenv("LIRA_TC_NO_SEED")) return 0;
+    if (sg.u8) {
+        U8Params up = u8_params(h, ws, sg);
+        up.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) & ~1 : 0;
+        up.work_counter = sg.seed_counter;
+        if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, up);
+        else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, up);
+        LIRA_LAUNCH_CHECK();
+        return 0;
+    }
     tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
     LIRA_LAUNCH_CHECK();
     return 0;
@@ -767,9 +848,13 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
     const int k = sg.k;
     const bool approx = h->tc_mode == 2;
     // one private candidate region per (pair, column part); every valid pair's owner writes its count
-    const int cap = k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP;   // k <= 16: full regions are compacted in the kernel
-    if (int rc = ws.cand_key.ensure((size_t)P * TC_PARTS * cap * 8)) return rc;
-    if (int rc = ws.cand_count.ensure((size_t)P * TC_PARTS * 4)) return rc;
+    // (byte scan: ONE region per pair, slots taken with atomics, counters zeroed beforehand)
+    const int cap = sg.u8 ? (k <= TC_KMAX_TIGHTEN ? U8_CAPK : U8_CAPP) : (k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP);   // fp16, k <= 16: full regions are compacted in the kernel
+    const int parts = sg.u8 ? 1 : TC_PARTS;
+    h->last_u8 = sg.u8;
+    if (int rc = ws.cand_key.ensure((size_t)P * parts * cap * 8)) return rc;
+    if (int rc = ws.cand_count.ensure((size_t)P * parts * 4)) return rc;
+    if (sg.u8 && !sg.counts_zeroed) LIRA_CUDA_OK(cudaMemsetAsync(ws.cand_count.p, 0, (size_t)P * 4, st));
     TcParams tp;
     tp.group_queries = ws.group_queries.as<int>();
     tp.list_offsets = h->d_offsets;
@@ -796,6 +881,16 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
         tp.trace = ws.trace.as<long long>();
     }
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[0], st));
+    if (sg.u8) {
+        U8Params up = u8_params(h, ws, sg);
+        up.work_counter = sg.filter_counter;
+        up.cand_key = tp.cand_key;
+        up.cand_count = tp.cand_count;
+        up.cap = cap;
+        up.exp = tp.exp;
+        if (up.is_ip) u8_scan_kernel<false, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, up);
+        else u8_scan_kernel<false, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, up);
+    } else
     if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
     else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
     LIRA_LAUNCH_CHECK();
@@ -806,7 +901,9 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
                     h->vecs, (long long)h->ds, sg.d_q, sg.ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, sg.margin_c, sg.margin_abs,
                     1.0f / (h->tc_sigma * h->tc_sigma)};
     const int warps = 8;
-    if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    if (sg.u8 && k <= 32) refine_topk_kernel<1, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else if (sg.u8) refine_topk_kernel<4, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     LIRA_LAUNCH_CHECK();
@@ -823,16 +920,28 @@ static void tc_debug_stats(lira_index* h, Workspace& ws, long long Q, long long 
 // the batch does not qualify at all.
 static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q, const ProbeSpec& ps, int k, int dedup,
                      float* d_D, long long* d_I, int* d_nprobe, long long* d_cmp, bool* done, int* n_redo, bool* retry,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool allow_u8 = true, bool* u8_tried = nullptr) {
     *done = false;
     *n_redo = 0;
     *retry = false;
     if (!h->tc_ok || Q < 256) return 0;
     const bool approx = h->tc_mode == 2;
     if (approx && k > TC_KMAX_TIGHTEN) return 0;   // the margin logic lives in the compaction path (k <= 16)
+    // byte-valued index: the integer tensor-core scan. Threshold / top-n / explicit probe sets need k <= 16 (per-list bounds of
+    // the in-kernel seed); exhaustive probe sets (exact kNN over disjoint base segments) pool the seed candidates of the first
+    // U8_SEED_LISTS lists, any k <= 128, as long as those lists hold enough candidates
+    const int u8_seed_lists = std::min(h->B, U8_SEED_LISTS);
+    // Measured (profiles/r2_u8_scan_notes.md): with its per-column norm subtraction the byte scan's epilogue costs ~3x the fp16
+    // scan's, so for threshold / top-n probe sets it only matches the fp16 scan; it is the default for exhaustive probe sets
+    // (no CUDA-core seed pass, half the operand bytes) and opt-in (LIRA_U8_SEARCH=1) for the rest.
+    const bool use_u8 = h->u8_ok && allow_u8 &&
+                        (ps.kind == 2 ? (u8_seed_lists * 16 >= k + 16 && h->E >= 2048) : (k <= TC_KMAX_TIGHTEN && getenv("LIRA_U8_SEARCH") != nullptr));
+    if (u8_tried) *u8_tried = use_u8;
+    if (use_u8) { if (int rc = ensure_u8_shadow(h)) return rc; }
+    else if (int rc = ensure_fp16_shadow(h)) return rc;
     // exhaustive probe sets (exact kNN over base segments) with k > 16: no in-kernel tightening, so the static seed must be
     // good: the CUDA-core seed scans two whole segments (below); a segment shorter than that would make the bound loose
-    if (ps.kind == 2 && k > TC_KMAX_TIGHTEN && h->E < 4 * 8192) return 0;
+    if (!use_u8 && ps.kind == 2 && k > TC_KMAX_TIGHTEN && h->E < 4 * 8192) return 0;
     LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
     Workspace& ws = h->ws;
     if (int rc = ws.qnorm.ensure((size_t)Q * 4)) return rc;
@@ -853,8 +962,11 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     int q_exact = 1;
     ProbeSpec psf = ps;
     psf.d_bad_flag = ws.flags.as<int>() + 3;
-    if (int rc = prepare_groups(h, ws, Q, psf, TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st,
-                                optimistic ? ws.flags.as<int>() + 2 : nullptr)) return rc;
+    // (byte scan: items of up to 512 queries x a segment of the list's rows; exhaustive probe sets keep whole lists, since
+    //  their pooled seed addresses one set of values per (query, list) pair)
+    const int u8_seg_rows = ps.kind == 2 ? (1 << 30) : U8_SEG_ROWS;
+    if (int rc = prepare_groups(h, ws, Q, psf, use_u8 ? h->u8_item_q() : TC_M, d_cmp, &P, &po, &q_exact, ws.flags.as<int>(), nullptr, st,
+                                optimistic ? ws.flags.as<int>() + 2 : nullptr, use_u8 ? u8_seg_rows : 0)) return rc;
     if (!q_exact || P == 0) return 0;  // not exact in fp16 (or nothing probed): exact CUDA-core path
     if (int rc = save_stats(h, ws, st)) return rc;
     if (ps.kind == 1) {
@@ -878,25 +990,62 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     int* d_ok = approx ? ws.flags.as<int>() : nullptr;
     Workspace& sw = h->ws_seed;
     // ---- queries in group order (one TMA box per tile) ----
-    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
-    gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
-                                                                                         ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale, d_ok);
-    LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
-    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
+    if (use_u8) {
+        // (the flag is CLEARED when a query value is not an integer in [0, 255]: the batch then takes the fp16 route)
+        if (int rc = ws.gq.ensure((size_t)(P + U8_ITEM_Q) * h->d8)) return rc;
+        gather_group_queries_u8_kernel<<<grid_for(P * (h->d8 / 4), 256, 148 * 16), 256, 0, st>>>(
+            d_q, ldq, h->ds, ws.group_queries.as<int>(), P, ws.group_offsets.as<long long>() + h->B, ws.gq.as<uint8_t>(), h->d8, ws.flags.as<int>());
+        LIRA_LAUNCH_CHECK();
+        if (int rc = make_tmap_u8(&tmap_q, ws.gq.p, P, h->d8, h->d8)) return rc;
+    } else {
+        if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
+        gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
+                                                                                             ws.group_offsets.as<long long>() + h->B, ws.gq.as<__half>(), h->d16, qscale, d_ok);
+        LIRA_LAUNCH_CHECK();
+        if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
+    }
     // Seed, k <= 16 and probe sets that are a small part of the index: the seed pass runs on the SAME work items as the filter
     // pass (no second grouping, no second gather) and EVERY (query, list) pair takes part: the k-th smallest of the 64 group
     // minima of a query's row in a list bounds the final k-th score, the smallest over the query's lists wins (atomicMin).
     // Exhaustive probe sets (exact kNN) keep the two-segment seed below: a full extra pass would double their work.
-    const bool seed_on_main = k <= TC_KMAX_TIGHTEN && ps.kind != 2 && !getenv("LIRA_TC_SEED_SEPARATE");
+    const bool seed_on_main = k <= TC_KMAX_TIGHTEN && ps.kind != 2 && (use_u8 || !getenv("LIRA_TC_SEED_SEPARATE"));
     if (seed_on_main) {
         fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u /* f32_to_ordered(+inf) */);
         LIRA_LAUNCH_CHECK();
         TcStage ss;
-        ss.k = k; ss.tmap_q = &tmap_q; ss.margin_c = margin_c; ss.margin_abs = margin_abs;
+        ss.k = k; ss.tmap_q = &tmap_q; ss.margin_c = margin_c; ss.margin_abs = margin_abs; ss.u8 = use_u8; ss.seg_rows = u8_seg_rows;
         ss.seed_counter = ws.n_items.as<int>() + 2;   // (prepare_groups zeroes the whole control block)
         if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));
         if (int rc = tc_seed_main(h, ws, ss, st)) return rc;
+    } else if (use_u8) {
+        // ---- exhaustive probe sets on the byte copy: seed pass over the first lists only, candidates pooled per query ----
+        const int S = u8_seed_lists;
+        const size_t max_items = (size_t)S * ((size_t)(Q + h->u8_item_q() - 1) / h->u8_item_q()) + 1;
+        if (int rc = ws.seed_items.ensure(max_items * sizeof(ScanItem))) return rc;
+        if (int rc = ws.seed_out.ensure((size_t)S * Q * U8_PARTS * 4 * 4)) return rc;
+        int* ctl = ws.n_items.as<int>();   // [4] seed items, [2] seed tickets (zeroed by prepare_groups)
+        if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));
+        u8_seed_items_kernel<<<grid_for((long long)h->B * ((Q + h->u8_item_q() - 1) / h->u8_item_q()), 256), 256, 0, st>>>(
+            ws.items.as<ScanItem>(), ctl, S, ws.seed_items.as<ScanItem>(), ctl + 4);
+        LIRA_LAUNCH_CHECK();
+        TcStage ss;
+        ss.k = k; ss.u8 = true; ss.seg_rows = u8_seg_rows;
+        U8Params up = u8_params(h, ws, ss);
+        up.items = ws.seed_items.as<ScanItem>();
+        up.n_items = ctl + 4;
+        up.work_counter = ctl + 2;
+        up.seed_out = ws.seed_out.as<int>();
+        if (!getenv("LIRA_TC_NO_SEED")) {
+            if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, up);
+            else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, up);
+            LIRA_LAUNCH_CHECK();
+            u8_seed_select_kernel<<<(int)((Q + 7) / 8), 256, 0, st>>>(ws.seed_out.as<int>(), (int)Q, S, k, ws.thr.as<uint32_t>());
+            LIRA_LAUNCH_CHECK();
+        } else {
+            fill_u32_kernel<<<grid_for(Q, 256), 256, 0, st>>>(ws.thr.as<uint32_t>(), Q, 0xFF800000u);
+            LIRA_LAUNCH_CHECK();
+        }
     } else if (k <= TC_KMAX_TIGHTEN) {
         // ---- seed on the tensor cores: first rows of every query's best list, 16 group minima per row ----
         if (int rc = sw.probe_offsets.ensure((size_t)(Q + 1) * 8)) return rc;
@@ -970,8 +1119,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
                                                                 ws.top1.as<int>(), (int)Q, k, ws.thr.as<uint32_t>());
         LIRA_LAUNCH_CHECK();
     }
-    if (!seed_on_main && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));   // (the other seeds' own grouping is not part of the scan time)
+    if (!seed_on_main && !use_u8 && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));   // (the other seeds' own grouping is not part of the scan time)
     TcStage sg;
+    sg.u8 = use_u8; sg.seg_rows = u8_seg_rows;
     sg.Q = Q; sg.P = P; sg.po = po; sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq; sg.d_D = d_D; sg.d_I = d_I;
     sg.redo_count = ws.flags.as<int>() + 1; sg.tmap_q = &tmap_q; sg.margin_c = margin_c; sg.margin_abs = margin_abs;
     sg.filter_counter = ws.n_items.as<int>() + 1;
@@ -983,7 +1133,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     LIRA_CUDA_OK(cudaStreamSynchronize(st));
     LIRA_REQUIRE(fl[3] == 0, "probed list id out of range");
     *n_redo = fl[1];
-    if ((optimistic && (fl[0] == 0 || fl[2] != 0)) || (approx && fl[0] == 0)) {
+    if ((optimistic && (fl[0] == 0 || fl[2] != 0)) || ((approx || use_u8) && fl[0] == 0)) {
         // the optimistic run is void: the batch is not exact in fp16 (-> the caller's CUDA-core path), or a probe set was
         // truncated (-> once more with the exact pair count and a larger cap from now on)
         if (fl[2] != 0) { h->nprobe_cap = std::min(h->B, h->nprobe_cap * 4); *retry = fl[0] != 0; }
@@ -1031,19 +1181,28 @@ static void tc_dump_trace(lira_index* h, Workspace& ws, const char* trace_path) 
 }
 
 static void tc_debug_stats(lira_index* h, Workspace& ws, long long Q, long long P, int n_redo) {
-        std::vector<uint32_t> th((size_t)Q);
-        cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
-        long long n_inf = 0;
-        for (uint32_t t : th) n_inf += (t == 0xFF800000u);
-        fprintf(stderr, "[lira] tc batch: final bound still +inf for %lld queries\n", n_inf);
-        std::vector<int> cc((size_t)P * TC_PARTS);
-        cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * TC_PARTS * 4, cudaMemcpyDeviceToHost);
-        std::vector<int> sorted(cc);
-        std::sort(sorted.begin(), sorted.end());
-        long long tot = 0;
-        for (int c : cc) tot += c;
-        fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, part) p50 %d p99 %d max %d; redo %d\n",
-                Q, P, (double)tot / Q, sorted[P * TC_PARTS / 2], sorted[(size_t)(P * TC_PARTS * 0.99)], sorted[P * TC_PARTS - 1], n_redo);
+    std::vector<uint32_t> th((size_t)Q);
+    cudaMemcpy(th.data(), ws.thr.p, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+    long long n_inf = 0;
+    for (uint32_t t : th) n_inf += (t == 0xFF800000u);
+    fprintf(stderr, "[lira] tc batch: final bound still +inf for %lld queries\n", n_inf);
+    int dbg[6] = {0, 0, 0, 0, 0, 0};
+    cudaMemcpy(dbg, ws.n_items.as<int>() + 10, 24, cudaMemcpyDeviceToHost);
+    if (dbg[1]) fprintf(stderr, "[lira] tc batch: %d of %d (warp, 32 columns) groups held a survivor; %d items, %d query tiles, %d chunks, %d units\n",
+                        dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5]);
+    long long n_slots = P;   // P may be an upper bound (fused flow): the valid pairs are the first group_offsets[B] slots
+    cudaMemcpy(&n_slots, ws.group_offsets.as<long long>() + h->B, 8, cudaMemcpyDeviceToHost);
+    P = std::min(P, n_slots);
+    if (P <= 0) return;
+    const int parts = h->last_u8 ? 1 : TC_PARTS;   // (byte scan: one region per pair)
+    std::vector<int> cc((size_t)P * parts);
+    cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * parts * 4, cudaMemcpyDeviceToHost);
+    std::vector<int> sorted(cc);
+    std::sort(sorted.begin(), sorted.end());
+    long long tot = 0, over32 = 0, over64 = 0;
+    for (int c : cc) { tot += c; over32 += c > 32; over64 += c > 64; }
+    fprintf(stderr, "[lira] tc batch Q=%lld P=%lld: survivors/query mean %.1f; per (pair, part) p50 %d p99 %d max %d; regions > 32: %lld, > 64: %lld; redo %d\n",
+            Q, P, (double)tot / Q, sorted[P * parts / 2], sorted[(size_t)(P * parts * 0.99)], sorted[P * parts - 1], over32, over64, n_redo);
 }
 
 // exact CUDA-core path: the whole batch (done = false), or only the queries the tensor-core pass flagged in ws.redo
@@ -1085,10 +1244,16 @@ static int search_core(lira_index* h, const float* d_q, long long ldq, long long
     bool done = false;
     int n_redo = 0;
     if (h->use_tc) {
-        bool retry = false;
-        if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st)) return rc;
+        bool retry = false, u8_tried = false;
+        if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st, true, &u8_tried)) return rc;
         if (!done && retry)
-            if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st)) return rc;
+            if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st, true, &u8_tried)) return rc;
+        if (!done && u8_tried) {   // e.g. a query batch with values outside [0, 255]: the fp16 route may still serve it
+            h->tc_force_sync = true;
+            if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st, false)) return rc;
+            if (!done && retry)
+                if (int rc = tc_search(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, &done, &n_redo, &retry, st, false)) return rc;
+        }
     }
     if (!done || n_redo > 0)
         if (int rc = exact_fallback(h, d_q, ldq, Q, ps, k, dedup, d_D, d_I, d_nprobe, d_cmp, st, done)) return rc;
@@ -1126,6 +1291,9 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     LIRA_REQUIRE((ldq % 4) == 0 && ((uintptr_t)d_q & 15) == 0, "queries must be 16-byte aligned with ld % 4 == 0");
     const int B = h->B;
     const bool approx = h->tc_mode == 2;
+    const bool u8 = h->u8_ok && getenv("LIRA_U8_SEARCH") != nullptr;
+    if (u8) { if (int rc = ensure_u8_shadow(h)) return rc; }
+    else if (int rc = ensure_fp16_shadow(h)) return rc;
     Workspace& ws = h->ws;
     const int cap = std::min(B, h->nprobe_cap);
     const long long P = Q * (long long)cap;   // bound: sizes the per-pair buffers
@@ -1143,8 +1311,12 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     if (int rc = ws.n_items.ensure(128)) return rc;
     if (int rc = ws.group_queries.ensure((size_t)P * 4)) return rc;
     if (int rc = ws.probe_slot.ensure((size_t)P * 4)) return rc;
-    if (int rc = ws.items.ensure(((size_t)P / 8 + B + 1) * sizeof(ScanItem))) return rc;
-    if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
+    size_t max_items = (size_t)P / 8 + B + 1;
+    if (u8) max_items = std::max(max_items, ((size_t)P / h->u8_item_q() + 1) * (size_t)h->u8_max_nseg + (size_t)h->u8_nseg_total + B + 1);
+    if (int rc = ws.items.ensure(max_items * sizeof(ScanItem))) return rc;
+    if (u8)
+        if (int rc = ws.cand_count.ensure((size_t)P * 4)) return rc;
+    if (int rc = ws.gq.ensure(u8 ? (size_t)(P + U8_ITEM_Q) * h->d8 : (size_t)(P + TC_M) * h->d16 * 2)) return rc;
     // control block: [0] work items, [1] filter tickets, [2] seed tickets, +64 B {E_p, pairs}, +96 B status words:
     // [24] batch not exact in fp16, [25] queries left for the exact path, [26] a probe set was truncated, [27] largest selection of a query
     LIRA_CUDA_OK(cudaMemsetAsync(ws.n_items.p, 0, 128, st));
@@ -1162,7 +1334,7 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     if (int rc = model_forward_tc(m, d_q, ldq, Q, nullptr, 0, nullptr, 0, st, /*prepped=*/true, &fs)) return rc;
     FinishSelectParams fp{ws.nsel.as<int>(), ws.sel.as<int>(), cap, fs.mode, ws.top1.as<unsigned long long>(), ws.list_count.as<int>(),
                           (int)Q, B, ws.probe_offsets.as<long long>(), ws.group_offsets.as<long long>(), fl_dev + 2, h->d_list_order,
-                          h->d_offsets, TC_M, ws.items.as<ScanItem>(), ctl, (unsigned long long*)((char*)ws.n_items.p + 64)};
+                          h->d_offsets, u8 ? h->u8_item_q() : TC_M, u8 ? U8_SEG_ROWS : 0, ws.items.as<ScanItem>(), ctl, (unsigned long long*)((char*)ws.n_items.p + 64)};
     finish_select_kernel<<<1, 1024, 0, st>>>(fp);
     LIRA_LAUNCH_CHECK();
     if (int rc = save_stats(h, ws, st)) return rc;
@@ -1170,15 +1342,17 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     const float qscale = (is_ip ? 1.0f : 2.0f) * h->tc_sigma;
     ScatterQueriesParams sc{d_q, (long)ldq, h->ds, ws.sel.as<int>(), ws.nsel.as<int>(), cap, ws.probe_offsets.as<long long>(),
                             ws.group_offsets.as<long long>(), h->d_offsets, ws.cursor.as<int>(), ws.group_queries.as<int>(),
-                            ws.probe_slot.as<int>(), ws.probe_ids.as<int>(), ws.gq.as<__half>(), h->d16, qscale, approx ? fl_dev : nullptr,
+                            ws.probe_slot.as<int>(), ws.probe_ids.as<int>(), ws.gq.as<__half>(), h->d16, qscale, u8 ? ws.cand_count.as<int>() : nullptr, u8 ? ws.gq.as<uint8_t>() : nullptr, h->d8,
+                            (approx || u8) ? fl_dev : nullptr,
                             d_nprobe, d_cmp, (int)Q};
     scatter_queries_kernel<<<qgrid, warps * 32, 0, st>>>(sc);
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
-    if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
+    if (u8) { if (int rc = make_tmap_u8(&tmap_q, ws.gq.p, P, h->d8, h->d8)) return rc; }
+    else if (int rc = make_tmap_f16(&tmap_q, ws.gq.as<__half>(), P, h->d16, h->d16)) return rc;
     TcStage sg;
     sg.Q = Q; sg.P = P; sg.po = ws.probe_offsets.as<long long>(); sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq;
-    sg.d_D = d_D; sg.d_I = d_I; sg.redo_count = fl_dev + 1; sg.tmap_q = &tmap_q;
+    sg.d_D = d_D; sg.d_I = d_I; sg.redo_count = fl_dev + 1; sg.tmap_q = &tmap_q; sg.u8 = u8; sg.counts_zeroed = u8;
     tc_margins(h, &sg.margin_c, &sg.margin_abs);
     sg.seed_counter = ctl + 2;
     sg.filter_counter = ctl + 1;
@@ -1301,6 +1475,56 @@ static int upload_rows(DevBuf& buf, const float* host, long long n, int d, int d
     return 0;
 }
 
+// the fp16 shadow copy of the list rows + their augmented-K blocks (tc_scan_kernels.cuh); built at create time, or on the
+// first batch that needs it when the index also has the byte copy
+static int ensure_fp16_shadow(lira_index* h) {
+    if (h->has16 || !h->tc_ok) return 0;
+    LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)std::max<long long>(h->E, 1) * 32));
+    LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
+    LIRA_CUDA_OK(cudaMalloc(&h->vecs16, (size_t)std::max<long long>(h->E, 1) * h->d16 * 2));
+    std::vector<__half> a(128 * 16, __float2half(0.0f));
+    for (int r = 0; r < 128; ++r) {
+        a[r * 16] = __float2half(h->tc_mode == 1 ? -2048.0f : -1.0f);
+        a[r * 16 + 1] = __float2half(-1.0f);
+    }
+    LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    shadow_rows_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, h->tc_sigma,
+                                                                            h->tc_mode == 1, h->vecs16, h->d16, h->vaug);
+    g_launches.fetch_add(1);
+    LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
+    if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
+    if (int rc = make_tmap_f16(&h->tmap16, h->vecs16, h->E, h->d16, h->d16)) return rc;
+    h->has16 = true;
+    return 0;
+}
+
+// the byte shadow copy of the list rows + their |v|^2 as int32 (u8_scan_kernels.cuh)
+static int ensure_u8_shadow(lira_index* h) {
+    if (h->has8 || !h->u8_ok) return 0;
+    h->u8_max_nseg = 1;
+    h->u8_nseg_total = 0;
+    for (int b = 0; b < h->B; ++b) {
+        const long long nseg = std::max<long long>(1, (h->h_offsets[b + 1] - h->h_offsets[b] + U8_SEG_ROWS - 1) / U8_SEG_ROWS);
+        h->u8_max_nseg = (int)std::max<long long>(h->u8_max_nseg, nseg);
+        h->u8_nseg_total += nseg;
+    }
+    const size_t rows = (size_t)h->E + U8_NS;   // (a box may reach past the last entry)
+    LIRA_CUDA_OK(cudaMalloc(&h->vecs8, rows * h->d8));
+    LIRA_CUDA_OK(cudaMalloc(&h->nv_i, rows * 4));
+    LIRA_CUDA_OK(cudaMemsetAsync(h->vecs8 + (size_t)h->E * h->d8, 0, (size_t)U8_NS * h->d8, h->stream));
+    LIRA_CUDA_OK(cudaMemsetAsync(h->nv_i + h->E, 0, (size_t)U8_NS * 4, h->stream));
+    if (h->E > 0) {
+        shadow_rows_u8_kernel<<<grid_for(h->E * (h->d8 / 4), 256, 148 * 16), 256, 0, h->stream>>>(
+            h->vecs, h->ds, h->ds, h->E, h->vnorm, h->metric == LIRA_METRIC_IP, h->vecs8, h->d8, h->nv_i);
+        g_launches.fetch_add(1);
+    }
+    LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (int rc = make_tmap_u8(&h->tmap8, h->vecs8, (long long)rows, h->d8, h->d8)) return rc;
+    h->has8 = true;
+    return 0;
+}
+
 static int index_finish_create(lira_index* h, const long long* offsets) {
     h->h_offsets.assign(offsets, offsets + h->B + 1);
     LIRA_CUDA_OK(cudaMalloc(&h->d_offsets, (size_t)(h->B + 1) * 8));
@@ -1349,23 +1573,26 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
         h->tc_mode = 2;
     }
     h->tc_ok = h->tc_mode != 0;
-    if (h->tc_ok) {
-        LIRA_CUDA_OK(cudaMalloc(&h->vaug, (size_t)h->E * 32));
-        LIRA_CUDA_OK(cudaMalloc(&h->aaug, 128 * 32));
-        LIRA_CUDA_OK(cudaMalloc(&h->vecs16, (size_t)h->E * h->d16 * 2));
-        std::vector<__half> a(128 * 16, __float2half(0.0f));
-        for (int r = 0; r < 128; ++r) {
-            a[r * 16] = __float2half(h->tc_mode == 1 ? -2048.0f : -1.0f);
-            a[r * 16 + 1] = __float2half(-1.0f);
-        }
-        LIRA_CUDA_OK(cudaMemcpy(h->aaug, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
-        shadow_rows_kernel<<<grid_for(h->E, 128, 148 * 16), 128, 0, h->stream>>>(h->vecs, h->ds, h->ds, h->E, h->vnorm, h->tc_sigma,
-                                                                                h->tc_mode == 1, h->vecs16, h->d16, h->vaug);
+    // byte-valued data: the u8 shadow copy (and no fp16 copy until a batch needs one)
+    h->d8 = (h->d + 15) / 16 * 16;
+    if (h->tc_mode == 1 && h->d8 <= U8_MAX_D && !getenv("LIRA_NO_U8")) {
+        int* d_u8 = nullptr;
+        LIRA_CUDA_OK(cudaMalloc(&d_u8, 4));
+        int one = 1;
+        LIRA_CUDA_OK(cudaMemcpy(d_u8, &one, 4, cudaMemcpyHostToDevice));
+        check_u8_kernel<<<grid_for(h->E * ((h->d + 3) / 4), 256, 148 * 16), 256, 0, h->stream>>>(h->vecs, h->ds, h->d, h->E, d_u8);
         g_launches.fetch_add(1);
         LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
-        if (int rc = make_tmap_aug(&h->tmap_vaug, h->vaug, h->E)) return rc;
-        if (int rc = make_tmap_aug(&h->tmap_aaug, h->aaug, 128)) return rc;
-        if (int rc = make_tmap_f16(&h->tmap16, h->vecs16, h->E, h->d16, h->d16)) return rc;
+        LIRA_CUDA_OK(cudaMemcpy(&one, d_u8, 4, cudaMemcpyDeviceToHost));
+        cudaFree(d_u8);
+        h->u8_ok = one == 1;
+    }
+    // which shadow copy is built now: the byte copy for exact-kNN handles (their exhaustive probe sets run the byte scan),
+    // the fp16 copy for everything else; the other one is built by the first batch that needs it
+    if (h->u8_ok && h->prefer_u8) {
+        if (int rc = ensure_u8_shadow(h)) return rc;
+    } else if (h->tc_ok) {
+        if (int rc = ensure_fp16_shadow(h)) return rc;
     }
     cudaDeviceProp prop;
     LIRA_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
@@ -1467,8 +1694,14 @@ int lira_index_create_from_assign(const float* base, int64_t N, int d, const int
     return lira_index_create(base, N, d, cnt.data(), ids.data(), B, metric, device, out);
 }
 
+static int index_create_dev_impl(const float* d_vecs, int64_t ld, int d, const int64_t* list_offsets, const int32_t* d_ids,
+                                 int B, int metric, int device, lira_index_t** out, bool prefer_u8);
 int lira_index_create_dev(const float* d_vecs, int64_t ld, int d, const int64_t* list_offsets, const int32_t* d_ids,
                           int B, int metric, int device, lira_index_t** out) {
+    return index_create_dev_impl(d_vecs, ld, d, list_offsets, d_ids, B, metric, device, out, false);
+}
+static int index_create_dev_impl(const float* d_vecs, int64_t ld, int d, const int64_t* list_offsets, const int32_t* d_ids,
+                                 int B, int metric, int device, lira_index_t** out, bool prefer_u8) {
     LIRA_REQUIRE(out && d_vecs && list_offsets && d_ids && B >= 1 && d >= 1, "bad argument");
     LIRA_REQUIRE(ld >= d && (ld % 4) == 0 && ((uintptr_t)d_vecs & 15) == 0, "device vectors need ld % 4 == 0 and 16-byte alignment");
     LIRA_REQUIRE(metric == LIRA_METRIC_L2 || metric == LIRA_METRIC_IP, "metric must be LIRA_METRIC_L2 or LIRA_METRIC_IP");
@@ -1477,6 +1710,7 @@ int lira_index_create_dev(const float* d_vecs, int64_t ld, int d, const int64_t*
     if (int rc = validate_offsets(list_offsets, B, &E)) return rc;
     lira_index* h = new lira_index();
     h->device = device; h->B = B; h->d = d; h->ds = (int)ld; h->metric = metric; h->E = E; h->owns = false;
+    h->prefer_u8 = prefer_u8;
     h->vecs = const_cast<float*>(d_vecs);
     h->ids = const_cast<int*>(d_ids);
     int rc = 0;
@@ -1500,6 +1734,8 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->vnorm);
     cudaFree(h->vaug);
     cudaFree(h->vecs16);
+    cudaFree(h->vecs8);
+    cudaFree(h->nv_i);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     for (PendingBatch& pb : h->pending) { if (pb.h_flags) cudaFreeHost(pb.h_flags); if (pb.ev) cudaEventDestroy(pb.ev); }
@@ -1542,6 +1778,8 @@ int lira_index_last_path(const lira_index_t* h) { return h ? h->last_path : -1; 
 int lira_index_last_redo(const lira_index_t* h) { return h ? h->last_redo : -1; }
 int lira_index_tensor_core_eligible(const lira_index_t* h) { return h ? (h->tc_ok ? 1 : 0) : -1; }
 int lira_index_tensor_core_mode(const lira_index_t* h) { return h ? h->tc_mode : -1; }
+int lira_index_byte_scan_eligible(const lira_index_t* h) { return h ? (h->u8_ok ? 1 : 0) : -1; }
+int lira_index_last_scan_kind(const lira_index_t* h) { return h ? (h->last_path == 0 ? 0 : (h->last_u8 ? 2 : 1)) : -1; }
 
 int lira_index_set_timing(lira_index_t* h, int enable) {
     LIRA_REQUIRE(h, "null index");
@@ -2165,7 +2403,7 @@ static int knn_finish_create(lira_knn_index* kn) {
     const int nseg = (int)((N + seg - 1) / seg);
     std::vector<int64_t> off(nseg + 1);
     for (int s = 0; s <= nseg; ++s) off[s] = std::min<long long>((long long)s * seg, N);
-    if (int r2 = lira_index_create_dev(kn->base, kn->ds, kn->d, off.data(), kn->dids.as<int>(), nseg, kn->metric, kn->device, &kn->index)) return r2;
+    if (int r2 = index_create_dev_impl(kn->base, kn->ds, kn->d, off.data(), kn->dids.as<int>(), nseg, kn->metric, kn->device, &kn->index, true)) return r2;
     kn->seg = seg;
     return 0;
 }
@@ -2222,6 +2460,7 @@ int lira_knn_free(lira_knn_t* kn) {
 int64_t lira_knn_ntotal(const lira_knn_t* kn) { return kn ? kn->N : -1; }
 int lira_knn_last_path(const lira_knn_t* kn) { return kn ? kn->last_path : -1; }
 int lira_knn_last_redo(const lira_knn_t* kn) { return (kn && kn->index) ? kn->index->last_redo : -1; }
+int lira_knn_last_scan_kind(const lira_knn_t* kn) { return (kn && kn->index) ? lira_index_last_scan_kind(kn->index) : -1; }
 int lira_knn_set_use_tensor_cores(lira_knn_t* kn, int enable) {
     LIRA_REQUIRE(kn && kn->index, "null handle");
     kn->index->use_tc = enable != 0;
@@ -2235,7 +2474,13 @@ static int knn_search_impl(lira_knn_t* kn, const float* host_q, const float* d_q
     const int d = kn->d, ds = kn->ds;
     // k <= 16 on a large base: long segments (the in-kernel compaction keeps their candidate regions small), i.e. 8x fewer
     // (query, segment) pairs, regions and refine work, and larger query batches
-    const long long seg = (k <= 16 && kn->N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
+    long long seg = (k <= 16 && kn->N >= 8 * 65536 && !getenv("LIRA_KNN_SHORT_SEGMENTS")) ? 65536 : 8192;
+    if (h->u8_ok) {
+        // byte copy: the seed pass scans the first U8_SEED_LISTS segments (a sample of the base), so short segments keep it
+        // cheap; at most ~512 segments so that a batch of (query, segment) pairs still holds thousands of queries
+        seg = 8192;
+        while (kn->N / seg > 512) seg *= 2;
+    }
     if (int rc = knn_set_segments(kn, seg)) return rc;
     const int nseg = h->B;
     cudaStream_t st = st_user ? st_user : h->stream;

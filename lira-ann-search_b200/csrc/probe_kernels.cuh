@@ -356,7 +356,7 @@ __device__ __forceinline__ int tile_class(int rem) { return rem > 32 ? 64 : rem 
 // algorithmic work of SURVEY.md 8(d), reported by lira_index_last_timing.
 __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order, const long long* group_offsets,
                                                            const long long* list_offsets, int B, int tile, ScanItem* items,
-                                                           int* n_items_out, unsigned long long* stats) {
+                                                           int* n_items_out, unsigned long long* stats, int seg_rows = 0) {
     __shared__ int warp_sum[32];
     __shared__ int carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -364,17 +364,19 @@ __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order
     __syncthreads();
     for (int base = 0; base < B; base += 1024) {
         const int i = base + threadIdx.x;
-        int b = 0, g = 0, cnt = 0;
+        int b = 0, g = 0, cnt = 0, nseg = 1;
         if (i < B) {
             b = list_order[i];
             g = (int)(group_offsets[b + 1] - group_offsets[b]);
             // (a list with no vectors but a non-empty group still gets items: its all-INF rows must be written)
             cnt = (g + tile - 1) / tile;
+            const unsigned long long nb = (unsigned long long)(list_offsets[b + 1] - list_offsets[b]);
             if (g > 0 && stats) {
-                const unsigned long long nb = (unsigned long long)(list_offsets[b + 1] - list_offsets[b]);
                 atomicAdd(stats + 0, nb);
                 atomicAdd(stats + 1, nb * (unsigned long long)g);
             }
+            // seg_rows > 0 (byte scan): one item per (query tile group, segment of seg_rows list rows); ScanItem::tm = segment
+            if (seg_rows > 0) { nseg = (int)((nb + seg_rows - 1) / seg_rows); if (nseg < 1) nseg = 1; cnt *= nseg; }
         }
         int x = cnt;
 #pragma unroll
@@ -399,12 +401,13 @@ __global__ void __launch_bounds__(1024) build_items_kernel(const int* list_order
         if (i < B) {
             const int gb = (int)group_offsets[b];
             for (int t = 0; t < cnt; ++t) {
-                const int left = g - t * tile;
+                const int tq = t / nseg;
+                const int left = g - tq * tile;
                 ScanItem it;
                 it.list = b;
-                it.q_begin = gb + t * tile;
+                it.q_begin = gb + tq * tile;
                 it.q_count = left < tile ? left : tile;
-                it.tm = tile > SCAN_TM_MAX ? tile : tile_class(it.q_count);
+                it.tm = seg_rows > 0 ? t % nseg : (tile > SCAN_TM_MAX ? tile : tile_class(it.q_count));
                 items[at + t] = it;
             }
         }

@@ -844,8 +844,8 @@ __global__ void seed_first_lists_kernel(int Q, int B, int* seed_ids) {
 // refine: the candidate regions (score, list entry) of a query's probed (list, column part) pairs -> exact top-k over
 // distinct ids. One warp per query.
 struct RefineParams {
-    const unsigned long long* cand_key;   // [TC_PARTS P, cap]
-    const int* cand_count;                // [TC_PARTS P]
+    const unsigned long long* cand_key;   // [PARTS P, cap]  (PARTS = TC_PARTS regions per pair, or 1 for the byte scan)
+    const int* cand_count;                // [PARTS P]
     int cap;
     const long long* probe_offsets;       // [Q+1]
     const int* probe_slot;                // [P] slot of the j-th probe of a query (-1: invalid probe)
@@ -866,7 +866,7 @@ struct RefineParams {
     float qn_scale, margin_c, margin_abs, inv_scale;   // scaled units of the shadow copy; inv_scale = 1 / sigma^2
 };
 
-template <int S, bool EXACT>
+template <int S, bool EXACT, int PARTS = TC_PARTS>
 __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
     unsigned long long kth = KEY_INF;
     bool overflow = false;
     const long long lo = p.probe_offsets[q], hi = p.probe_offsets[q + 1];
-    constexpr int PPP = 32 / TC_PARTS;   // probes per 32 regions
+    constexpr int PPP = 32 / PARTS;   // probes per 32 regions
     for (long long j0 = lo; j0 < hi; j0 += 2 * PPP) {
         // 2 PPP probes = 64 regions per pass, TWO per lane: lane l looks at regions (probe j0 + l / TC_PARTS, part l % TC_PARTS) and
         // (probe j0 + PPP + l / TC_PARTS, same part); the loads of both are in flight together, which halves the chain of dependent
@@ -895,12 +895,12 @@ __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) 
         const unsigned long long* src2[2];
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-            const long long j = j0 + w * PPP + (lane / TC_PARTS);
+            const long long j = j0 + w * PPP + (lane / PARTS);
             int region = -1, cnt = 0;
             if (j < hi) {
                 const int slot = p.probe_slot[j];
                 if (slot >= 0) {
-                    region = slot * TC_PARTS + (lane % TC_PARTS);
+                    region = slot * PARTS + (lane % PARTS);
                     cnt = p.cand_count[region];
                 }
             }

@@ -1,0 +1,610 @@
+// K2-U8: the grouped list scan on the integer tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM) for
+// byte-valued data -- every stored value and every query value an integer in [0, 255] (SIFT / BigANN-style) with
+// |x|^2 < 2^22. The list rows stream as ONE byte per component (a quarter of the fp32 bytes the reference scans at
+// search.cpp:468-514, half of the fp16 shadow copy of tc_scan_kernels.cuh), the tensor pipe runs K = 32 per
+// instruction (twice the fp16 rate), and all arithmetic is integer, so distances equal the fp32 direct-difference
+// distances bit for bit.
+//
+//   work item  (list b, a segment of at most `seg_rows` of its rows, up to 512 queries of b's group) = up to FOUR query
+//              tiles of 128 rows (16 KiB each) that share every staged chunk of the list: the L2 -> shared-memory operand
+//              stream -- what bounds the scan once the rows are bytes -- is paid once per 512 queries instead of once per
+//              128. Long lists are cut into row segments so that no item exceeds a small part of an SM's share.
+//   unit       one (query tile, chunk of 256 list rows): 4 MMAs of M = 128, N = 256, K = 32 per 128 bytes of d into one
+//              of the two 256-column accumulators; the epilogue of a unit overlaps the MMAs of the next.
+//   epilogue   16 warps; a thread owns one query row and 64 of the 256 columns: u = 2 acc - |v|^2 (|v|^2 of the chunk's
+//              rows is staged next to them), a 3-input-max tree, and ONE compare + vote per 32 columns.
+//   seed pass  (SEED = true) every thread keeps the 4 largest of its 16-column sub-group maxima over the item's rows
+//              (4-column blocks in the first chunk of a short list): 16 distinct entries per (query, list segment) row,
+//              whose k-th largest bounds the query's final k-th best score (k <= 16); the tightest bound over a query's
+//              lists is T[q] (atomicMin). Exhaustive probe sets pool the values of several lists instead (any k).
+//   filter     (SEED = false) entries with score <= T[q] are appended to the candidate region of their (query, list)
+//              pair (`cap` keys, slot taken with an atomic: survivors are a few per query); refine_topk_kernel turns the
+//              regions into the top k over distinct ids. A region that overflows flags the query for the exact path.
+#pragma once
+#include "tc_scan_kernels.cuh"
+
+namespace lira {
+
+static constexpr int U8_M = 128;                    // queries per tile (UMMA M)
+static constexpr int U8_NS = 256;                   // list rows per chunk (UMMA N, accumulator columns)
+static constexpr int U8_KB = 128;                   // bytes (= components) per K block: one 128-byte swizzle row
+static constexpr int U8_KBLK_BYTES = 128 * U8_KB;   // 16 KiB: 128 rows of one K block
+static constexpr int U8_SLOT_BYTES = 2 * U8_KBLK_BYTES;   // 32 KiB: one K block of a chunk (256 rows)
+static constexpr int U8_A_KB = 4;                   // A ring in 16 KiB blocks: 4 query tiles of d <= 128, or 2 of d <= 256
+static constexpr int U8_NT = U8_A_KB;               // tiles per work item at most
+static constexpr int U8_ITEM_Q = U8_NT * U8_M;      // queries per work item at most (d <= 128; half of it for d <= 256)
+static constexpr int U8_NSLOT_MAX = 4;              // B ring: 4 slots in the filter pass, 3 in the seed pass (which needs the exchange area)
+static constexpr int U8_NNORM = 4;                  // ring of the chunks' |v|^2 (256 int32 each)
+static constexpr int U8_NQ = 3;                     // work-item queue depth (the scheduler warp runs this far ahead)
+static constexpr int U8_PARTS = 4;                  // column parts = epilogue warps per TMEM lane quadrant
+static constexpr int U8_EPI_WARPS = 4 * U8_PARTS;
+static constexpr int U8_THREADS = (U8_EPI_WARPS + 3) * 32;
+static constexpr int U8_MAX_D = 2 * U8_KB;          // d <= 256
+static constexpr int U8_SEG_ROWS = 4096;            // rows of a list per work item (16 chunks x up to 4 tiles = 64 units at most)
+__host__ __device__ constexpr int u8_nslot(bool seed) { return seed ? 3 : 4; }
+__host__ __device__ constexpr size_t u8_smem_bytes(bool seed) {
+    return (size_t)U8_A_KB * U8_KBLK_BYTES + (size_t)u8_nslot(seed) * U8_SLOT_BYTES   // operands
+           + (size_t)U8_NNORM * U8_NS * 4                                             // norms ring
+           + 512                                                                      // barriers, item queue, tmem slot
+           + (size_t)U8_NQ * U8_ITEM_Q * 12                                           // per queued item and row: query id, |q|^2, bound
+           + (seed ? (size_t)U8_PARTS * U8_ITEM_Q * 16 : 0);                          // seed pass: 4 values per (row, part)
+}
+
+// D = S32, A = B = unsigned 8 bit, both K-major, M = 128, N = 256 / 128
+static constexpr uint32_t U8_IDESC_N256 = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(U8_M >> 4) << 24);
+static constexpr uint32_t U8_IDESC_N128 = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(U8_M >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+struct U8Params {
+    const int* group_queries;        // [P] query id per slot
+    const long long* list_offsets;   // [B+1]
+    const ScanItem* items;           // items of up to 512 queries; ScanItem::tm = row segment of the list
+    const int* n_items;
+    int* work_counter;               // zeroed before launch: dynamic item scheduler
+    int nk;                          // K blocks of 128 bytes (1 or 2)
+    int d8;                          // padded row length in bytes (multiple of 16)
+    int seg_rows;                    // rows per segment (multiple of 256)
+    const int* nv;                   // [E + 256] |v|^2 per list entry (L2) or 0 (IP)
+    const float* qnorm;              // [Q] |q|^2 (exact integers)
+    uint32_t* thr;                   // [Q] bound T[q] on the k-th best score as f32_to_ordered(T): written by the seed pass, read by the filter
+    unsigned long long* cand_key;    // [P, cap] (score, list entry) keys: one region per (query, list) pair
+    int* cand_count;                 // [P] zeroed before the filter pass
+    int* seed_out;                   // seed pass, exhaustive probe sets: [P, U8_PARTS, 4] the 16 best scores of every pair go here instead
+                                     //   of being turned into a bound in the kernel (u8_seed_select_kernel pools them); null otherwise
+    int cap;
+    int k;
+    int is_ip;
+    int* dbg;                        // LIRA_TC_EXP bit 6: {groups with a survivor, groups} counters
+    int exp;                         // experiments (LIRA_TC_EXP, wrong results, timing only): bit 0 = skip the survivor path,
+                                     //   bit 1 = skip the whole epilogue arithmetic, bit 2 = skip the MMAs
+};
+
+// inserts x into the descending list a[0] >= a[1] >= a[2] >= a[3] (the 4 largest values seen)
+__device__ __forceinline__ void u8_top4_insert(int (&a)[4], int x) {
+    const int n0 = max(a[0], x), x1 = min(a[0], x);
+    const int n1 = max(a[1], x1), x2 = min(a[1], x1);
+    const int n2 = max(a[2], x2), x3 = min(a[2], x2);
+    a[0] = n0; a[1] = n1; a[2] = n2; a[3] = max(a[3], x3);
+}
+
+// filter pass: the entries of one block of 4 columns that pass (u >= lim) are appended to the pair's candidate region as
+// (score = |q|^2 - u, list entry) keys; returns true when the region overflowed (the query is then redone exactly).
+// Out of line on purpose: see the note on code size in the epilogue.
+__device__ __noinline__ bool u8_append4(int x0, int x1, int x2, int x3, int lim, int qn, uint32_t e0, unsigned long long* cand, int* cnt_ptr, int cap) {
+    const int n = (x0 >= lim) + (x1 >= lim) + (x2 >= lim) + (x3 >= lim);
+    if (n == 0) return false;
+    int pos = atomicAdd(cnt_ptr, n);
+    if (x0 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x0), e0); ++pos; }
+    if (x1 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x1), e0 + 1); ++pos; }
+    if (x2 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x2), e0 + 2); ++pos; }
+    if (x3 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x3), e0 + 3); ++pos; }
+    return pos > cap;
+}
+
+template <bool SEED, bool IP>
+__global__ void __launch_bounds__(U8_THREADS, 1)   // (96 registers per thread: 19 warps x 104 no longer fit the register file)
+u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
+               const U8Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    constexpr int NSLOT = u8_nslot(SEED);
+    uint8_t* sA = smem_raw;                                             // [A ring: U8_A_KB blocks of 128 x 128 B]
+    uint8_t* sB = sA + (size_t)U8_A_KB * U8_KBLK_BYTES;                 // [NSLOT][256 x 128 B]
+    int* s_nv = (int*)(sB + (size_t)NSLOT * U8_SLOT_BYTES);             // [U8_NNORM][256]
+    uint64_t* bars = (uint64_t*)(s_nv + U8_NNORM * U8_NS);
+    uint64_t* a_full = bars;                        // [U8_A_KB] per tile buffer
+    uint64_t* a_empty = a_full + U8_A_KB;           // [U8_A_KB]
+    uint64_t* b_full = a_empty + U8_A_KB;           // [U8_NSLOT_MAX]
+    uint64_t* b_empty = b_full + U8_NSLOT_MAX;      // [U8_NSLOT_MAX]
+    uint64_t* n_full = b_empty + U8_NSLOT_MAX;      // [U8_NNORM]
+    uint64_t* n_empty = n_full + U8_NNORM;          // [U8_NNORM]
+    uint64_t* t_full = n_empty + U8_NNORM;          // [2]
+    uint64_t* t_empty = t_full + 2;                 // [2]
+    uint64_t* i_full = t_empty + 2;                 // [U8_NQ]
+    uint64_t* i_empty = i_full + U8_NQ;             // [U8_NQ]
+    TcQItem* iq = (TcQItem*)(i_empty + U8_NQ);      // [U8_NQ]   (32 barriers = 256 B, 2 items = 64 B)
+    uint32_t* tmem_slot = (uint32_t*)(iq + U8_NQ);
+    int* s_q = (int*)((uint8_t*)bars + 512);                    // [U8_NQ][512] query id (-1: padding row)
+    int* s_qn = s_q + U8_NQ * U8_ITEM_Q;                        // [U8_NQ][512] |q|^2 (0 for IP)
+    int* s_lim = s_qn + U8_NQ * U8_ITEM_Q;                      // [U8_NQ][512] an entry survives iff u >= lim
+    int4* s_x = reinterpret_cast<int4*>(s_lim + U8_NQ * U8_ITEM_Q);   // [U8_PARTS][512]: seed pass, the 4 largest u per (row, part)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_PROD = U8_EPI_WARPS, W_MMA = W_PROD + 1, W_ALLOC = W_PROD + 2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < U8_A_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < U8_NSLOT_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < U8_NNORM; ++i) { mbar_init(&n_full[i], 32); mbar_init(&n_empty[i], U8_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], U8_EPI_WARPS); }
+        for (int i = 0; i < U8_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + U8_EPI_WARPS); }   // producer + MMA + epilogue warps
+        mbar_fence_init();
+    }
+    if (warp == W_ALLOC) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == W_PROD * 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_items = *p.n_items;
+    const int nk = p.nk;
+    const int abuf = U8_A_KB / nk;                  // tile buffers of the A ring (a tile = nk blocks): 4 (d <= 128) or 2
+
+    if (warp == W_ALLOC) {
+        // ===== scheduler (the TMEM allocator warp has nothing else to do): claims work items and stages what the other warps
+        // need to start one -- row range, and per row the query id, |q|^2 and the bound -- in the shared-memory queue, U8_NQ
+        // items ahead. Its chain of dependent global round trips (ticket -> descriptor -> list range + row ids -> per-row
+        // gathers, ~2-3 us) therefore never sits between two items of the pipeline, however short they are.
+        // The chain is software-pipelined over FOUR items: every iteration issues the ticket of item n+3, the descriptor load of
+        // item n+2, the row-range / row-id loads of item n+1 and the per-row gathers of item n -- four independent round trips in
+        // flight together -- and then stages item n. So the scheduler delivers one item per memory latency (< 1 us).
+        auto ticket = [&]() { return lane == 0 ? atomicAdd(p.work_counter, 1) : 0; };
+        auto descriptor = [&](int tk) {
+            const int idx = __shfl_sync(0xffffffffu, tk, 0);
+            ScanItem d;
+            if (idx < n_items) d = p.items[idx];
+            else { d.list = -1; d.q_begin = 0; d.q_count = 0; d.tm = 0; }
+            return d;
+        };
+        constexpr int RPL = U8_ITEM_Q / 32;   // rows per lane (row = lane + 32 j)
+        // pipeline registers: tk3 (ticket n+3 in flight) ; d2 (descriptor n+2) ; {o1, rq1} (rows of n+1) ; item n is staged
+        int tk = ticket();
+        ScanItem d2 = descriptor(tk);          // item 0
+        tk = ticket();
+        ScanItem d2n = descriptor(tk);         // item 1
+        tk = ticket();                         // item 2's ticket
+        TcQItem o1;
+        int rq1[RPL];
+        auto rows_of = [&](const ScanItem& d, TcQItem& o, int (&rq)[RPL]) {
+            o.list = d.list; o.q_begin = d.q_begin; o.q_count = d.q_count; o.pad = 0;
+            o.lo = 0; o.hi = 0;
+            if (d.list >= 0) {
+                const long long l0 = p.list_offsets[d.list], l1 = p.list_offsets[d.list + 1];
+                o.lo = min(l1, l0 + (long long)d.tm * p.seg_rows);
+                o.hi = min(l1, o.lo + p.seg_rows);
+            }
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) rq[j] = (d.list >= 0 && lane + 32 * j < d.q_count) ? __ldg(p.group_queries + d.q_begin + lane + 32 * j) : -1;
+        };
+        rows_of(d2, o1, rq1);                  // rows of item 0
+        d2 = d2n;                              // d2 = descriptor of item 1
+        for (int n = 0;; ++n) {
+            // ---- issue: gathers of item n, rows of item n+1, descriptor of item n+2, ticket of item n+3 ----
+            const TcQItem o0 = o1;
+            int rq0[RPL], rqn[RPL], rlim[RPL];
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) rq0[j] = rq1[j];
+            float qn_f[RPL];
+            uint32_t thr_u[RPL];
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                qn_f[j] = (!IP && rq0[j] >= 0) ? __ldg(p.qnorm + rq0[j]) : 0.f;
+                thr_u[j] = (!SEED && rq0[j] >= 0) ? __ldg(p.thr + rq0[j]) : 0xFF800000u;
+            }
+            if (o0.list >= 0) {
+                rows_of(d2, o1, rq1);
+                d2 = descriptor(tk);
+                tk = ticket();
+            }
+            // ---- consume: stage item n ----
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const int qn = (int)qn_f[j];
+                rqn[j] = qn;
+                rlim[j] = 0x7FFFFFFF;   // padding rows: nothing ever passes
+                if (!SEED && rq0[j] >= 0) {
+                    // score = qn - u <= T  <=>  u >= qn - T; T = +inf (no bound): everything real passes (u > -2^26)
+                    const float T = ordered_to_f32(thr_u[j]);
+                    const int Ti = T >= 1073741824.f ? 1073741824 : (T <= -1073741824.f ? -1073741824 : (int)floorf(T));
+                    rlim[j] = qn - Ti;
+                }
+            }
+            const int qs = n % U8_NQ;
+            mbar_wait(&i_empty[qs], ((n / U8_NQ) & 1) ^ 1u);
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                s_q[qs * U8_ITEM_Q + lane + 32 * j] = rq0[j];
+                s_qn[qs * U8_ITEM_Q + lane + 32 * j] = rqn[j];
+                s_lim[qs * U8_ITEM_Q + lane + 32 * j] = rlim[j];
+            }
+            __syncwarp();   // every lane's rows are written before lane 0 publishes the item (arrive = release)
+            if (lane == 0) { iq[qs] = o0; mbar_arrive(&i_full[qs]); }
+            __syncwarp();
+            if (o0.list < 0) break;
+        }
+    } else if (warp == W_PROD) {
+        // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+        PipeState bs{0, 0};
+        uint32_t cn = 0;   // running chunk counter -> norms ring slot
+        uint32_t ga = 0;   // running tile counter -> A ring buffer and phase
+        for (int n = 0;; ++n) {
+            const int qs = n % U8_NQ;
+            mbar_wait(&i_full[qs], (n / U8_NQ) & 1);
+            const TcQItem it = iq[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[qs]);
+            if (it.list < 0) break;
+            const int ntile = (it.q_count + U8_M - 1) / U8_M;
+            for (int t = 0; t < ntile; ++t, ++ga) {   // the item's query tiles into the next buffers of the A ring
+                const uint32_t x = ga % (uint32_t)abuf;
+                mbar_wait(&a_empty[x], ((ga / (uint32_t)abuf) & 1) ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[x], (uint32_t)nk * U8_KBLK_BYTES);
+                    for (int kb = 0; kb < nk; ++kb)
+                        tma_load_2d(sA + (size_t)(x * nk + kb) * U8_KBLK_BYTES, &tmap_q, kb * U8_KB, it.q_begin + t * U8_M, &a_full[x]);
+                }
+                __syncwarp();
+            }
+            const long long lo = it.lo, hi = it.hi;
+            for (long long row0 = lo; row0 < hi; row0 += U8_NS, ++cn) {
+                const int nh = hi - row0 > 128 ? 2 : 1;   // boxes of 128 rows (the tail of a list may need one only)
+                const int ns = cn % U8_NNORM;
+                mbar_wait(&n_empty[ns], ((cn / U8_NNORM) & 1) ^ 1u);
+                {   // |v|^2 of the chunk's rows: 4-byte cp.async (a list starts at any entry, TMA needs 16-byte aligned starts);
+                    // every lane's arrival lands when its copies have (n_full counts 32)
+                    const int* src = p.nv + row0 + lane;
+                    const uint32_t dst = smem_u32(s_nv + ns * U8_NS + lane);
+#pragma unroll
+                    for (int j = 0; j < U8_NS / 32; ++j) cp_async_4(dst + j * 128, src + j * 32);
+                    cp_async_mbar_arrive_noinc(&n_full[ns]);
+                }
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
+                    if (elect_one()) {
+                        uint8_t* slot = sB + (size_t)bs.stage * U8_SLOT_BYTES;
+                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nh * U8_KBLK_BYTES);
+                        for (int x = 0; x < nh; ++x)
+                            tma_load_2d(slot + (size_t)x * U8_KBLK_BYTES, &tmap_v, kb * U8_KB, (int)row0 + x * 128, &b_full[bs.stage]);
+                    }
+                    __syncwarp();
+                    bs.advance(NSLOT);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===== MMA issuer =====
+        PipeState bs{0, 0};
+        uint32_t m = 0;   // running unit counter -> accumulator and phase
+        uint32_t gm = 0;  // running tile counter -> A ring buffer and phase
+        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+        for (int n = 0;; ++n) {
+            const int qs = n % U8_NQ;
+            mbar_wait(&i_full[qs], (n / U8_NQ) & 1);
+            const TcQItem it = iq[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[qs]);
+            if (it.list < 0) break;
+            const int ntile = (it.q_count + U8_M - 1) / U8_M;
+            if ((p.exp & 64) && lane == 0) {   // {.., .., items, tiles, chunks, units}
+                const int nch = (int)((it.hi - it.lo + U8_NS - 1) / U8_NS);
+                atomicAdd(p.dbg + 2, 1); atomicAdd(p.dbg + 3, ntile); atomicAdd(p.dbg + 4, nch); atomicAdd(p.dbg + 5, nch * ntile);
+            }
+            for (int t = 0; t < ntile; ++t) {
+                const uint32_t g = gm + t;
+                mbar_wait(&a_full[g % (uint32_t)abuf], (g / (uint32_t)abuf) & 1);
+            }
+            tc_fence_after();
+            const long long lo = it.lo, hi = it.hi;
+            for (long long row0 = lo; row0 < hi; row0 += U8_NS) {
+                const uint32_t idesc = hi - row0 > 128 ? U8_IDESC_N256 : U8_IDESC_N128;
+                const PipeState b0 = bs;
+                for (int t = 0; t < ntile; ++t, ++m) {
+                    const uint32_t acc = m & 1u;
+                    mbar_wait(&t_empty[acc], ((m >> 1) & 1) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * U8_NS;
+                    const uint32_t x = (gm + t) % (uint32_t)abuf;
+                    PipeState s = b0;
+                    for (int kb = 0; kb < nk; ++kb) {
+                        if (t == 0) { mbar_wait(&b_full[s.stage], s.phase); tc_fence_after(); }
+                        const uint32_t a_addr = sA_u32 + (uint32_t)(x * nk + kb) * U8_KBLK_BYTES;
+                        const uint32_t b_addr = sB_u32 + (uint32_t)s.stage * U8_SLOT_BYTES;
+                        const int ksteps = min(4, (p.d8 - kb * U8_KB + 31) / 32);
+                        if (elect_one() && !(p.exp & 4)) {
+                            for (int j = 0; j < ksteps; ++j)   // K = 32 bytes inside the 128-byte swizzle row
+                                tc_mma_i8(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), idesc, (kb || j) ? 1u : 0u);
+                        }
+                        __syncwarp();
+                        s.advance(NSLOT);
+                    }
+                    if (elect_one()) tc_commit(&t_full[acc]);
+                    __syncwarp();
+                }
+                for (int kb = 0; kb < nk; ++kb) {   // the chunk's slots are free once every MMA above has read them
+                    if (elect_one()) tc_commit(&b_empty[bs.stage]);
+                    __syncwarp();
+                    bs.advance(NSLOT);
+                }
+            }
+            for (int t = 0; t < ntile; ++t, ++gm) {   // ... and so are the item's query tiles
+                if (elect_one()) tc_commit(&a_empty[gm % (uint32_t)abuf]);
+                __syncwarp();
+            }
+        }
+    } else if (warp < U8_EPI_WARPS) {
+        // ===== epilogue =====
+        // (code size matters here: with the tile / half loops unrolled and the append code inlined per column the kernel no
+        //  longer fits the instruction cache and every survivor costs microseconds -- measured; so the loops below are real
+        //  loops, per-tile state lives in shared memory, and the append is one out-of-line function)
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int part = warp >> 2;                // which 32 columns of each 128-column half
+        const int cap = p.cap;
+        const uint32_t t_full_u32 = smem_u32(t_full), t_empty_u32 = smem_u32(t_empty);
+        uint32_t m = 0, cn = 0;
+        for (int n = 0;; ++n) {
+            const int qs = n % U8_NQ;
+            mbar_wait(&i_full[qs], (n / U8_NQ) & 1);
+            const TcQItem it = iq[qs];
+            if (it.list < 0) break;
+            const int* iq_q = s_q + qs * U8_ITEM_Q;
+            const int* iq_qn = s_qn + qs * U8_ITEM_Q;
+            int* iq_lim = s_lim + qs * U8_ITEM_Q;
+            const int ntile = (it.q_count + U8_M - 1) / U8_M;
+            const int n_rows = (int)(it.hi - it.lo);
+            const int trow = quad * 32 + lane;     // this thread's row inside a tile
+            if (SEED) {
+                if (n > 0) named_bar_sync(2, U8_EPI_WARPS * 32);   // the previous item's values have been read
+                for (int t = 0; t < ntile; ++t) s_x[part * U8_ITEM_Q + t * U8_M + trow] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+            }
+            uint32_t ebase = (uint32_t)it.lo + part * 32;
+            int left = n_rows - part * 32;
+            for (int rows_left = n_rows; rows_left > 0; rows_left -= U8_NS, ebase += U8_NS, left -= U8_NS, ++cn) {
+                const int nh = rows_left > 128 ? 2 : 1;
+                const int ns = cn % U8_NNORM;
+                mbar_wait(&n_full[ns], (cn / U8_NNORM) & 1);
+                const int* nvc = s_nv + ns * U8_NS + part * 32;
+                const bool fine = SEED && rows_left == n_rows && n_rows <= 1024;   // first chunk of a short list: 4-column blocks
+#pragma unroll 1
+                for (int t = 0; t < ntile; ++t, ++m) {
+                    const uint32_t acc = m & 1u;
+                    const uint32_t par = (m >> 1) & 1u;
+                    mbar_wait_addr(t_full_u32 + acc * 8, par);
+                    // a warp whose 32 rows of this tile are all padding only keeps the accumulator handshake going
+                    if (t * U8_M + quad * 32 >= it.q_count) {
+                        if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
+                        __syncwarp();
+                        continue;
+                    }
+                    tc_fence_after();
+                    const int row = t * U8_M + trow;
+                    const int lim = SEED ? 0 : iq_lim[row];
+                    int a[4];
+                    if (SEED) { const int4 v = s_x[part * U8_ITEM_Q + row]; a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+                    // both 128-column halves of the unit are requested at once and the accumulator goes back to the MMA warp as
+                    // soon as they are in registers: the handshake round trip, not the arithmetic, paces short work items
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * U8_NS + part * 32;
+                    uint32_t ra[32], rb[32];
+                    tc_ld32_async(taddr, ra);
+                    if (nh > 1) tc_ld32_async(taddr + 128, rb);
+                    tc_ld_wait(ra);
+                    tc_ld_wait(rb);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
+                    auto process = [&](uint32_t (&ru)[32], const int h) {
+                        int r[32];
+                        if (IP) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = (int)ru[i];
+                        } else {
+                            const int4* nv4 = reinterpret_cast<const int4*>(nvc + h * 128);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int4 nv = nv4[i];
+                                r[4 * i + 0] = 2 * (int)ru[4 * i + 0] - nv.x;
+                                r[4 * i + 1] = 2 * (int)ru[4 * i + 1] - nv.y;
+                                r[4 * i + 2] = 2 * (int)ru[4 * i + 2] - nv.z;
+                                r[4 * i + 3] = 2 * (int)ru[4 * i + 3] - nv.w;
+                            }
+                        }
+                        // columns past the end of the segment hold other rows
+                        const int n_valid = left - h * 128;
+                        if (n_valid < 32) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (c >= n_valid) r[c] = INT_MIN;
+                        }
+                        int m4[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m4[i] = max(max(r[4 * i], r[4 * i + 1]), max(r[4 * i + 2], r[4 * i + 3]));
+                        const int m16a = max(max(m4[0], m4[1]), max(m4[2], m4[3]));
+                        const int m16b = max(max(m4[4], m4[5]), max(m4[6], m4[7]));
+                        if (SEED) {
+                            if (fine) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) u8_top4_insert(a, m4[i]);
+                            } else { u8_top4_insert(a, m16a); u8_top4_insert(a, m16b); }
+                        } else {
+                            const int mx = max(m16a, m16b);
+                            if ((p.exp & 64) && lane == 0) atomicAdd(p.dbg + 1, 1);
+                            if (__any_sync(0xffffffffu, mx >= lim) && !(p.exp & 1)) {
+                                if ((p.exp & 64) && lane == 0) atomicAdd(p.dbg, 1);
+                                const size_t slot = (size_t)(it.q_begin + row);
+                                unsigned long long* cand = p.cand_key + slot * cap;
+                                int* cnt_ptr = p.cand_count + slot;
+                                const uint32_t eb = ebase + h * 128;
+                                const int qn = iq_qn[row];
+                                bool over = false;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    // one vote per block of 4 columns (warp-uniform branch): the lanes with a passing entry append it
+                                    if (__any_sync(0xffffffffu, m4[j] >= lim))
+                                        over |= u8_append4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt_ptr, cap);
+                                }
+                                if (over) iq_lim[row] = 0x7FFFFFFF;   // the region overflowed (the query is redone exactly): stop collecting
+                            }
+                        }
+                    };
+                    if (!(p.exp & 2)) {
+                        process(ra, 0);
+                        if (nh > 1) process(rb, 1);
+                    }
+                    if (SEED) s_x[part * U8_ITEM_Q + row] = make_int4(a[0], a[1], a[2], a[3]);
+                }
+                // this warp is done with the chunk's norms
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&n_empty[ns]);
+            }
+            if (SEED) {
+                // a row's four column parts kept 4 values each: 16 distinct entries of this list segment. Their k-th largest has
+                // k entries at or above it  =>  T = |q|^2 - that value bounds the query's final k-th best score (k <= 16).
+                // Exhaustive probe sets (p.seed_out): the 16 scores go to global memory and are pooled over the query's lists.
+                named_bar_sync(1, U8_EPI_WARPS * 32);
+                const int row = warp * 32 + lane;   // 512 epilogue threads, one row each
+                if (row < it.q_count) {
+                    const int qn = iq_qn[row];
+                    if (p.seed_out) {
+#pragma unroll
+                        for (int pp = 0; pp < U8_PARTS; ++pp) {
+                            const int4 x = s_x[pp * U8_ITEM_Q + row];
+                            int4 o;
+                            o.x = x.x > INT_MIN ? qn - x.x : INT_MAX; o.y = x.y > INT_MIN ? qn - x.y : INT_MAX;
+                            o.z = x.z > INT_MIN ? qn - x.z : INT_MAX; o.w = x.w > INT_MIN ? qn - x.w : INT_MAX;
+                            *reinterpret_cast<int4*>(p.seed_out + ((size_t)(it.q_begin + row) * U8_PARTS + pp) * 4) = o;
+                        }
+                    } else {
+                        float v[16];   // (descending order wanted: sort the negated values ascending)
+#pragma unroll
+                        for (int pp = 0; pp < U8_PARTS; ++pp) {
+                            const int4 x = s_x[pp * U8_ITEM_Q + row];
+                            v[4 * pp + 0] = -(float)x.x; v[4 * pp + 1] = -(float)x.y; v[4 * pp + 2] = -(float)x.z; v[4 * pp + 3] = -(float)x.w;
+                        }
+                        tc_sort16(v);
+                        const float tk = tc_pick16(v, p.k - 1);   // = -(k-th largest u); 2^31 when fewer than k entries were seen
+                        if (tk < 1073741824.f) atomicMin(p.thr + iq_q[row], f32_to_ordered((float)qn + tk));
+                    }
+                }
+            }
+            // the item's per-row data has been read: its queue slot may be reused
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&i_empty[qs]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ALLOC) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// exhaustive probe sets (exact kNN over disjoint base segments; group slot of (query q, list b) = b Q + q): T[q] = k-th
+// smallest of the 16 S scores the seed pass kept for the query's first S lists -- all distinct entries. One warp per query.
+__global__ void __launch_bounds__(256) u8_seed_select_kernel(const int* __restrict__ seed_out, int Q, int S, int k, uint32_t* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    unsigned long long key[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) key[s] = KEY_INF;
+    unsigned long long kth = KEY_INF;
+    uint32_t tag = 0;
+    for (int b0 = 0; b0 < S; b0 += 2) {   // two lists (32 values) per round, one per lane
+        const int b = b0 + (lane >> 4);
+        int v = INT_MAX;
+        if (b < S) v = seed_out[((size_t)b * Q + q) * (U8_PARTS * 4) + (lane & 15)];
+        uint32_t mm = __ballot_sync(0xffffffffu, v != INT_MAX);
+        while (mm) {
+            const int sl = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const unsigned long long y = make_key((float)__shfl_sync(0xffffffffu, v, sl), tag++);
+            if (y < kth) {
+                warp_sorted_insert<4>(key, y, lane);
+                kth = warp_sorted_get<4>(key, k - 1);
+            }
+        }
+    }
+    if (lane == 0) thr[q] = kth == KEY_INF ? 0xFF800000u /* +inf */ : (uint32_t)(kth >> 32);
+}
+
+// items of lists 0 .. S-1 (the seed pass of exhaustive probe sets runs on these only)
+__global__ void u8_seed_items_kernel(const ScanItem* __restrict__ items, const int* __restrict__ n_items, int S,
+                                     ScanItem* __restrict__ out, int* __restrict__ n_out) {
+    const int n = *n_items;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ScanItem it = items[i];
+        if (it.list < S) out[atomicAdd(n_out, 1)] = it;
+    }
+}
+
+// the byte shadow copy of the list rows: x8[n, d8] = uint8(x) (zero padded) and nv[n] = |x|^2 (L2) or 0 (IP) as int32
+__global__ void shadow_rows_u8_kernel(const float* __restrict__ x, long ld, int d, long long n, const float* __restrict__ norm,
+                                      int is_ip, uint8_t* __restrict__ x8, int d8, int* __restrict__ nv) {
+    const int per_row = d8 / 4;
+    const long long total = n * per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / per_row;
+        const int c = (int)(i % per_row) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) v = *reinterpret_cast<const float4*>(x + row * ld + c);   // (ld and the padding up to round_up(d, 4) are zero filled)
+        const uint32_t pk = (uint32_t)(int)v.x | ((uint32_t)(int)v.y << 8) | ((uint32_t)(int)v.z << 16) | ((uint32_t)(int)v.w << 24);
+        *reinterpret_cast<uint32_t*>(x8 + row * d8 + c) = pk;
+        if (c == 0) nv[row] = is_ip ? 0 : (int)norm[row];
+    }
+}
+
+// *flag is cleared unless every value of x[n, d] is an integer in [0, 255]
+__global__ void check_u8_kernel(const float* __restrict__ x, long ld, int d, long long n, int* __restrict__ flag) {
+    const int per_row = (d + 3) / 4;
+    const long long total = n * per_row;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / per_row;
+        const int c = (int)(i % per_row) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + row * ld + c);
+        bad |= !(v.x >= 0.f && v.x <= 255.f && v.y >= 0.f && v.y <= 255.f && v.z >= 0.f && v.z <= 255.f && v.w >= 0.f && v.w <= 255.f);
+        bad |= (v.x != rintf(v.x)) | (v.y != rintf(v.y)) | (v.z != rintf(v.z)) | (v.w != rintf(v.w));
+    }
+    if (bad) *flag = 0;
+}
+
+// gq8[slot, :] = uint8(q[group_queries[slot], :]) (queries in group order, zero padded to d8 bytes); *bad_flag is set
+// when a value is not an integer in [0, 255] (the batch then takes another path)
+__global__ void gather_group_queries_u8_kernel(const float* __restrict__ q, long ldq, int ds, const int* __restrict__ group_queries,
+                                               long long P, const long long* __restrict__ n_slots, uint8_t* __restrict__ gq8, int d8,
+                                               int* __restrict__ ok_flag) {
+    const int per_row = d8 / 4;
+    const long long total = (*n_slots < P ? *n_slots : P) * per_row;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / per_row;
+        const int c = (int)(i % per_row) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ds) v = *reinterpret_cast<const float4*>(q + (long long)group_queries[s] * ldq + c);
+        bad |= !(v.x >= 0.f && v.x <= 255.f && v.y >= 0.f && v.y <= 255.f && v.z >= 0.f && v.z <= 255.f && v.w >= 0.f && v.w <= 255.f);
+        const uint32_t pk = (uint32_t)(int)v.x | ((uint32_t)(int)v.y << 8) | ((uint32_t)(int)v.z << 16) | ((uint32_t)(int)v.w << 24);
+        *reinterpret_cast<uint32_t*>(gq8 + s * d8 + c) = pk;
+    }
+    if (bad && ok_flag) *ok_flag = 0;
+}
+
+}  // namespace lira

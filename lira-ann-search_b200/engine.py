@@ -260,6 +260,15 @@ class LiraIndex:
         return int(C.lib().lira_index_last_redo(self._h))
 
     @property
+    def last_scan_kind(self) -> str:
+        """Kernel family of the last batch: "cuda-core", "fp16" (tcgen05 kind::f16 scan) or "u8" (tcgen05 kind::i8 byte scan)."""
+        return {0: "cuda-core", 1: "fp16", 2: "u8"}.get(int(C.lib().lira_index_last_scan_kind(self._h)), "?")
+
+    @property
+    def byte_scan_eligible(self) -> bool:
+        return bool(C.lib().lira_index_byte_scan_eligible(self._h))
+
+    @property
     def tensor_core_eligible(self) -> bool:
         return bool(C.lib().lira_index_tensor_core_eligible(self._h))
 
@@ -422,6 +431,10 @@ class KnnIndex:
     @property
     def last_redo(self) -> int:
         return int(C.lib().lira_knn_last_redo(self._h))
+
+    @property
+    def last_scan_kind(self) -> str:
+        return {0: "cuda-core", 1: "fp16", 2: "u8"}.get(int(C.lib().lira_knn_last_scan_kind(self._h)), "?")
 
     def close(self):
         if self._h is not None:

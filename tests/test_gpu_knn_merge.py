@@ -30,7 +30,7 @@ def test_knn_exhaustive_tensor_core_path_k_above_16(L, metric, k):
     x_d, x_q = synth(70_000, 64, 300, seed=100 + k, integer=True)
     index = L.KnnIndex(x_d, metric)
     D, I = index.search(x_q, k)
-    assert index.last_path == "tensor-core"
+    assert index.last_path == "tensor-core" and index.last_scan_kind == "u8"   # byte-valued base: the kind::i8 scan
     D_ref, I_ref = O.knn(x_d, x_q, k, metric, O.F64, 0)
     assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
     D_blas, I_blas = O.knn(x_d, x_q, k, metric, O.F32, 1)   # |x|^2 + |y|^2 - 2 x.y in fp32 (faiss nx >= 20 path)
@@ -44,10 +44,14 @@ def test_knn_exhaustive_tensor_core_path_k_above_16(L, metric, k):
     assert np.array_equal(I1, I) and np.array_equal(D1, D)
 
 
-def test_knn_k100_overflow_is_redone_exactly(L):
-    """The static bound of the k > 16 path comes from the first two base segments. Here they hold a far-away cluster, so
-    the bound is loose, the 64-slot candidate regions of the near segments overflow and the flagged queries are answered
-    again by the exact CUDA-core scan (last_redo > 0): the result must not change."""
+@pytest.mark.parametrize("scan", ["fp16", "u8"])
+def test_knn_k100_overflow_is_redone_exactly(L, scan, monkeypatch):
+    """fp16 scan: the static bound of the k > 16 path comes from the first two base segments. Here they hold a far-away
+    cluster, so the bound is loose, the 64-slot candidate regions of the near segments overflow and the flagged queries are
+    answered again by the exact CUDA-core scan (last_redo > 0): the result must not change. Byte scan: its seed pools
+    the first 16 segments, here the whole base, so nothing overflows; same result."""
+    if scan == "fp16":
+        monkeypatch.setenv("LIRA_NO_U8", "1")   # (read when the index is created)
     rng = np.random.RandomState(5)
     d, k = 32, 100
     far = np.clip(np.round(rng.randn(16_384, d) * 4 + 200), 0, 255)
@@ -56,7 +60,8 @@ def test_knn_k100_overflow_is_redone_exactly(L):
     x_q = np.clip(np.round(rng.randn(400, d) * 4 + 40), 0, 255).astype(np.float32)
     index = L.KnnIndex(x_d, O.L2)
     D, I = index.search(x_q, k)
-    assert index.last_path == "tensor-core" and index.last_redo > 0
+    assert index.last_path == "tensor-core" and index.last_scan_kind == scan
+    assert index.last_redo > 0 if scan == "fp16" else index.last_redo == 0
     D_ref, I_ref = O.knn(x_d, x_q, k, O.L2, O.F64, 0)
     assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
 
@@ -149,3 +154,32 @@ def test_merge_ranks_dev_matches_numpy_merge(L, R, k, metric, dedup):
     assert np.array_equal(got_I, I_ref)
     assert np.array_equal(np.where(got_I >= 0, got_D, np.inf), D_ref)
     assert np.all(got_I[7] == -1)
+
+
+def test_knn_byte_scan_far_seed_segments_overflow_is_redone(L):
+    """Byte scan, exhaustive probe sets: the pooled seed comes from the first 16 base segments (131 072 rows). Here they
+    hold a far-away cluster, so T[q] is loose, the 128-slot regions of the near segments overflow and the flagged queries
+    go to the exact CUDA-core scan. The result must not change."""
+    rng = np.random.RandomState(6)
+    d, k = 32, 100
+    far = np.clip(np.round(rng.randn(16 * 8192, d) * 4 + 200), 0, 255)
+    near = np.clip(np.round(rng.randn(30_000, d) * 4 + 40), 0, 255)
+    x_d = np.concatenate([far, near]).astype(np.float32)
+    x_q = np.clip(np.round(rng.randn(300, d) * 4 + 40), 0, 255).astype(np.float32)
+    index = L.KnnIndex(x_d, O.L2)
+    D, I = index.search(x_q, k)
+    assert index.last_scan_kind == "u8" and index.last_redo > 0
+    D_ref, I_ref = O.knn(x_d, x_q, k, O.L2, O.F64, 0)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)
+
+
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_knn_fp16_scan_still_serves_byte_valued_data(L, metric, monkeypatch):
+    """LIRA_NO_U8=1 at create time: the same data on the fp16 scan (kind::f16), identical rows."""
+    monkeypatch.setenv("LIRA_NO_U8", "1")
+    x_d, x_q = synth(70_000, 64, 300, seed=117, integer=True)
+    index = L.KnnIndex(x_d, metric)
+    D, I = index.search(x_q, 17)
+    assert index.last_scan_kind == "fp16"
+    D_ref, I_ref = O.knn(x_d, x_q, 17, metric, O.F64, 0)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref)

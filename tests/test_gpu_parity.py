@@ -720,3 +720,63 @@ def test_tensor_core_batch_size_edges(L, Q):
         I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, O.L2, O.F64, 1)
         assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
 
+
+
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("k,d", [(10, 128), (10, 96), (1, 20), (10, 200), (16, 256), (10, 8)])
+def test_byte_scan_is_bit_identical(L, metric, k, d, monkeypatch):
+    """LIRA_U8_SEARCH=1: explicit probe sets on the kind::i8 scan (one byte per component, int32 accumulators). Lists longer
+    than one row segment (4096 rows), a group of more than 512 queries (several work items per list), an empty list, a list
+    shorter than k, ids stored in two lists: ids, distances and cmp equal the oracle's and the CUDA-core scan's bit for bit."""
+    monkeypatch.setenv("LIRA_U8_SEARCH", "1")
+    rng = np.random.RandomState(170 + k + d)
+    x_d, x_q = synth(40000, d, 900, seed=310 + d, integer=True)
+    B = 12
+    cl = random_lists(len(x_d), B, rng, redundancy=0.5, empty=(5,))
+    cl[3] = cl[3][:7]  # a list shorter than k
+    off, ids, vecs = lists_csr(x_d, cl)
+    assert (np.diff(off) > 4096).any()
+    nprobe = rng.randint(0, 7, len(x_q))
+    nprobe[:700] = np.maximum(nprobe[:700], 1)
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    sets = [rng.choice(B, n, replace=False) for n in nprobe]
+    for i in range(700):
+        sets[i][0] = 0 if 0 not in sets[i][1:] else sets[i][0]   # list 0 is probed by more than 512 queries
+    pids = np.concatenate(sets + [np.empty(0, int)]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, metric)
+    assert index.byte_scan_eligible
+    D, I, cmp_ = index.search(x_q, poff, pids, k)
+    assert index.last_path == "tensor-core" and index.last_scan_kind == "u8"
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
+    D0, I0, _ = index.search(x_q, poff, pids, k, dedup=False)
+    I0_ref, D0_ref, _ = O.search(off, ids, vecs, x_q, poff, pids, k, metric, O.F64, 0)
+    assert np.array_equal(I0, I0_ref) and np.array_equal(D0, D0_ref)
+    # a query batch that is not byte valued falls back to the fp16 scan (same handle), same result
+    x_q2 = x_q.copy()
+    x_q2[0, 0] = 300.0
+    D2, I2, _ = index.search(x_q2, poff, pids, k)
+    assert index.last_scan_kind == "fp16"
+    I2_ref, D2_ref, _ = O.search(off, ids, vecs, x_q2, poff, pids, k, metric, O.F64, 1)
+    assert np.array_equal(I2, I2_ref) and np.array_equal(D2, D2_ref)
+
+
+def test_byte_scan_without_seed_overflows_to_the_exact_path(L, monkeypatch):
+    """LIRA_TC_NO_SEED=1: every bound is +inf, every region overflows, every query is redone by the CUDA-core scan."""
+    monkeypatch.setenv("LIRA_U8_SEARCH", "1")
+    monkeypatch.setenv("LIRA_TC_NO_SEED", "1")
+    rng = np.random.RandomState(9)
+    x_d, x_q = synth(20000, 64, 400, seed=78, integer=True)
+    B = 6
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(x_d, cl)
+    nprobe = rng.randint(1, 5, len(x_q))
+    poff = np.zeros(len(x_q) + 1, np.int64)
+    np.cumsum(nprobe, out=poff[1:])
+    pids = np.concatenate([rng.choice(B, n, replace=False) for n in nprobe]).astype(np.int32)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    D, I, cmp_ = index.search(x_q, poff, pids, 10)
+    assert index.last_scan_kind == "u8" and index.last_redo == len(x_q)
+    I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
+    assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
