@@ -12,15 +12,18 @@ partitions, LIRA probing model trained here with the reference loop shape (BCELo
 (n_mul = 2), k = 10, L2. One step = the whole query phase for the 10k-query batch: centroid features -> MLP ->
 threshold select -> grouped list scan -> dedup merge.
 
-N > 1, default, `config.workload = "bigann-shape-sharded"` (BASELINE.json configs[4] scaled as N x 12.5 M vectors, weak
-scaling of the DATASET): every rank generates only its own 12.5 M vectors on the device (chunk-seeded generator), stores
-each of them in its two nearest partitions (25 M list entries per rank, full 2x redundancy), so every one of the B = 1024
-lists is striped across the ranks by vector id. Every rank answers all 10k queries on its stripe; the per-rank top-k
-lists are all-gathered over NCCL (packed 64-bit keys) and merged with id de-duplication by lira_merge_ranks_dev -- the
-collective and the merge are inside the timed region. QPS = Q / step time on a dataset that grows with N; the
-line also carries the time one rank needs for its share alone (`share_alone_ms`), so the weak-scaling efficiency is
-share_alone_ms / ms_per_step. `--shard queries` (index replicas of config 1, no collective) and
-`--workload sift1m --shard lists` (config 1 striped, strong scaling) are kept behind flags.
+N > 1, default, `config.workload = "bigann-shape-sharded"` (BASELINE.json configs[4]: 100 M x 128 vectors, every one stored in
+its two nearest partitions = 200 M list entries, split over the ranks: STRONG scaling, queries/s should grow with N): every
+rank generates only its own 100 M / N vectors on the device (chunk-seeded generator), so every one of the B = 1024 lists is
+striped across the ranks by vector id. Every rank answers all 10k queries on its stripe; the per-rank top-k lists are
+all-gathered over NCCL (packed 64-bit keys) and merged with id de-duplication by lira_merge_ranks_dev -- the collective and
+the merge are inside the timed region. The line also carries the time one rank needs for its stripe alone
+(`share_alone_ms`: what the exchange step adds is ms_per_step - share_alone_ms). `--share S` keeps S vectors per rank instead
+(the dataset grows with N: weak scaling of the dataset). `--shard queries` (index replicas of config 1, no collective) and
+`--workload sift1m --shard lists` (config 1 striped) are kept behind flags.
+
+`--workload knn` (one GPU): BASELINE.json configs[1], compute_knn's exact ground truth on SIFT1M shape (1 M x 128 base, 10k
+queries, k = 100) through lira_knn_search_dev, plus the reference program's own use (self-kNN, k + 1 = 11) on a sample.
 
 The reference arm never imports this repo's package or loads liblira_b200.so: it reads the cached workload and operating
 point (built in a separate `--prepare` process when missing) and times oracle/_ref/search_ref, the reference's unmodified
@@ -49,7 +52,8 @@ GEN = {"kind": "gaussian mixture, integer valued", "components": 4096, "weight_l
        "affine": "clip(round(16 x + 100), 0, 255)", "seed": SEED}
 MLP_KEYS = ("distance_net.0", "distance_net.2", "vector_net.0", "vector_net.2", "fc.0", "fc.2")
 REF_SAMPLE = int(os.environ.get("LIRA_REF_SAMPLE", "1000"))   # queries per step of the reference arm (config 1)
-SHARE = 12_500_000        # vectors per rank of the sharded workload
+SHARE = 12_500_000        # vectors per rank of the sharded workload in its weak-scaling form (--share)
+TOTAL = 100_000_000       # the BigANN-100M-shape dataset (BASELINE.json configs[4]): N > 1 default, split over the ranks
 CHUNK = 500_000           # rows per generator chunk (chunk c has its own Philox seed: any rank can produce any chunk)
 REF_SHARD_ROWS = 1_000_000   # reference arm at N > 1: search.cpp runs on rank 0's first two chunks
 REF_SHARD_QUERIES = 200
@@ -393,7 +397,8 @@ def config_sift1m(wl, op, k, world, shard):
             "parallelism": par}
 
 
-def config_shard(meta, op, world):
+def config_shard(meta, op, world, share=None):
+    SHARE = share if share else TOTAL // world   # (shadows the module constant: vectors per rank of THIS run)
     return {"workload": "bigann-shape-sharded", "N": int(world * SHARE), "vectors_per_rank": SHARE, "d": meta["d"], "Q": meta["Q"],
             "B": meta["B"], "k": meta["k"], "n_mul": 2, "redundancy": "full 2x: every vector is stored in its two nearest partitions",
             "list_entries": int(2 * world * SHARE), "generator": dict(GEN, chunk_rows=CHUNK, chunk_seed="43 * 1000003 + 1 + chunk"),
@@ -421,8 +426,13 @@ def save_op(path, op):
     os.replace(tmp, os.path.join(path, "op.json"))
 
 
+def shard_share(args, world):
+    """vectors per rank: --share given = weak scaling (the dataset grows with N); default = the 100 M-vector dataset split over the ranks"""
+    return args.share if args.share else TOTAL // world
+
+
 def shard_op_path(world, args):
-    return os.path.join(CACHE, f"bigann_op_N{world}_Q{args.Q}_B{args.B}_k{args.k}_r{args.recall}_v1")
+    return os.path.join(CACHE, f"bigann_op_N{world}_S{shard_share(args, world)}_Q{args.Q}_B{args.B}_k{args.k}_r{args.recall}_v2")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -444,7 +454,9 @@ def prepare_in_subprocess(args, world, log):
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                 "--master-port", str(free_port())]
     cmd += [os.path.join(ROOT, "bench.py"), "--prepare", "--gpus", str(world), "--k", str(args.k), "--N", str(args.N),
-            "--Q", str(args.Q), "--B", str(args.B), "--recall", str(args.recall)]
+            "--Q", str(args.Q), "--B", str(args.B), "--recall", str(args.recall), "--share", str(args.share)]
+    if args.workload:
+        cmd += ["--workload", args.workload]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_PORT", "MASTER_ADDR",
                                                              "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE",
                                                              "TORCHELASTIC_RUN_ID", "GROUP_WORLD_SIZE", "ROLE_NAME")}
@@ -556,15 +568,15 @@ def run_reference(args, world, log):
         art["x_d"] = x.cpu().numpy().astype(np.float32)
         art["data_2_bkt"] = b2.cpu().numpy().astype(np.int32)
         qps, rec, kind, used = time_search_cpp(args, art, x_q.cpu().numpy(), gt.cpu().numpy(), op["threshold"], log)
-        config = config_shard({"d": d, "Q": Q, "B": B, "k": k}, op, world)
-        sample = (f"rank 0's first {REF_SHARD_ROWS} vectors only (1/{world * SHARE // REF_SHARD_ROWS} of the dataset; search.cpp's time per "
+        config = config_shard({"d": d, "Q": Q, "B": B, "k": k}, op, world, shard_share(args, world))
+        sample = (f"rank 0's first {REF_SHARD_ROWS} vectors only (1/{world * shard_share(args, world) // REF_SHARD_ROWS} of the dataset; search.cpp's time per "
                   f"query grows linearly with the probed entries), first {REF_SHARD_QUERIES} queries per step, threshold "
                   f"{op['threshold']:g}, recall@{k} on that sub-sample {rec:.4f}")
         ms = 1e3 * REF_SHARD_QUERIES / qps
     line = {"metric": "qps_at_recall10_ge_0.95", "value": qps, "unit": "queries/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config,
+            "higher_is_better": True, "scaling": "strong" if (sharded and not args.share) else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config,
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": used, "kind": kind, "sample": sample, "host_cores": cores},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -902,7 +914,8 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
 
 
 def run_shard(args, rank, world, local, dist, log):
-    """N > 1 default: the BigANN-shape workload scaled as N x 12.5 M vectors, every list striped over the ranks."""
+    """N > 1 default: the BigANN-100M-shape dataset (100 M vectors, 200 M list entries) split over the ranks, every list striped
+    by vector id: strong scaling, queries/s grows with N. --share S: S vectors per rank instead (weak scaling)."""
     import torch
     import lira_ann_search_b200 as L
     from lira_ann_search_b200.parallel import allgather_merge
@@ -916,13 +929,13 @@ def run_shard(args, rank, world, local, dist, log):
     if rank != 0:
         mdl, _ = make_shard_model(d, B, k, dev, log)
     _, centres, w = mixture(d, dev)
-    share = args.share
+    share = shard_share(args, world)
     n_chunks = share // CHUNK
     x = torch.empty((share, d), dtype=torch.float32, device=dev)
     for j in range(n_chunks):
-        x[j * CHUNK:(j + 1) * CHUNK] = shard_chunk(rank * (SHARE // CHUNK) + j, d, centres, w, dev)
+        x[j * CHUNK:(j + 1) * CHUNK] = shard_chunk(rank * n_chunks + j, d, centres, w, dev)
     x_q = shard_queries(Q, d, centres, w, dev)
-    base_id = rank * SHARE
+    base_id = rank * share
     # exact ground truth of the whole dataset: per-rank exact kNN (library, base adopted on the device) + the cross-rank merge
     kn = L.KnnIndex(x, "L2")
     Dg, Ig = kn.search_dev(x_q, k)
@@ -1040,7 +1053,7 @@ def run_shard(args, rank, world, local, dist, log):
             return merged
         return out[0], out[1]
 
-    # one rank's share alone (no collective): what a single GPU needs for a 12.5 M-vector dataset
+    # one rank's share alone (no collective): what a single GPU needs for its stripe
     for _ in range(3):
         local_step()
     alone = []
@@ -1121,18 +1134,18 @@ def run_shard(args, rank, world, local, dist, log):
     flops = 2.0 * d * float(np.mean([t["scan_pairs"] for t in tms]))
     ach_tf = flops / (s_ms * 1e-3) / 1e12
     meta = {"d": d, "Q": Q, "B": B, "k": k}
-    cfg = config_shard(meta, op, world)
-    if share != SHARE:
-        cfg["vectors_per_rank"] = share
-        cfg["N"] = world * share
-        cfg["list_entries"] = 2 * world * share
+    cfg = config_shard(meta, op, world, share)
+    strong = not args.share
     line = {
         "metric": "qps_at_recall10_ge_0.95", "value": Q * args.steps / (total_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg, "recall_at_10": rec,
-        "weak_scaling": {"what_grows": "the dataset (vectors_per_rank fixed, N = n_gpus x vectors_per_rank); the query batch is fixed, so "
-                                       "ideal weak scaling keeps queries/s constant while the dataset grows n_gpus-fold",
+        "scaling_note": {"what_is_fixed": ("the dataset: 100 M vectors = 200 M list entries split over the ranks, and the query batch; ideal strong "
+                                          "scaling multiplies queries/s by n_gpus. bench.py --gpus 1 runs the SIFT1M-shape workload "
+                                          "(BASELINE.json configs[0]) instead, so compare N = 2, 4, 8 with each other: queries/s x n_gpus / 2") if strong else
+                                         ("vectors_per_rank (the dataset grows n_gpus-fold, the query batch is fixed): ideal weak scaling keeps "
+                                          "queries/s constant"),
                          "share_alone_ms": alone_ms, "ms_per_step": total_ms / args.steps,
                          "entries_scanned_per_s": op["avg_cmp"] * Q * args.steps / (total_ms * 1e-3),
                          "note": "share_alone_ms = one rank answering the batch on its own stripe, no collective (max over ranks); "
@@ -1158,6 +1171,149 @@ def run_shard(args, rank, world, local, dist, log):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# --workload knn: BASELINE.json configs[1] -- compute_knn's exact ground truth on SIFT1M shape
+# ---------------------------------------------------------------------------------------------
+def knn_data(N, Q, d, dev):
+    import torch
+    _, centres, w = mixture(d, dev)
+    x = torch.cat([shard_chunk(c, d, centres, w, dev) for c in range((N + CHUNK - 1) // CHUNK)])[:N].contiguous()
+    return x, shard_queries(Q, d, centres, w, dev)
+
+
+def knn_cpu_baseline(x_h, q_h, k, n, log):
+    """the oracle's exact kNN (plain C restatement of compute_knn.cpp:208-259, OpenMP over the queries) on the first n queries"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    O.knn(x_h[:20000], q_h[:4], k, O.L2, O.F32, 0)
+    t0 = time.perf_counter()
+    D, I = O.knn(x_h, q_h[:n], k, O.L2, O.F32, 0)
+    dt = time.perf_counter() - t0
+    return n / dt, cores, D, I
+
+
+def run_knn_reference(args, log):
+    import torch
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    d, k, N, Q = 128, 100, args.N, args.Q
+    x, x_q = knn_data(N, Q, d, dev)
+    n = 64
+    qps, cores, _, _ = knn_cpu_baseline(x.cpu().numpy(), x_q.cpu().numpy(), k, n, log)
+    line = {"metric": "exact_knn_queries_per_s", "value": qps, "unit": "queries/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / qps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_knn(N, Q, d, k),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"first {n} of {Q} queries against all {N} base vectors; compute_knn.cpp itself needs Faiss "
+                                       "(absent here), so this is the oracle's restatement of its exact branch, OpenMP over the queries"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_knn(N, Q, d, k):
+    return {"workload": "compute_knn-exact-ground-truth", "N": N, "d": d, "Q": Q, "k": k, "metric": "L2",
+            "generator": dict(GEN, chunk_rows=CHUNK, chunk_seed="43 * 1000003 + 1 + chunk"),
+            "reference": "compute_knn.cpp:208-259 (IndexFlatL2.add + search in 10 000-row batches); --queries mode of bin/compute_knn",
+            "l2_between_steps": "flushed (256 MiB write); the base (128 MB as bytes) is streamed once per 512 queries"}
+
+
+def run_knn(args, rank, local, log):
+    import torch
+    import lira_ann_search_b200 as L
+    dev = f"cuda:{local}"
+    d, k, N, Q = 128, 100, args.N, args.Q
+    x, x_q = knn_data(N, Q, d, dev)
+    kn = L.KnnIndex(x, "L2")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = kn.search_dev(x_q, k, stream=stream.cuda_stream)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        kn.search_dev(x_q, k, out=out, stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    launches0 = L.launch_count()
+    clocks = Clocks(local)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks.mark_begin()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        kn.search_dev(x_q, k, out=out, stream=stream.cuda_stream)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall
+    clocks.mark_end()
+    clk = clocks.stop()
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    launches = L.launch_count() - launches0
+    scan_kind, redo = kn.last_scan_kind, kn.last_redo
+    D, I = out[0].cpu().numpy(), out[1].cpu().numpy()
+    # the reference program's own use: self-kNN with k + 1 = 11 (compute_knn.cpp:237), first 10 000 base rows as the batch
+    self_ms = []
+    o2 = kn.search_dev(x[:10000], 11, stream=stream.cuda_stream)
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        kn.search_dev(x[:10000], 11, out=o2, stream=stream.cuda_stream)
+        e1.record(stream)
+        e1.synchronize()
+        self_ms.append(e0.elapsed_time(e1))
+    self_ok = bool((o2[1][:, 0].cpu().numpy() == np.arange(10000)).mean() > 0.99)   # (exact duplicates may put a twin first)
+    # end to end from host buffers: lira_knn_search uploads the queries and brings D / I back inside the timed region
+    x_q_h = x_q.cpu().numpy()
+    kn.search(x_q_h, k)
+    e2e_s = []
+    for _ in range(5):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Dh, Ih = kn.search(x_q_h, k)
+        e2e_s.append(time.perf_counter() - t0)
+    e2e_t = float(np.median(e2e_s))
+    # check: the oracle on a query sample (bit-identical on integer data), and the CPU baseline in one go
+    n = 64
+    cpu_qps, cores, D_ref, I_ref = knn_cpu_baseline(x.cpu().numpy(), x_q_h, k, n, log)
+    same = bool(np.array_equal(I[:n], I_ref) and np.array_equal(D[:n], D_ref) and np.array_equal(Ih[:n], I_ref))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    ms = total_ms / args.steps
+    flops = 2.0 * N * Q * d
+    ach = flops / (ms * 1e-3) / 1e12
+    line = {
+        "metric": "exact_knn_queries_per_s", "value": Q / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 operands, s32 accumulation (exact)" if scan_kind == "u8" else "f16 operands, f32 accumulation (exact on integer data)",
+        "data": "synthetic", "config": config_knn(N, Q, d, k),
+        "check": {"queries": n, "ids_and_distances_identical_to_oracle": same, "queries_redone_on_cuda_cores": int(redo)},
+        "self_knn_k11": {"batch": 10000, "ms_per_batch": float(np.mean(self_ms)), "self_is_first": self_ok,
+                         "whole_base_estimate_s": float(np.mean(self_ms)) * 1e-3 * N / 10000,
+                         "tflops_algorithmic": 2.0 * N * 10000 * d / (float(np.mean(self_ms)) * 1e-3) / 1e12},
+        "e2e": {"value": Q / e2e_t, "unit": "queries/s", "h2d_bytes_per_step": int(Q * d * 4), "d2h_bytes_per_step": int(Q * k * 12),
+                "api": "lira_knn_search (host queries in, host D / I out; base resident behind the handle)"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                     "flops_algorithmic": flops, "kernel": f"u8_scan_kernel (tcgen05.mma kind::i8), scan kind {scan_kind}",
+                     "what": "2 Q N d over the WHOLE search (seed pass over 16 base segments + filter pass + refine), against the measured "
+                             "cuBLAS bf16 burst figure (the i8 pipe's nominal peak is twice that)",
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback"},
+        "wall_s_timed_region": wall,
+        "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"first {n} of {Q} queries against all {N} base vectors (oracle restatement of compute_knn.cpp:208-259, "
+                                   "OpenMP over the queries)"},
+    }
+    print(json.dumps(line), flush=True)
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -1173,9 +1329,11 @@ def main():
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=2000)
     ap.add_argument("--check", type=int, default=32, help="sharded workload: queries checked against brute force")
-    ap.add_argument("--share", type=int, default=SHARE, help="sharded workload: vectors per rank (multiple of 500 000)")
-    ap.add_argument("--workload", default=None, choices=["sift1m", "bigann"],
-                    help="default: sift1m (config 1) on one GPU, bigann (config 5 shape, N x 12.5 M vectors, lists striped) on several")
+    ap.add_argument("--share", type=int, default=0, help="sharded workload: vectors per rank (multiple of 500 000) = weak scaling; "
+                                                         "default 0 = the 100 M-vector dataset split over the ranks (strong scaling)")
+    ap.add_argument("--workload", default=None, choices=["sift1m", "bigann", "knn"],
+                    help="default: sift1m (config 1) on one GPU, bigann (config 5: 100 M vectors split over the ranks, lists striped) on several; "
+                         "knn: config 2 (compute_knn exact ground truth, k = 100) on one GPU")
     ap.add_argument("--shard", default=None, choices=["queries", "lists"],
                     help="sift1m on N > 1: index replicas + sharded query stream (queries) or striped lists + NCCL merge (lists)")
     args = ap.parse_args()
@@ -1191,7 +1349,10 @@ def main():
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args, world, log)
+            if args.workload == "knn":
+                run_knn_reference(args, log)
+            else:
+                run_reference(args, world, log)
         return
 
     import torch
@@ -1203,7 +1364,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     try:
-        if args.workload == "bigann":
+        if args.workload == "knn":
+            if rank == 0:
+                run_knn(args, rank, local, log)
+        elif args.workload == "bigann":
             run_shard(args, rank, world, local, dist, log)
         else:
             run_sift1m(args, rank, world, local, dist, log)

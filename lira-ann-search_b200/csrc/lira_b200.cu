@@ -261,6 +261,7 @@ struct lira_index {
     float tc_vmax = 0.0f;        // largest |v| of the index (mode 2: error margin)
     bool use_tc = true;
     bool last_u8 = false;        // the last tensor-core batch ran the byte scan
+    int last_parts = 4;          // candidate regions per pair of the last tensor-core batch
     int last_path = 0;           // 0 = CUDA-core scan, 1 = tensor-core scan
     int last_redo = 0;           // queries of the last tensor-core batch redone on the CUDA cores
     bool timing = false, timing_pending = false;
@@ -764,6 +765,7 @@ struct TcStage {   // one tensor-core batch after the grouping: what the seed / 
     int* filter_counter = nullptr;
     bool u8 = false;                 // byte-valued index and batch: the integer tensor-core scan (u8_scan_kernels.cuh)
     bool counts_zeroed = false;      // byte scan: the pair counters were zeroed by the front end (fused flow)
+    bool private_regions = false;    // byte scan, exhaustive probe sets: one candidate region per (pair, column part), no atomics
     int seg_rows = U8_SEG_ROWS;      // byte scan: rows of a list per work item (exhaustive probe sets: whole lists)
 };
 
@@ -784,6 +786,7 @@ static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg)
     up.cand_key = nullptr;
     up.cand_count = nullptr;
     up.seed_out = nullptr;
+    up.private_regions = sg.private_regions ? 1 : 0;
     up.cap = 0;
     up.k = sg.k;
     up.is_ip = h->metric == LIRA_METRIC_IP;
@@ -849,12 +852,14 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
     const bool approx = h->tc_mode == 2;
     // one private candidate region per (pair, column part); every valid pair's owner writes its count
     // (byte scan: ONE region per pair, slots taken with atomics, counters zeroed beforehand)
-    const int cap = sg.u8 ? (k <= TC_KMAX_TIGHTEN ? U8_CAPK : U8_CAPP) : (k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP);   // fp16, k <= 16: full regions are compacted in the kernel
-    const int parts = sg.u8 ? 1 : TC_PARTS;
+    const int cap = sg.u8 ? (sg.private_regions ? (k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP) : (k <= TC_KMAX_TIGHTEN ? U8_CAPK : U8_CAPP))
+                          : (k <= TC_KMAX_TIGHTEN ? TC_CAPK : TC_CAPP);   // fp16, k <= 16: full regions are compacted in the kernel
+    const int parts = (sg.u8 && !sg.private_regions) ? 1 : TC_PARTS;
+    h->last_parts = parts;
     h->last_u8 = sg.u8;
     if (int rc = ws.cand_key.ensure((size_t)P * parts * cap * 8)) return rc;
     if (int rc = ws.cand_count.ensure((size_t)P * parts * 4)) return rc;
-    if (sg.u8 && !sg.counts_zeroed) LIRA_CUDA_OK(cudaMemsetAsync(ws.cand_count.p, 0, (size_t)P * 4, st));
+    if (sg.u8 && !sg.private_regions && !sg.counts_zeroed) LIRA_CUDA_OK(cudaMemsetAsync(ws.cand_count.p, 0, (size_t)P * 4, st));
     TcParams tp;
     tp.group_queries = ws.group_queries.as<int>();
     tp.list_offsets = h->d_offsets;
@@ -901,8 +906,8 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
                     h->vecs, (long long)h->ds, sg.d_q, sg.ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, sg.margin_c, sg.margin_abs,
                     1.0f / (h->tc_sigma * h->tc_sigma)};
     const int warps = 8;
-    if (sg.u8 && k <= 32) refine_topk_kernel<1, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else if (sg.u8) refine_topk_kernel<4, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    if (parts == 1 && k <= 32) refine_topk_kernel<1, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    else if (parts == 1) refine_topk_kernel<4, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
     else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
@@ -930,7 +935,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // byte-valued index: the integer tensor-core scan. Threshold / top-n / explicit probe sets need k <= 16 (per-list bounds of
     // the in-kernel seed); exhaustive probe sets (exact kNN over disjoint base segments) pool the seed candidates of the first
     // U8_SEED_LISTS lists, any k <= 128, as long as those lists hold enough candidates
-    const int u8_seed_lists = std::min(h->B, U8_SEED_LISTS);
+    const int u8_seed_lists = std::min(h->B, getenv("LIRA_U8_SEED_LISTS") ? std::max(1, atoi(getenv("LIRA_U8_SEED_LISTS"))) : U8_SEED_LISTS);
     // Measured (profiles/r2_u8_scan_notes.md): with its per-column norm subtraction the byte scan's epilogue costs ~3x the fp16
     // scan's, so for threshold / top-n probe sets it only matches the fp16 scan; it is the default for exhaustive probe sets
     // (no CUDA-core seed pass, half the operand bytes) and opt-in (LIRA_U8_SEARCH=1) for the rest.
@@ -1121,7 +1126,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     }
     if (!seed_on_main && !use_u8 && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));   // (the other seeds' own grouping is not part of the scan time)
     TcStage sg;
-    sg.u8 = use_u8; sg.seg_rows = u8_seg_rows;
+    sg.u8 = use_u8; sg.seg_rows = u8_seg_rows; sg.private_regions = use_u8 && ps.kind == 2;
     sg.Q = Q; sg.P = P; sg.po = po; sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq; sg.d_D = d_D; sg.d_I = d_I;
     sg.redo_count = ws.flags.as<int>() + 1; sg.tmap_q = &tmap_q; sg.margin_c = margin_c; sg.margin_abs = margin_abs;
     sg.filter_counter = ws.n_items.as<int>() + 1;
@@ -1194,7 +1199,7 @@ static void tc_debug_stats(lira_index* h, Workspace& ws, long long Q, long long 
     cudaMemcpy(&n_slots, ws.group_offsets.as<long long>() + h->B, 8, cudaMemcpyDeviceToHost);
     P = std::min(P, n_slots);
     if (P <= 0) return;
-    const int parts = h->last_u8 ? 1 : TC_PARTS;   // (byte scan: one region per pair)
+    const int parts = h->last_parts;
     std::vector<int> cc((size_t)P * parts);
     cudaMemcpy(cc.data(), ws.cand_count.p, (size_t)P * parts * 4, cudaMemcpyDeviceToHost);
     std::vector<int> sorted(cc);

@@ -47,7 +47,8 @@ __host__ __device__ constexpr size_t u8_smem_bytes(bool seed) {
            + (size_t)U8_NNORM * U8_NS * 4                                             // norms ring
            + 512                                                                      // barriers, item queue, tmem slot
            + (size_t)U8_NQ * U8_ITEM_Q * 12                                           // per queued item and row: query id, |q|^2, bound
-           + (seed ? (size_t)U8_PARTS * U8_ITEM_Q * 16 : 0);                          // seed pass: 4 values per (row, part)
+           + (seed ? (size_t)U8_PARTS * U8_ITEM_Q * 16                                // seed pass: 4 values per (row, part)
+                   : (size_t)U8_PARTS * U8_ITEM_Q * 4);                               // filter pass: private region fill per (row, part)
 }
 
 // D = S32, A = B = unsigned 8 bit, both K-major, M = 128, N = 256 / 128
@@ -75,7 +76,9 @@ struct U8Params {
     const float* qnorm;              // [Q] |q|^2 (exact integers)
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score as f32_to_ordered(T): written by the seed pass, read by the filter
     unsigned long long* cand_key;    // [P, cap] (score, list entry) keys: one region per (query, list) pair
-    int* cand_count;                 // [P] zeroed before the filter pass
+    int* cand_count;                 // [P] zeroed before the filter pass (private_regions: [U8_PARTS P], written by the owners)
+    int private_regions;             // exhaustive probe sets (one work item per pair): one region per (pair, column part) filled by its
+                                     //   owner thread, no atomics (their round trip is what a pass with hundreds of survivors per query waits for)
     int* seed_out;                   // seed pass, exhaustive probe sets: [P, U8_PARTS, 4] the 16 best scores of every pair go here instead
                                      //   of being turned into a bound in the kernel (u8_seed_select_kernel pools them); null otherwise
     int cap;
@@ -108,6 +111,15 @@ __device__ __noinline__ bool u8_append4(int x0, int x1, int x2, int x3, int lim,
     return pos > cap;
 }
 
+// the same for a region owned by the calling thread: returns the new fill (it may run past cap)
+__device__ __noinline__ int u8_append4_private(int x0, int x1, int x2, int x3, int lim, int qn, uint32_t e0, unsigned long long* cand, int cnt, int cap) {
+    if (x0 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x0), e0); ++cnt; }
+    if (x1 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x1), e0 + 1); ++cnt; }
+    if (x2 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x2), e0 + 2); ++cnt; }
+    if (x3 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x3), e0 + 3); ++cnt; }
+    return cnt;
+}
+
 template <bool SEED, bool IP>
 __global__ void __launch_bounds__(U8_THREADS, 1)   // (96 registers per thread: 19 warps x 104 no longer fit the register file)
 u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
@@ -135,6 +147,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     int* s_qn = s_q + U8_NQ * U8_ITEM_Q;                        // [U8_NQ][512] |q|^2 (0 for IP)
     int* s_lim = s_qn + U8_NQ * U8_ITEM_Q;                      // [U8_NQ][512] an entry survives iff u >= lim
     int4* s_x = reinterpret_cast<int4*>(s_lim + U8_NQ * U8_ITEM_Q);   // [U8_PARTS][512]: seed pass, the 4 largest u per (row, part)
+    int* s_cnt = s_lim + U8_NQ * U8_ITEM_Q;                           // [U8_PARTS][512]: filter pass, fill of the private regions (same area)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_PROD = U8_EPI_WARPS, W_MMA = W_PROD + 1, W_ALLOC = W_PROD + 2;
@@ -374,6 +387,8 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (SEED) {
                 if (n > 0) named_bar_sync(2, U8_EPI_WARPS * 32);   // the previous item's values have been read
                 for (int t = 0; t < ntile; ++t) s_x[part * U8_ITEM_Q + t * U8_M + trow] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+            } else if (p.private_regions) {
+                for (int t = 0; t < ntile; ++t) s_cnt[part * U8_ITEM_Q + t * U8_M + trow] = 0;   // (only this thread touches its entries)
             }
             uint32_t ebase = (uint32_t)it.lo + part * 32;
             int left = n_rows - part * 32;
@@ -399,17 +414,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const int lim = SEED ? 0 : iq_lim[row];
                     int a[4];
                     if (SEED) { const int4 v = s_x[part * U8_ITEM_Q + row]; a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-                    // both 128-column halves of the unit are requested at once and the accumulator goes back to the MMA warp as
-                    // soon as they are in registers: the handshake round trip, not the arithmetic, paces short work items
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * U8_NS + part * 32;
-                    uint32_t ra[32], rb[32];
-                    tc_ld32_async(taddr, ra);
-                    if (nh > 1) tc_ld32_async(taddr + 128, rb);
-                    tc_ld_wait(ra);
-                    tc_ld_wait(rb);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
                     auto process = [&](uint32_t (&ru)[32], const int h) {
                         int r[32];
                         if (IP) {
@@ -449,24 +454,49 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                             if (__any_sync(0xffffffffu, mx >= lim) && !(p.exp & 1)) {
                                 if ((p.exp & 64) && lane == 0) atomicAdd(p.dbg, 1);
                                 const size_t slot = (size_t)(it.q_begin + row);
-                                unsigned long long* cand = p.cand_key + slot * cap;
-                                int* cnt_ptr = p.cand_count + slot;
                                 const uint32_t eb = ebase + h * 128;
                                 const int qn = iq_qn[row];
                                 bool over = false;
+                                // which blocks of 4 columns hold a passing entry in SOME lane: one warp reduction, then warp-uniform
+                                // branches (a vote per block would put eight dependent round trips on the warp's critical path)
+                                uint32_t qm = 0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    // one vote per block of 4 columns (warp-uniform branch): the lanes with a passing entry append it
-                                    if (__any_sync(0xffffffffu, m4[j] >= lim))
-                                        over |= u8_append4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt_ptr, cap);
+                                for (int j = 0; j < 8; ++j) qm |= (m4[j] >= lim) ? (1u << j) : 0u;
+                                const uint32_t um = __reduce_or_sync(0xffffffffu, qm);
+                                if (p.private_regions) {
+                                    unsigned long long* cand = p.cand_key + (slot * U8_PARTS + part) * cap;
+                                    int cnt = s_cnt[part * U8_ITEM_Q + row];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        if (um & (1u << j))
+                                            cnt = u8_append4_private(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt, cap);
+                                    }
+                                    s_cnt[part * U8_ITEM_Q + row] = cnt;
+                                    over = cnt > cap;
+                                } else {
+                                    unsigned long long* cand = p.cand_key + slot * cap;
+                                    int* cnt_ptr = p.cand_count + slot;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        if (um & (1u << j))
+                                            over |= u8_append4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt_ptr, cap);
+                                    }
                                 }
                                 if (over) iq_lim[row] = 0x7FFFFFFF;   // the region overflowed (the query is redone exactly): stop collecting
                             }
                         }
                     };
-                    if (!(p.exp & 2)) {
-                        process(ra, 0);
-                        if (nh > 1) process(rb, 1);
+#pragma unroll 1
+                    for (int h = 0; h < nh; ++h) {   // the two 128-column halves of the accumulator, one after the other
+                        uint32_t ra[32];
+                        tc_ld32_async(taddr + h * 128, ra);
+                        tc_ld_wait(ra);
+                        if (h == nh - 1) {   // the thread's last columns of this unit are in registers: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
+                        }
+                        if (!(p.exp & 2)) process(ra, h);
                     }
                     if (SEED) s_x[part * U8_ITEM_Q + row] = make_int4(a[0], a[1], a[2], a[3]);
                 }
@@ -502,6 +532,12 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         const float tk = tc_pick16(v, p.k - 1);   // = -(k-th largest u); 2^31 when fewer than k entries were seen
                         if (tk < 1073741824.f) atomicMin(p.thr + iq_q[row], f32_to_ordered((float)qn + tk));
                     }
+                }
+            }
+            if (!SEED && p.private_regions) {
+                for (int t = 0; t < ntile; ++t) {
+                    const int row = t * U8_M + trow;
+                    if (row < it.q_count) p.cand_count[(size_t)(it.q_begin + row) * U8_PARTS + part] = s_cnt[part * U8_ITEM_Q + row];
                 }
             }
             // the item's per-row data has been read: its queue slot may be reused
