@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn the raw outputs of tools/profile_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/:
    tools/make_profiles.py <tag> <round-prefix>     e.g.  tools/make_profiles.py r1b r1"""
-import csv, json, os, subprocess, sys
+import csv, hashlib, json, os, subprocess, sys
 tag, rnd = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
@@ -18,7 +18,7 @@ with open(os.path.join(P, f"{rnd}_launches.csv"), "w") as f:
 h, data = rows[hi], rows[hi + 1:]
 kn, mv, gs = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size")
 L = [(r[kn].split("(")[0].replace("void ", "").replace("lira::", ""), float(r[mv].replace(",", "")), r[gs]) for r in data if len(r) > mv]
-idx = [i for i, (n, _, _) in enumerate(L) if n.startswith("split_rows")]
+idx = [i for i, (n, _, _) in enumerate(L) if n.startswith("prep_queries")]
 step = L[idx[-2]:]
 step = step[:[i for i, (n, _, _) in enumerate(step) if n.startswith("refine_topk")][0] + 1]
 tot = sum(t for _, t, _ in step)
@@ -53,7 +53,13 @@ with open(os.path.join(P, f"{rnd}_scan_ncu_metrics.txt"), "w") as f:
                 v, u = float(d[name].replace(",", "")), units[hdr.index(name)].lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
             rd, wr = b("dram__bytes_read.sum"), b("dram__bytes_write.sum")
-            traffic = {"kernel": "tc_scan_kernel<false, false>", "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+            hsh = hashlib.sha256()
+            cs = os.path.join(ROOT, "lira-ann-search_b200", "csrc")
+            for fn in sorted(os.listdir(cs)):
+                if fn.endswith((".cu", ".cuh")):
+                    hsh.update(open(os.path.join(cs, fn), "rb").read())
+            traffic = {"kernel": "tc_scan_kernel<false, false>", "workload": "sift1m-shape", "source_hash": hsh.hexdigest()[:16],
+                       "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "algorithmic_bytes": json.loads(line)["roofline"]["algorithmic_bytes"],
                        "source": f"ncu --set full --clock-control none (gpurun_out/{tag}_tc_scan.ncu-rep): dram__bytes_read.sum + dram__bytes_write.sum of one "
                                  "launch, bench.py config 1, 10k-query batch. The kernel streams the fp16 shadow copy of the list rows (half the "
