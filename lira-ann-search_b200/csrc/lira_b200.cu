@@ -2290,22 +2290,24 @@ int lira_probe_search_submit(lira_index_t* h, lira_model_t* m, const float* q, i
         LIRA_CUDA_OK(cudaHostAlloc(&s.pin_out, total + total / 4, cudaHostAllocDefault));
         s.pin_out_cap = total + total / 4;
     }
-    // queries: through a pinned staging buffer of this handle. A pageable cudaMemcpyAsync would be
-    // staged by the driver synchronously and in small pieces; and a caller's own pinned array is not necessarily the faster
-    // source either (measured on this pool: pages pinned by another allocator, possibly on the other NUMA node, upload at
-    // less than half the rate of this buffer), so LIRA_DIRECT_PINNED=1 is needed to copy straight from it
+    // queries: a caller's pinned array is copied from directly (the copy engine does the work while this thread goes on to
+    // enqueue the batch); a pageable one goes through a pinned staging buffer of this handle -- cudaMemcpyAsync from pageable
+    // memory would be staged by the driver synchronously and in small pieces (that memcpy is ~0.3 ms of this thread's time
+    // per 5 MB batch, the largest host-side cost of a batch: callers that can should hand over pinned arrays).
+    // LIRA_STAGE_PINNED=1 stages pinned arrays too (on this pool, pages pinned by another allocator upload at about half
+    // the rate of this buffer: worth it only when the upload, not the host thread, is the bottleneck).
     cudaPointerAttributes attr;
     const bool pageable = cudaPointerGetAttributes(&attr, q) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
     cudaGetLastError();
     const void* src = q;
-    if (pageable || !getenv("LIRA_DIRECT_PINNED")) {
+    if (pageable || getenv("LIRA_STAGE_PINNED")) {
         if (bq > s.pin_in_cap) {
             if (s.pin_in) cudaFreeHost(s.pin_in);
             s.pin_in = nullptr; s.pin_in_cap = 0;
             LIRA_CUDA_OK(cudaHostAlloc(&s.pin_in, bq + bq / 4, cudaHostAllocDefault));
             s.pin_in_cap = bq + bq / 4;
         }
-        memcpy(s.pin_in, q, bq);
+        memcpy(s.pin_in, q, bq);   // (spreading this over helper threads was measured slower: creating them costs more than it saves)
         src = s.pin_in;
     }
     LIRA_CUDA_OK(cudaMemcpyAsync(s.q.p, src, bq, cudaMemcpyHostToDevice, h->st_in));
