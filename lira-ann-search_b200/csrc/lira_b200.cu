@@ -251,7 +251,7 @@ struct lira_index {
     bool has8 = false;           // vecs8 / nv_i exist
     bool prefer_u8 = false;      // exact-kNN handles: the byte copy is the one built at create time
     uint8_t* vecs8 = nullptr;    // [E + 256, d8]
-    int* nv_i = nullptr;         // [E + 256] |v|^2 (L2) or 0 (IP)
+    int* nv_i = nullptr;         // [E + 256] -|v|^2 (L2) or 0 (IP)
     int d8 = 0;                  // round_up(d, 16)
     int u8_max_nseg = 1;         // most row segments (of U8_SEG_ROWS rows) any list is cut into
     long long u8_nseg_total = 0; // segments of all lists
@@ -780,6 +780,7 @@ static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg)
     up.d8 = h->d8;
     up.seg_rows = sg.seg_rows;
     up.nv = h->nv_i;
+    up.mul = 2;
     up.dbg = ws.n_items.as<int>() + 10;
     up.qnorm = ws.qnorm.as<float>();
     up.thr = ws.thr.as<uint32_t>();

@@ -72,7 +72,8 @@ struct U8Params {
     int nk;                          // K blocks of 128 bytes (1 or 2)
     int d8;                          // padded row length in bytes (multiple of 16)
     int seg_rows;                    // rows per segment (multiple of 256)
-    const int* nv;                   // [E + 256] |v|^2 per list entry (L2) or 0 (IP)
+    const int* nv;                   // [E + 256] -|v|^2 per list entry (L2) or 0 (IP)
+    int mul;                         // 2: u = mul acc + nv (kept a run-time value on purpose, see the epilogue)
     const float* qnorm;              // [Q] |q|^2 (exact integers)
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score as f32_to_ordered(T): written by the seed pass, read by the filter
     unsigned long long* cand_key;    // [P, cap] (score, list entry) keys: one region per (query, list) pair
@@ -421,14 +422,19 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
                             for (int i = 0; i < 32; ++i) r[i] = (int)ru[i];
                         } else {
+                            // u = 2 acc - |v|^2 as ONE integer multiply-add per column: the factor comes from the parameter block (so that
+                            // it stays an IMAD, which issues on the FMA pipe) and the staged norms are stored negated; as IADD3 the
+                            // subtraction shares the half-rate ALU pipe with the max tree, which is what bounds this epilogue (ncu: ALU
+                            // pipe 70 % active, tensor pipe 29 %)
+                            const int mul = p.mul;
                             const int4* nv4 = reinterpret_cast<const int4*>(nvc + h * 128);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int4 nv = nv4[i];
-                                r[4 * i + 0] = 2 * (int)ru[4 * i + 0] - nv.x;
-                                r[4 * i + 1] = 2 * (int)ru[4 * i + 1] - nv.y;
-                                r[4 * i + 2] = 2 * (int)ru[4 * i + 2] - nv.z;
-                                r[4 * i + 3] = 2 * (int)ru[4 * i + 3] - nv.w;
+                                r[4 * i + 0] = (int)ru[4 * i + 0] * mul + nv.x;
+                                r[4 * i + 1] = (int)ru[4 * i + 1] * mul + nv.y;
+                                r[4 * i + 2] = (int)ru[4 * i + 2] * mul + nv.z;
+                                r[4 * i + 3] = (int)ru[4 * i + 3] * mul + nv.w;
                             }
                         }
                         // columns past the end of the segment hold other rows
@@ -592,7 +598,7 @@ __global__ void u8_seed_items_kernel(const ScanItem* __restrict__ items, const i
     }
 }
 
-// the byte shadow copy of the list rows: x8[n, d8] = uint8(x) (zero padded) and nv[n] = |x|^2 (L2) or 0 (IP) as int32
+// the byte shadow copy of the list rows: x8[n, d8] = uint8(x) (zero padded) and nv[n] = -|x|^2 (L2) or 0 (IP) as int32
 __global__ void shadow_rows_u8_kernel(const float* __restrict__ x, long ld, int d, long long n, const float* __restrict__ norm,
                                       int is_ip, uint8_t* __restrict__ x8, int d8, int* __restrict__ nv) {
     const int per_row = d8 / 4;
@@ -604,7 +610,7 @@ __global__ void shadow_rows_u8_kernel(const float* __restrict__ x, long ld, int 
         if (c < d) v = *reinterpret_cast<const float4*>(x + row * ld + c);   // (ld and the padding up to round_up(d, 4) are zero filled)
         const uint32_t pk = (uint32_t)(int)v.x | ((uint32_t)(int)v.y << 8) | ((uint32_t)(int)v.z << 16) | ((uint32_t)(int)v.w << 24);
         *reinterpret_cast<uint32_t*>(x8 + row * d8 + c) = pk;
-        if (c == 0) nv[row] = is_ip ? 0 : (int)norm[row];
+        if (c == 0) nv[row] = is_ip ? 0 : -(int)norm[row];
     }
 }
 
