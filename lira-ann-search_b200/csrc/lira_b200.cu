@@ -765,6 +765,7 @@ struct TcStage {   // one tensor-core batch after the grouping: what the seed / 
     int* filter_counter = nullptr;
     bool u8 = false;                 // byte-valued index and batch: the integer tensor-core scan (u8_scan_kernels.cuh)
     bool counts_zeroed = false;      // byte scan: the pair counters were zeroed by the front end (fused flow)
+    int q_mod = 0;                   // byte scan, exhaustive probe sets: the batch size (one copy of the query rows serves every list)
     bool private_regions = false;    // byte scan, exhaustive probe sets: one candidate region per (pair, column part), no atomics
     int seg_rows = U8_SEG_ROWS;      // byte scan: rows of a list per work item (exhaustive probe sets: whole lists)
 };
@@ -779,6 +780,7 @@ static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg)
     up.nk = (h->d8 + U8_KB - 1) / U8_KB;
     up.d8 = h->d8;
     up.seg_rows = sg.seg_rows;
+    up.q_mod = sg.q_mod;
     up.nv = h->nv_i;
     up.mul = 2;
     up.dbg = ws.n_items.as<int>() + 10;
@@ -936,7 +938,9 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // byte-valued index: the integer tensor-core scan. Threshold / top-n / explicit probe sets need k <= 16 (per-list bounds of
     // the in-kernel seed); exhaustive probe sets (exact kNN over disjoint base segments) pool the seed candidates of the first
     // U8_SEED_LISTS lists, any k <= 128, as long as those lists hold enough candidates
-    const int u8_seed_lists = std::min(h->B, getenv("LIRA_U8_SEED_LISTS") ? std::max(1, atoi(getenv("LIRA_U8_SEED_LISTS"))) : U8_SEED_LISTS);
+    // (k > 16: twice the seed sample -- the tighter bound saves more in the filter pass than the longer seed pass costs: measured)
+    const int u8_seed_lists = std::min(h->B, getenv("LIRA_U8_SEED_LISTS") ? std::max(1, atoi(getenv("LIRA_U8_SEED_LISTS")))
+                                                                          : (k > TC_KMAX_TIGHTEN ? 2 * U8_SEED_LISTS : U8_SEED_LISTS));
     // Measured (profiles/r2_u8_scan_notes.md): with its per-column norm subtraction the byte scan's epilogue costs ~3x the fp16
     // scan's, so for threshold / top-n probe sets it only matches the fp16 scan; it is the default for exhaustive probe sets
     // (no CUDA-core seed pass, half the operand bytes) and opt-in (LIRA_U8_SEARCH=1) for the rest.
@@ -999,11 +1003,13 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     CUtensorMap tmap_q;
     if (use_u8) {
         // (the flag is CLEARED when a query value is not an integer in [0, 255]: the batch then takes the fp16 route)
-        if (int rc = ws.gq.ensure((size_t)(P + U8_ITEM_Q) * h->d8)) return rc;
-        gather_group_queries_u8_kernel<<<grid_for(P * (h->d8 / 4), 256, 148 * 16), 256, 0, st>>>(
-            d_q, ldq, h->ds, ws.group_queries.as<int>(), P, ws.group_offsets.as<long long>() + h->B, ws.gq.as<uint8_t>(), h->d8, ws.flags.as<int>());
+        // (exhaustive probe sets: the first Q slots are the batch in query order, and one copy of the rows serves every list)
+        const long long Pg = ps.kind == 2 ? Q : P;
+        if (int rc = ws.gq.ensure((size_t)(Pg + U8_ITEM_Q) * h->d8)) return rc;
+        gather_group_queries_u8_kernel<<<grid_for(Pg * (h->d8 / 4), 256, 148 * 16), 256, 0, st>>>(
+            d_q, ldq, h->ds, ws.group_queries.as<int>(), Pg, ws.group_offsets.as<long long>() + h->B, ws.gq.as<uint8_t>(), h->d8, ws.flags.as<int>());
         LIRA_LAUNCH_CHECK();
-        if (int rc = make_tmap_u8(&tmap_q, ws.gq.p, P, h->d8, h->d8)) return rc;
+        if (int rc = make_tmap_u8(&tmap_q, ws.gq.p, Pg, h->d8, h->d8)) return rc;
     } else {
         if (int rc = ws.gq.ensure((size_t)(P + TC_M) * h->d16 * 2)) return rc;
         gather_group_queries_kernel<<<grid_for(P * (h->d16 / 4), 256, 148 * 16), 256, 0, st>>>(d_q, ldq, h->ds, ws.group_queries.as<int>(), P,
@@ -1036,7 +1042,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
             ws.items.as<ScanItem>(), ctl, S, ws.seed_items.as<ScanItem>(), ctl + 4);
         LIRA_LAUNCH_CHECK();
         TcStage ss;
-        ss.k = k; ss.u8 = true; ss.seg_rows = u8_seg_rows;
+        ss.k = k; ss.u8 = true; ss.seg_rows = u8_seg_rows; ss.q_mod = (int)Q;
         U8Params up = u8_params(h, ws, ss);
         up.items = ws.seed_items.as<ScanItem>();
         up.n_items = ctl + 4;
@@ -1127,7 +1133,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     }
     if (!seed_on_main && !use_u8 && h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[4], st));   // (the other seeds' own grouping is not part of the scan time)
     TcStage sg;
-    sg.u8 = use_u8; sg.seg_rows = u8_seg_rows; sg.private_regions = use_u8 && ps.kind == 2;
+    sg.u8 = use_u8; sg.seg_rows = u8_seg_rows; sg.private_regions = use_u8 && ps.kind == 2; sg.q_mod = (use_u8 && ps.kind == 2) ? (int)Q : 0;
     sg.Q = Q; sg.P = P; sg.po = po; sg.k = k; sg.dedup = dedup; sg.d_q = d_q; sg.ldq = ldq; sg.d_D = d_D; sg.d_I = d_I;
     sg.redo_count = ws.flags.as<int>() + 1; sg.tmap_q = &tmap_q; sg.margin_c = margin_c; sg.margin_abs = margin_abs;
     sg.filter_counter = ws.n_items.as<int>() + 1;

@@ -72,6 +72,8 @@ struct U8Params {
     int nk;                          // K blocks of 128 bytes (1 or 2)
     int d8;                          // padded row length in bytes (multiple of 16)
     int seg_rows;                    // rows per segment (multiple of 256)
+    int q_mod;                       // > 0: exhaustive probe sets -- every list's group is the whole batch in query order, so the A tiles
+                                     //   are read from ONE [Q, d8] copy of the queries (row = slot % Q) instead of one copy per list
     const int* nv;                   // [E + 256] -|v|^2 per list entry (L2) or 0 (IP)
     int mul;                         // 2: u = mul acc + nv (kept a run-time value on purpose, see the epilogue)
     const float* qnorm;              // [Q] |q|^2 (exact integers)
@@ -274,7 +276,8 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[x], (uint32_t)nk * U8_KBLK_BYTES);
                     for (int kb = 0; kb < nk; ++kb)
-                        tma_load_2d(sA + (size_t)(x * nk + kb) * U8_KBLK_BYTES, &tmap_q, kb * U8_KB, it.q_begin + t * U8_M, &a_full[x]);
+                        tma_load_2d(sA + (size_t)(x * nk + kb) * U8_KBLK_BYTES, &tmap_q, kb * U8_KB,
+                                    (p.q_mod > 0 ? it.q_begin % p.q_mod : it.q_begin) + t * U8_M, &a_full[x]);
                 }
                 __syncwarp();
             }
@@ -560,32 +563,45 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 }
 
 // exhaustive probe sets (exact kNN over disjoint base segments; group slot of (query q, list b) = b Q + q): T[q] = k-th
-// smallest of the 16 S scores the seed pass kept for the query's first S lists -- all distinct entries. One warp per query.
+// smallest of the 16 S scores the seed pass kept for the query's first S lists (S <= 32) -- all distinct entries. One warp per
+// query: the values sit in registers (16 per lane) and the k-th smallest is found bit by bit (radix select on the
+// order-preserving unsigned image of the int32 scores: 32 rounds of 16 compares + one warp sum).
 __global__ void __launch_bounds__(256) u8_seed_select_kernel(const int* __restrict__ seed_out, int Q, int S, int k, uint32_t* __restrict__ thr) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
-    unsigned long long key[4];
+    uint32_t v[16];   // lane l holds the 16 values of list l (missing: 0xFFFFFFFF)
+    if (lane < S) {
+        const int4* src = reinterpret_cast<const int4*>(seed_out + ((size_t)lane * Q + q) * (U8_PARTS * 4));
 #pragma unroll
-    for (int s = 0; s < 4; ++s) key[s] = KEY_INF;
-    unsigned long long kth = KEY_INF;
-    uint32_t tag = 0;
-    for (int b0 = 0; b0 < S; b0 += 2) {   // two lists (32 values) per round, one per lane
-        const int b = b0 + (lane >> 4);
-        int v = INT_MAX;
-        if (b < S) v = seed_out[((size_t)b * Q + q) * (U8_PARTS * 4) + (lane & 15)];
-        uint32_t mm = __ballot_sync(0xffffffffu, v != INT_MAX);
-        while (mm) {
-            const int sl = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const unsigned long long y = make_key((float)__shfl_sync(0xffffffffu, v, sl), tag++);
-            if (y < kth) {
-                warp_sorted_insert<4>(key, y, lane);
-                kth = warp_sorted_get<4>(key, k - 1);
-            }
+        for (int j = 0; j < 4; ++j) {
+            const int4 x = src[j];
+            v[4 * j + 0] = (uint32_t)x.x ^ 0x80000000u; v[4 * j + 1] = (uint32_t)x.y ^ 0x80000000u;
+            v[4 * j + 2] = (uint32_t)x.z ^ 0x80000000u; v[4 * j + 3] = (uint32_t)x.w ^ 0x80000000u;
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0xFFFFFFFFu;
     }
-    if (lane == 0) thr[q] = kth == KEY_INF ? 0xFF800000u /* +inf */ : (uint32_t)(kth >> 32);
+    // (INT_MAX marks a missing value: its image 0xFFFFFFFF is the largest key)
+    int valid = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) valid += v[j] != 0xFFFFFFFFu;
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if (valid < k) {
+        if (lane == 0) thr[q] = 0xFF800000u;   // f32_to_ordered(+inf): fewer than k candidates seen
+        return;
+    }
+    uint32_t res = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t t = res | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) c += v[j] < t;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c < k) res = t;   // fewer than k keys below t: the k-th smallest is at least t
+    }
+    if (lane == 0) thr[q] = f32_to_ordered((float)(int)(res ^ 0x80000000u));
 }
 
 // items of lists 0 .. S-1 (the seed pass of exhaustive probe sets runs on these only)
