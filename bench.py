@@ -398,7 +398,7 @@ def config_sift1m(wl, op, k, world, shard):
 
 
 def config_shard(meta, op, world, share=None):
-    SHARE = share if share else TOTAL // world   # (shadows the module constant: vectors per rank of THIS run)
+    SHARE = share if share else (TOTAL // world if world > 1 else 12_500_000)   # (shadows the module constant: vectors per rank of THIS run)
     return {"workload": "bigann-shape-sharded", "N": int(world * SHARE), "vectors_per_rank": SHARE, "d": meta["d"], "Q": meta["Q"],
             "B": meta["B"], "k": meta["k"], "n_mul": 2, "redundancy": "full 2x: every vector is stored in its two nearest partitions",
             "list_entries": int(2 * world * SHARE), "generator": dict(GEN, chunk_rows=CHUNK, chunk_seed="43 * 1000003 + 1 + chunk"),
@@ -428,7 +428,9 @@ def save_op(path, op):
 
 def shard_share(args, world):
     """vectors per rank: --share given = weak scaling (the dataset grows with N); default = the 100 M-vector dataset split over the ranks"""
-    return args.share if args.share else TOTAL // world
+    if args.share:
+        return args.share
+    return TOTAL // world if world > 1 else SHARE   # (one GPU cannot hold the fp32 rows of all 200 M entries: one eighth of them)
 
 
 def shard_op_path(world, args):
@@ -1135,7 +1137,7 @@ def run_shard(args, rank, world, local, dist, log):
     ach_tf = flops / (s_ms * 1e-3) / 1e12
     meta = {"d": d, "Q": Q, "B": B, "k": k}
     cfg = config_shard(meta, op, world, share)
-    strong = not args.share
+    strong = not args.share and world > 1
     line = {
         "metric": "qps_at_recall10_ge_0.95", "value": Q * args.steps / (total_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
