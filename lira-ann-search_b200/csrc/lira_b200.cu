@@ -939,7 +939,7 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
     // the in-kernel seed); exhaustive probe sets (exact kNN over disjoint base segments) pool the seed candidates of the first
     // U8_SEED_LISTS lists, any k <= 128, as long as those lists hold enough candidates
     // (k > 16: twice the seed sample -- the tighter bound saves more in the filter pass than the longer seed pass costs: measured)
-    const int u8_seed_lists = std::min(h->B, getenv("LIRA_U8_SEED_LISTS") ? std::max(1, atoi(getenv("LIRA_U8_SEED_LISTS")))
+    const int u8_seed_lists = std::min(h->B, getenv("LIRA_U8_SEED_LISTS") ? std::max(1, std::min(32, atoi(getenv("LIRA_U8_SEED_LISTS"))))
                                                                           : (k > TC_KMAX_TIGHTEN ? 2 * U8_SEED_LISTS : U8_SEED_LISTS));
     // Measured (profiles/r2_u8_scan_notes.md): with its per-column norm subtraction the byte scan's epilogue costs ~3x the fp16
     // scan's, so for threshold / top-n probe sets it only matches the fp16 scan; it is the default for exhaustive probe sets
