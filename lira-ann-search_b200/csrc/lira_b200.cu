@@ -140,6 +140,24 @@ static int make_tmap_u8(CUtensorMap* m, const void* base, long long rows, int co
     return 0;
 }
 
+// rows x 64 byte matrix (the norm digits of the byte scan); box = 128 rows x 64 bytes, 64-byte swizzle.
+static int make_tmap_u8_aug(CUtensorMap* m, const void* base, long long rows, CUtensorMapDataType dt) {
+    PFN_encodeTiled enc;
+    if (int rc = get_encode_fn(&enc)) return rc;
+    LIRA_REQUIRE(((uintptr_t)base & 63) == 0, "tensor map: digit block must be 64-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)U8_AUG, (cuuint64_t)std::max<long long>(rows, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)U8_AUG};
+    cuuint32_t box[2] = {(cuuint32_t)U8_AUG, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, dt, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (norm digits) failed with CUresult " + std::to_string((int)r));
+        return 2;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // grow-only device buffers
 // ---------------------------------------------------------------------------------------------
@@ -250,12 +268,15 @@ struct lira_index {
     bool has16 = false;          // vecs16 / vaug exist
     bool has8 = false;           // vecs8 / nv_i exist
     bool prefer_u8 = false;      // exact-kNN handles: the byte copy is the one built at create time
+    uint8_t* vaug8 = nullptr;    // [E + 256, 64] norm digits of every entry (the B side of the augmented MMAs)
+    uint8_t* aaug8 = nullptr;    // [128, 64] their constant A side: (-128 x 63, -1) as signed bytes
+    CUtensorMap tmap_vaug8, tmap_aaug8;
     uint8_t* vecs8 = nullptr;    // [E + 256, d8]
     int* nv_i = nullptr;         // [E + 256] -|v|^2 (L2) or 0 (IP)
     int d8 = 0;                  // round_up(d, 16)
     int u8_max_nseg = 1;         // most row segments (of U8_SEG_ROWS rows) any list is cut into
     long long u8_nseg_total = 0; // segments of all lists
-    int u8_item_q() const { return (U8_A_KB / ((d8 + U8_KB - 1) / U8_KB)) * U8_M; }   // queries per work item: 512 (d <= 128) or 256
+    int u8_item_q() const { return U8_ITEM_Q; }   // queries per work item
     CUtensorMap tmap8;
     float tc_sigma = 1.0f;       // power-of-two scale of the fp16 shadow copy
     float tc_vmax = 0.0f;        // largest |v| of the index (mode 2: error margin)
@@ -777,12 +798,10 @@ static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg)
     up.items = ws.items.as<ScanItem>();
     up.n_items = ws.n_items.as<int>();
     up.work_counter = nullptr;
-    up.nk = (h->d8 + U8_KB - 1) / U8_KB;
     up.d8 = h->d8;
     up.seg_rows = sg.seg_rows;
     up.q_mod = sg.q_mod;
     up.nv = h->nv_i;
-    up.mul = 2;
     up.dbg = ws.n_items.as<int>() + 10;
     up.qnorm = ws.qnorm.as<float>();
     up.thr = ws.thr.as<uint32_t>();
@@ -838,8 +857,8 @@ static int tc_seed_main(lira_index* h, Workspace& ws, const TcStage& sg, cudaStr
         U8Params up = u8_params(h, ws, sg);
         up.exp = getenv("LIRA_TC_EXP") ? atoi(getenv("LIRA_TC_EXP")) & ~1 : 0;
         up.work_counter = sg.seed_counter;
-        if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, up);
-        else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, up);
+        if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
+        else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
         LIRA_LAUNCH_CHECK();
         return 0;
     }
@@ -896,8 +915,8 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
         up.cand_count = tp.cand_count;
         up.cap = cap;
         up.exp = tp.exp;
-        if (up.is_ip) u8_scan_kernel<false, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, up);
-        else u8_scan_kernel<false, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, up);
+        if (up.is_ip) u8_scan_kernel<false, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
+        else u8_scan_kernel<false, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
     } else
     if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
     else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
@@ -1049,8 +1068,8 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         up.work_counter = ctl + 2;
         up.seed_out = ws.seed_out.as<int>();
         if (!getenv("LIRA_TC_NO_SEED")) {
-            if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, up);
-            else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, up);
+            if (up.is_ip) u8_scan_kernel<true, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
+            else u8_scan_kernel<true, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(true), st>>>(tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
             LIRA_LAUNCH_CHECK();
             u8_seed_select_kernel<<<(int)((Q + 7) / 8), 256, 0, st>>>(ws.seed_out.as<int>(), (int)Q, S, k, ws.thr.as<uint32_t>());
             LIRA_LAUNCH_CHECK();
@@ -1524,15 +1543,32 @@ static int ensure_u8_shadow(lira_index* h) {
     const size_t rows = (size_t)h->E + U8_NS;   // (a box may reach past the last entry)
     LIRA_CUDA_OK(cudaMalloc(&h->vecs8, rows * h->d8));
     LIRA_CUDA_OK(cudaMalloc(&h->nv_i, rows * 4));
+    LIRA_CUDA_OK(cudaMalloc(&h->vaug8, rows * U8_AUG));
+    LIRA_CUDA_OK(cudaMalloc(&h->aaug8, U8_AUG_BOX));
     LIRA_CUDA_OK(cudaMemsetAsync(h->vecs8 + (size_t)h->E * h->d8, 0, (size_t)U8_NS * h->d8, h->stream));
     LIRA_CUDA_OK(cudaMemsetAsync(h->nv_i + h->E, 0, (size_t)U8_NS * 4, h->stream));
+    LIRA_CUDA_OK(cudaMemsetAsync(h->vaug8 + (size_t)h->E * U8_AUG, 0, (size_t)U8_NS * U8_AUG, h->stream));
+    {
+        std::vector<int8_t> a((size_t)U8_AUG_BOX);
+        for (int r = 0; r < 128; ++r)
+            for (int j = 0; j < U8_AUG; ++j) a[(size_t)r * U8_AUG + j] = j == U8_AUG - 1 ? (int8_t)-1 : (int8_t)-128;
+        LIRA_CUDA_OK(cudaMemcpy(h->aaug8, a.data(), a.size(), cudaMemcpyHostToDevice));
+    }
     if (h->E > 0) {
         shadow_rows_u8_kernel<<<grid_for(h->E * (h->d8 / 4), 256, 148 * 16), 256, 0, h->stream>>>(
             h->vecs, h->ds, h->ds, h->E, h->vnorm, h->metric == LIRA_METRIC_IP, h->vecs8, h->d8, h->nv_i);
         g_launches.fetch_add(1);
+        if (h->metric != LIRA_METRIC_IP) {
+            shadow_digits_u8_kernel<<<grid_for(h->E * 16, 256, 148 * 16), 256, 0, h->stream>>>(h->vnorm, h->E, h->vaug8);
+            g_launches.fetch_add(1);
+        } else {
+            LIRA_CUDA_OK(cudaMemsetAsync(h->vaug8, 0, (size_t)h->E * U8_AUG, h->stream));
+        }
     }
     LIRA_CUDA_OK(cudaStreamSynchronize(h->stream));
     if (int rc = make_tmap_u8(&h->tmap8, h->vecs8, (long long)rows, h->d8, h->d8)) return rc;
+    if (int rc = make_tmap_u8_aug(&h->tmap_vaug8, h->vaug8, (long long)rows, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return rc;
+    if (int rc = make_tmap_u8_aug(&h->tmap_aaug8, h->aaug8, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return rc;
     h->has8 = true;
     return 0;
 }
@@ -1587,7 +1623,7 @@ static int index_finish_create(lira_index* h, const long long* offsets) {
     h->tc_ok = h->tc_mode != 0;
     // byte-valued data: the u8 shadow copy (and no fp16 copy until a batch needs one)
     h->d8 = (h->d + 15) / 16 * 16;
-    if (h->tc_mode == 1 && h->d8 <= U8_MAX_D && !getenv("LIRA_NO_U8")) {
+    if (h->tc_mode == 1 && h->d8 <= U8_MAX_D && max_norm2 <= (float)U8_MAX_NORM && !getenv("LIRA_NO_U8")) {
         int* d_u8 = nullptr;
         LIRA_CUDA_OK(cudaMalloc(&d_u8, 4));
         int one = 1;
@@ -1748,6 +1784,8 @@ int lira_index_free(lira_index_t* h) {
     cudaFree(h->vecs16);
     cudaFree(h->vecs8);
     cudaFree(h->nv_i);
+    cudaFree(h->vaug8);
+    cudaFree(h->aaug8);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     for (PendingBatch& pb : h->pending) { if (pb.h_flags) cudaFreeHost(pb.h_flags); if (pb.ev) cudaEventDestroy(pb.ev); }

@@ -1,25 +1,31 @@
 // K2-U8: the grouped list scan on the integer tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM) for
-// byte-valued data -- every stored value and every query value an integer in [0, 255] (SIFT / BigANN-style) with
-// |x|^2 < 2^22. The list rows stream as ONE byte per component (a quarter of the fp32 bytes the reference scans at
-// search.cpp:468-514, half of the fp16 shadow copy of tc_scan_kernels.cuh), the tensor pipe runs K = 32 per
-// instruction (twice the fp16 rate), and all arithmetic is integer, so distances equal the fp32 direct-difference
-// distances bit for bit.
+// byte-valued data -- every stored value and every query value an integer in [0, 255] (SIFT / BigANN-style), d <= 128,
+// |x|^2 <= 4 112 895. The list rows stream as ONE byte per component (a quarter of the fp32 bytes the reference scans at
+// search.cpp:468-514, half of the fp16 shadow copy of tc_scan_kernels.cuh) plus 64 bytes of norm digits, the tensor pipe
+// runs K = 32 per instruction (twice the fp16 rate), and all arithmetic is integer, so distances equal the fp32
+// direct-difference distances bit for bit.
 //
-//   work item  (list b, a segment of at most `seg_rows` of its rows, up to 512 queries of b's group) = up to FOUR query
+//   work item  (list b, a segment of at most `seg_rows` of its rows, up to 384 queries of b's group) = up to THREE query
 //              tiles of 128 rows (16 KiB each) that share every staged chunk of the list: the L2 -> shared-memory operand
-//              stream -- what bounds the scan once the rows are bytes -- is paid once per 512 queries instead of once per
-//              128. Long lists are cut into row segments so that no item exceeds a small part of an SM's share.
-//   unit       one (query tile, chunk of 256 list rows): 4 MMAs of M = 128, N = 256, K = 32 per 128 bytes of d into one
-//              of the two 256-column accumulators; the epilogue of a unit overlaps the MMAs of the next.
-//   epilogue   16 warps; a thread owns one query row and 64 of the 256 columns: u = 2 acc - |v|^2 (|v|^2 of the chunk's
-//              rows is staged next to them), a 3-input-max tree, and ONE compare + vote per 32 columns.
+//              stream is paid once per 384 queries instead of once per 128. Long lists are cut into row segments so that no
+//              item exceeds a small part of an SM's share.
+//   unit       one (query tile, chunk of 256 list rows) into one of the two 256-column accumulators: TWO augmented MMAs that
+//              put -floor(|v|^2 / 2) into the accumulator -- A side: the constant signed row (-128 x 63, -1), B side: 64
+//              unsigned digits of the row with  sum 128 d_j + l = floor(|v|^2 / 2)  (8-bit digits carry at most 128 x 255 per
+//              K step, hence two K = 32 blocks) -- then 4 MMAs of M = 128, N = 256, K = 32 per 128 bytes of d. The
+//              accumulator holds  a = q.v - floor(|v|^2 / 2),  so  2 a  is the score-side value u = 2 q.v - |v|^2  up to the
+//              parity of |v|^2, and the epilogue needs NO per-column arithmetic before its max tree (a per-column
+//              subtraction made the epilogue, not the tensor pipe, the limit of the first version: 17 % tensor pipe active).
+//   epilogue   16 warps; a thread owns one query row and 64 of the 256 columns: 3-input-max tree over the raw accumulator,
+//              ONE compare + vote per 32 columns (conservative by the parity bit); entries that pass are scored exactly
+//              (2 a - (|v|^2 & 1), the parity read from global memory) in the out-of-line append.
 //   seed pass  (SEED = true) every thread keeps the 4 largest of its 16-column sub-group maxima over the item's rows
 //              (4-column blocks in the first chunk of a short list): 16 distinct entries per (query, list segment) row,
-//              whose k-th largest bounds the query's final k-th best score (k <= 16); the tightest bound over a query's
-//              lists is T[q] (atomicMin). Exhaustive probe sets pool the values of several lists instead (any k).
-//   filter     (SEED = false) entries with score <= T[q] are appended to the candidate region of their (query, list)
-//              pair (`cap` keys, slot taken with an atomic: survivors are a few per query); refine_topk_kernel turns the
-//              regions into the top k over distinct ids. A region that overflows flags the query for the exact path.
+//              whose k-th largest (as 2 a - 1 <= u) bounds the query's final k-th best score (k <= 16); the tightest bound
+//              over a query's lists is T[q] (atomicMin). Exhaustive probe sets pool the values of several lists instead.
+//   filter     (SEED = false) entries with score <= T[q] are appended to a candidate region (exhaustive probe sets: one
+//              private region per (pair, column part); otherwise one per pair with atomic slots); refine_topk_kernel turns
+//              the regions into the top k over distinct ids. A region that overflows flags the query for the exact path.
 #pragma once
 #include "tc_scan_kernels.cuh"
 
@@ -27,33 +33,37 @@ namespace lira {
 
 static constexpr int U8_M = 128;                    // queries per tile (UMMA M)
 static constexpr int U8_NS = 256;                   // list rows per chunk (UMMA N, accumulator columns)
-static constexpr int U8_KB = 128;                   // bytes (= components) per K block: one 128-byte swizzle row
-static constexpr int U8_KBLK_BYTES = 128 * U8_KB;   // 16 KiB: 128 rows of one K block
-static constexpr int U8_SLOT_BYTES = 2 * U8_KBLK_BYTES;   // 32 KiB: one K block of a chunk (256 rows)
-static constexpr int U8_A_KB = 4;                   // A ring in 16 KiB blocks: 4 query tiles of d <= 128, or 2 of d <= 256
-static constexpr int U8_NT = U8_A_KB;               // tiles per work item at most
-static constexpr int U8_ITEM_Q = U8_NT * U8_M;      // queries per work item at most (d <= 128; half of it for d <= 256)
-static constexpr int U8_NSLOT_MAX = 4;              // B ring: 4 slots in the filter pass, 3 in the seed pass (which needs the exchange area)
-static constexpr int U8_NNORM = 4;                  // ring of the chunks' |v|^2 (256 int32 each)
-static constexpr int U8_NQ = 3;                     // work-item queue depth (the scheduler warp runs this far ahead)
+static constexpr int U8_KB = 128;                   // bytes (= components) per row of the data operand: one 128-byte swizzle row
+static constexpr int U8_KBLK_BYTES = 128 * U8_KB;   // 16 KiB: a box of 128 rows
+static constexpr int U8_AUG = 64;                   // norm digits per row (two K = 32 blocks, 64-byte swizzle rows)
+static constexpr int U8_AUG_BOX = 128 * U8_AUG;     // 8 KiB: the digits of a box of 128 rows
+static constexpr int U8_SLOT_BYTES = 2 * U8_KBLK_BYTES + 2 * U8_AUG_BOX;   // 48 KiB: a chunk (256 rows) and its digits
+static constexpr int U8_NT = 3;                     // query tiles per work item at most = buffers of the A ring
+static constexpr int U8_ITEM_Q = U8_NT * U8_M;      // queries per work item at most
+static constexpr int U8_NSLOT_MAX = 3;              // B ring: 3 slots in the filter pass, 2 in the seed pass (which needs the exchange area)
+static constexpr int U8_NQ = 2;                     // work-item queue depth (the scheduler warp runs this far ahead)
 static constexpr int U8_PARTS = 4;                  // column parts = epilogue warps per TMEM lane quadrant
 static constexpr int U8_EPI_WARPS = 4 * U8_PARTS;
 static constexpr int U8_THREADS = (U8_EPI_WARPS + 3) * 32;
-static constexpr int U8_MAX_D = 2 * U8_KB;          // d <= 256
-static constexpr int U8_SEG_ROWS = 4096;            // rows of a list per work item (16 chunks x up to 4 tiles = 64 units at most)
-__host__ __device__ constexpr int u8_nslot(bool seed) { return seed ? 3 : 4; }
+static constexpr int U8_MAX_D = U8_KB;              // d <= 128
+static constexpr int U8_MAX_NORM = 128 * (63 * 255) * 2 + 255;   // |v|^2 <= 4 112 895: floor(|v|^2 / 2) = 128 H + l, H <= 63 x 255, l <= 127
+static constexpr int U8_MASKED = -(3 << 28);         // accumulator value given to columns past the end of a segment: below every real value
+                                                    //   (>= -2^21) and every bound, and 2 x it still fits an int32
+static constexpr int U8_SEG_ROWS = 4096;            // rows of a list per work item (16 chunks x up to 3 tiles = 48 units at most)
+__host__ __device__ constexpr int u8_nslot(bool seed) { return seed ? 2 : 3; }
 __host__ __device__ constexpr size_t u8_smem_bytes(bool seed) {
-    return (size_t)U8_A_KB * U8_KBLK_BYTES + (size_t)u8_nslot(seed) * U8_SLOT_BYTES   // operands
-           + (size_t)U8_NNORM * U8_NS * 4                                             // norms ring
+    return (size_t)U8_NT * U8_KBLK_BYTES + (size_t)u8_nslot(seed) * U8_SLOT_BYTES     // operands
+           + (size_t)U8_AUG_BOX                                                       // the constant A side of the augmented MMAs
            + 512                                                                      // barriers, item queue, tmem slot
            + (size_t)U8_NQ * U8_ITEM_Q * 12                                           // per queued item and row: query id, |q|^2, bound
            + (seed ? (size_t)U8_PARTS * U8_ITEM_Q * 16                                // seed pass: 4 values per (row, part)
                    : (size_t)U8_PARTS * U8_ITEM_Q * 4);                               // filter pass: private region fill per (row, part)
 }
 
-// D = S32, A = B = unsigned 8 bit, both K-major, M = 128, N = 256 / 128
+// D = S32, A = B = unsigned 8 bit (the augmented MMAs: A signed), both K-major, M = 128, N = 256 / 128
 static constexpr uint32_t U8_IDESC_N256 = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(U8_M >> 4) << 24);
 static constexpr uint32_t U8_IDESC_N128 = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(U8_M >> 4) << 24);
+static constexpr uint32_t U8_IDESC_AUG = 1u << 7;   // a_format = signed 8 bit
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -62,20 +72,22 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// K-major, 64-byte swizzle: rows of 64 B (two K = 32 steps), 8-row groups 512 B apart (SBO)
+__device__ __forceinline__ uint64_t tc_smem_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 
 struct U8Params {
     const int* group_queries;        // [P] query id per slot
     const long long* list_offsets;   // [B+1]
-    const ScanItem* items;           // items of up to 512 queries; ScanItem::tm = row segment of the list
+    const ScanItem* items;           // items of up to 384 queries; ScanItem::tm = row segment of the list
     const int* n_items;
     int* work_counter;               // zeroed before launch: dynamic item scheduler
-    int nk;                          // K blocks of 128 bytes (1 or 2)
-    int d8;                          // padded row length in bytes (multiple of 16)
+    int d8;                          // padded row length in bytes (multiple of 16, <= 128)
     int seg_rows;                    // rows per segment (multiple of 256)
     int q_mod;                       // > 0: exhaustive probe sets -- every list's group is the whole batch in query order, so the A tiles
                                      //   are read from ONE [Q, d8] copy of the queries (row = slot % Q) instead of one copy per list
-    const int* nv;                   // [E + 256] -|v|^2 per list entry (L2) or 0 (IP)
-    int mul;                         // 2: u = mul acc + nv (kept a run-time value on purpose, see the epilogue)
+    const int* nv;                   // [E + 256] -|v|^2 per list entry (L2) or 0 (IP): the append reads its parity
     const float* qnorm;              // [Q] |q|^2 (exact integers)
     uint32_t* thr;                   // [Q] bound T[q] on the k-th best score as f32_to_ordered(T): written by the seed pass, read by the filter
     unsigned long long* cand_key;    // [P, cap] (score, list entry) keys: one region per (query, list) pair
@@ -87,7 +99,7 @@ struct U8Params {
     int cap;
     int k;
     int is_ip;
-    int* dbg;                        // LIRA_TC_EXP bit 6: {groups with a survivor, groups} counters
+    int* dbg;                        // LIRA_TC_EXP bit 6: {groups with a survivor, groups, items, tiles, chunks, units} counters
     int exp;                         // experiments (LIRA_TC_EXP, wrong results, timing only): bit 0 = skip the survivor path,
                                      //   bit 1 = skip the whole epilogue arithmetic, bit 2 = skip the MMAs
 };
@@ -100,80 +112,83 @@ __device__ __forceinline__ void u8_top4_insert(int (&a)[4], int x) {
     a[0] = n0; a[1] = n1; a[2] = n2; a[3] = max(a[3], x3);
 }
 
-// filter pass: the entries of one block of 4 columns that pass (u >= lim) are appended to the pair's candidate region as
-// (score = |q|^2 - u, list entry) keys; returns true when the region overflowed (the query is then redone exactly).
-// Out of line on purpose: see the note on code size in the epilogue.
-__device__ __noinline__ bool u8_append4(int x0, int x1, int x2, int x3, int lim, int qn, uint32_t e0, unsigned long long* cand, int* cnt_ptr, int cap) {
-    const int n = (x0 >= lim) + (x1 >= lim) + (x2 >= lim) + (x3 >= lim);
+// filter pass, one block of 4 columns whose accumulator values a0..a3 may pass: u = 2 a - parity(|v|^2) exactly (nvp points at
+// the block's -|v|^2, null for the inner product where u = a), and the entries with u >= lim are appended as
+// (score = |q|^2 - u, list entry) keys. Out of line on purpose: see the note on code size in the epilogue.
+// Shared region of the pair, slot taken with an atomic: returns true when the region overflowed (the query is redone exactly).
+__device__ __noinline__ bool u8_append4(int a0, int a1, int a2, int a3, const int* nvp, int lim, int qn, uint32_t e0, unsigned long long* cand,
+                                       int* cnt_ptr, int cap) {
+    const int u0 = nvp ? 2 * a0 - (nvp[0] & 1) : a0, u1 = nvp ? 2 * a1 - (nvp[1] & 1) : a1;
+    const int u2 = nvp ? 2 * a2 - (nvp[2] & 1) : a2, u3 = nvp ? 2 * a3 - (nvp[3] & 1) : a3;
+    const int n = (u0 >= lim) + (u1 >= lim) + (u2 >= lim) + (u3 >= lim);
     if (n == 0) return false;
     int pos = atomicAdd(cnt_ptr, n);
-    if (x0 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x0), e0); ++pos; }
-    if (x1 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x1), e0 + 1); ++pos; }
-    if (x2 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x2), e0 + 2); ++pos; }
-    if (x3 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - x3), e0 + 3); ++pos; }
+    if (u0 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - u0), e0); ++pos; }
+    if (u1 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - u1), e0 + 1); ++pos; }
+    if (u2 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - u2), e0 + 2); ++pos; }
+    if (u3 >= lim) { if (pos < cap) cand[pos] = make_key((float)(qn - u3), e0 + 3); ++pos; }
     return pos > cap;
 }
-
 // the same for a region owned by the calling thread: returns the new fill (it may run past cap)
-__device__ __noinline__ int u8_append4_private(int x0, int x1, int x2, int x3, int lim, int qn, uint32_t e0, unsigned long long* cand, int cnt, int cap) {
-    if (x0 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x0), e0); ++cnt; }
-    if (x1 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x1), e0 + 1); ++cnt; }
-    if (x2 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x2), e0 + 2); ++cnt; }
-    if (x3 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - x3), e0 + 3); ++cnt; }
+__device__ __noinline__ int u8_append4_private(int a0, int a1, int a2, int a3, const int* nvp, int lim, int qn, uint32_t e0,
+                                              unsigned long long* cand, int cnt, int cap) {
+    const int u0 = nvp ? 2 * a0 - (nvp[0] & 1) : a0, u1 = nvp ? 2 * a1 - (nvp[1] & 1) : a1;
+    const int u2 = nvp ? 2 * a2 - (nvp[2] & 1) : a2, u3 = nvp ? 2 * a3 - (nvp[3] & 1) : a3;
+    if (u0 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - u0), e0); ++cnt; }
+    if (u1 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - u1), e0 + 1); ++cnt; }
+    if (u2 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - u2), e0 + 2); ++cnt; }
+    if (u3 >= lim) { if (cnt < cap) cand[cnt] = make_key((float)(qn - u3), e0 + 3); ++cnt; }
     return cnt;
 }
 
 template <bool SEED, bool IP>
 __global__ void __launch_bounds__(U8_THREADS, 1)   // (96 registers per thread: 19 warps x 104 no longer fit the register file)
 u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
-               const U8Params p) {
+               const __grid_constant__ CUtensorMap tmap_vaug, const __grid_constant__ CUtensorMap tmap_aaug, const U8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     constexpr int NSLOT = u8_nslot(SEED);
-    uint8_t* sA = smem_raw;                                             // [A ring: U8_A_KB blocks of 128 x 128 B]
-    uint8_t* sB = sA + (size_t)U8_A_KB * U8_KBLK_BYTES;                 // [NSLOT][256 x 128 B]
-    int* s_nv = (int*)(sB + (size_t)NSLOT * U8_SLOT_BYTES);             // [U8_NNORM][256]
-    uint64_t* bars = (uint64_t*)(s_nv + U8_NNORM * U8_NS);
-    uint64_t* a_full = bars;                        // [U8_A_KB] per tile buffer
-    uint64_t* a_empty = a_full + U8_A_KB;           // [U8_A_KB]
-    uint64_t* b_full = a_empty + U8_A_KB;           // [U8_NSLOT_MAX]
+    uint8_t* sA = smem_raw;                                             // [A ring: U8_NT tiles of 128 x 128 B]
+    uint8_t* sB = sA + (size_t)U8_NT * U8_KBLK_BYTES;                   // [NSLOT]{[256 x 128 B] rows, [256 x 64 B] norm digits}
+    uint8_t* sGA = sB + (size_t)NSLOT * U8_SLOT_BYTES;                  // [128 x 64 B] constant A side of the augmented MMAs
+    uint64_t* bars = (uint64_t*)(sGA + U8_AUG_BOX);
+    uint64_t* a_full = bars;                        // [U8_NT] per tile buffer
+    uint64_t* a_empty = a_full + U8_NT;             // [U8_NT]
+    uint64_t* b_full = a_empty + U8_NT;             // [U8_NSLOT_MAX]
     uint64_t* b_empty = b_full + U8_NSLOT_MAX;      // [U8_NSLOT_MAX]
-    uint64_t* n_full = b_empty + U8_NSLOT_MAX;      // [U8_NNORM]
-    uint64_t* n_empty = n_full + U8_NNORM;          // [U8_NNORM]
-    uint64_t* t_full = n_empty + U8_NNORM;          // [2]
+    uint64_t* t_full = b_empty + U8_NSLOT_MAX;      // [2]
     uint64_t* t_empty = t_full + 2;                 // [2]
     uint64_t* i_full = t_empty + 2;                 // [U8_NQ]
     uint64_t* i_empty = i_full + U8_NQ;             // [U8_NQ]
-    TcQItem* iq = (TcQItem*)(i_empty + U8_NQ);      // [U8_NQ]   (32 barriers = 256 B, 2 items = 64 B)
+    uint64_t* ga_full = i_empty + U8_NQ;            // [1]
+    TcQItem* iq = (TcQItem*)(ga_full + 1);          // [U8_NQ]   (21 barriers = 168 B, 2 items = 64 B)
     uint32_t* tmem_slot = (uint32_t*)(iq + U8_NQ);
-    int* s_q = (int*)((uint8_t*)bars + 512);                    // [U8_NQ][512] query id (-1: padding row)
-    int* s_qn = s_q + U8_NQ * U8_ITEM_Q;                        // [U8_NQ][512] |q|^2 (0 for IP)
-    int* s_lim = s_qn + U8_NQ * U8_ITEM_Q;                      // [U8_NQ][512] an entry survives iff u >= lim
-    int4* s_x = reinterpret_cast<int4*>(s_lim + U8_NQ * U8_ITEM_Q);   // [U8_PARTS][512]: seed pass, the 4 largest u per (row, part)
-    int* s_cnt = s_lim + U8_NQ * U8_ITEM_Q;                           // [U8_PARTS][512]: filter pass, fill of the private regions (same area)
+    int* s_q = (int*)((uint8_t*)bars + 512);                    // [U8_NQ][384] query id (-1: padding row)
+    int* s_qn = s_q + U8_NQ * U8_ITEM_Q;                        // [U8_NQ][384] |q|^2 (0 for IP)
+    int* s_lim = s_qn + U8_NQ * U8_ITEM_Q;                      // [U8_NQ][384] an entry survives iff u >= lim
+    int4* s_x = reinterpret_cast<int4*>(s_lim + U8_NQ * U8_ITEM_Q);   // [U8_PARTS][384]: seed pass, the 4 largest values per (row, part)
+    int* s_cnt = s_lim + U8_NQ * U8_ITEM_Q;                           // [U8_PARTS][384]: filter pass, fill of the private regions (same area)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_PROD = U8_EPI_WARPS, W_MMA = W_PROD + 1, W_ALLOC = W_PROD + 2;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < U8_A_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < U8_NT; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < U8_NSLOT_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < U8_NNORM; ++i) { mbar_init(&n_full[i], 32); mbar_init(&n_empty[i], U8_EPI_WARPS); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], U8_EPI_WARPS); }
         for (int i = 0; i < U8_NQ; ++i) { mbar_init(&i_full[i], 1); mbar_init(&i_empty[i], 2 + U8_EPI_WARPS); }   // producer + MMA + epilogue warps
+        mbar_init(ga_full, 1);
         mbar_fence_init();
     }
     if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x == W_PROD * 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); }
+    if (threadIdx.x == W_PROD * 32) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_vaug); tma_prefetch_desc(&tmap_aaug); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_items = *p.n_items;
-    const int nk = p.nk;
-    const int abuf = U8_A_KB / nk;                  // tile buffers of the A ring (a tile = nk blocks): 4 (d <= 128) or 2
 
     if (warp == W_ALLOC) {
         // ===== scheduler (the TMEM allocator warp has nothing else to do): claims work items and stages what the other warps
@@ -192,7 +207,6 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             return d;
         };
         constexpr int RPL = U8_ITEM_Q / 32;   // rows per lane (row = lane + 32 j)
-        // pipeline registers: tk3 (ticket n+3 in flight) ; d2 (descriptor n+2) ; {o1, rq1} (rows of n+1) ; item n is staged
         int tk = ticket();
         ScanItem d2 = descriptor(tk);          // item 0
         tk = ticket();
@@ -259,8 +273,14 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
     } else if (warp == W_PROD) {
         // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+        if (!IP) {   // the constant A side of the augmented MMAs: every row is (-128 x 63, -1)
+            if (elect_one()) {
+                mbar_arrive_expect_tx(ga_full, U8_AUG_BOX);
+                tma_load_2d(sGA, &tmap_aaug, 0, 0, ga_full);
+            }
+            __syncwarp();
+        }
         PipeState bs{0, 0};
-        uint32_t cn = 0;   // running chunk counter -> norms ring slot
         uint32_t ga = 0;   // running tile counter -> A ring buffer and phase
         for (int n = 0;; ++n) {
             const int qs = n % U8_NQ;
@@ -271,40 +291,28 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (it.list < 0) break;
             const int ntile = (it.q_count + U8_M - 1) / U8_M;
             for (int t = 0; t < ntile; ++t, ++ga) {   // the item's query tiles into the next buffers of the A ring
-                const uint32_t x = ga % (uint32_t)abuf;
-                mbar_wait(&a_empty[x], ((ga / (uint32_t)abuf) & 1) ^ 1u);
+                const uint32_t x = ga % (uint32_t)U8_NT;
+                mbar_wait(&a_empty[x], ((ga / (uint32_t)U8_NT) & 1) ^ 1u);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&a_full[x], (uint32_t)nk * U8_KBLK_BYTES);
-                    for (int kb = 0; kb < nk; ++kb)
-                        tma_load_2d(sA + (size_t)(x * nk + kb) * U8_KBLK_BYTES, &tmap_q, kb * U8_KB,
-                                    (p.q_mod > 0 ? it.q_begin % p.q_mod : it.q_begin) + t * U8_M, &a_full[x]);
+                    mbar_arrive_expect_tx(&a_full[x], U8_KBLK_BYTES);
+                    tma_load_2d(sA + (size_t)x * U8_KBLK_BYTES, &tmap_q, 0, (p.q_mod > 0 ? it.q_begin % p.q_mod : it.q_begin) + t * U8_M, &a_full[x]);
                 }
                 __syncwarp();
             }
             const long long lo = it.lo, hi = it.hi;
-            for (long long row0 = lo; row0 < hi; row0 += U8_NS, ++cn) {
+            for (long long row0 = lo; row0 < hi; row0 += U8_NS) {
                 const int nh = hi - row0 > 128 ? 2 : 1;   // boxes of 128 rows (the tail of a list may need one only)
-                const int ns = cn % U8_NNORM;
-                mbar_wait(&n_empty[ns], ((cn / U8_NNORM) & 1) ^ 1u);
-                {   // |v|^2 of the chunk's rows: 4-byte cp.async (a list starts at any entry, TMA needs 16-byte aligned starts);
-                    // every lane's arrival lands when its copies have (n_full counts 32)
-                    const int* src = p.nv + row0 + lane;
-                    const uint32_t dst = smem_u32(s_nv + ns * U8_NS + lane);
-#pragma unroll
-                    for (int j = 0; j < U8_NS / 32; ++j) cp_async_4(dst + j * 128, src + j * 32);
-                    cp_async_mbar_arrive_noinc(&n_full[ns]);
-                }
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
-                    if (elect_one()) {
-                        uint8_t* slot = sB + (size_t)bs.stage * U8_SLOT_BYTES;
-                        mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nh * U8_KBLK_BYTES);
-                        for (int x = 0; x < nh; ++x)
-                            tma_load_2d(slot + (size_t)x * U8_KBLK_BYTES, &tmap_v, kb * U8_KB, (int)row0 + x * 128, &b_full[bs.stage]);
+                mbar_wait(&b_empty[bs.stage], bs.phase ^ 1u);
+                if (elect_one()) {
+                    uint8_t* slot = sB + (size_t)bs.stage * U8_SLOT_BYTES;
+                    mbar_arrive_expect_tx(&b_full[bs.stage], (uint32_t)nh * (U8_KBLK_BYTES + (IP ? 0 : U8_AUG_BOX)));
+                    for (int x = 0; x < nh; ++x) {
+                        tma_load_2d(slot + (size_t)x * U8_KBLK_BYTES, &tmap_v, 0, (int)row0 + x * 128, &b_full[bs.stage]);
+                        if (!IP) tma_load_2d(slot + 2 * U8_KBLK_BYTES + (size_t)x * U8_AUG_BOX, &tmap_vaug, 0, (int)row0 + x * 128, &b_full[bs.stage]);
                     }
-                    __syncwarp();
-                    bs.advance(NSLOT);
                 }
+                __syncwarp();
+                bs.advance(NSLOT);
             }
         }
     } else if (warp == W_MMA) {
@@ -312,7 +320,9 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         PipeState bs{0, 0};
         uint32_t m = 0;   // running unit counter -> accumulator and phase
         uint32_t gm = 0;  // running tile counter -> A ring buffer and phase
-        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+        if (!IP) { mbar_wait(ga_full, 0); tc_fence_after(); }
+        const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB), sGA_u32 = smem_u32(sGA);
+        const int ksteps = min(4, (p.d8 + 31) / 32);
         for (int n = 0;; ++n) {
             const int qs = n % U8_NQ;
             mbar_wait(&i_full[qs], (n / U8_NQ) & 1);
@@ -327,43 +337,39 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             for (int t = 0; t < ntile; ++t) {
                 const uint32_t g = gm + t;
-                mbar_wait(&a_full[g % (uint32_t)abuf], (g / (uint32_t)abuf) & 1);
+                mbar_wait(&a_full[g % (uint32_t)U8_NT], (g / (uint32_t)U8_NT) & 1);
             }
             tc_fence_after();
             const long long lo = it.lo, hi = it.hi;
             for (long long row0 = lo; row0 < hi; row0 += U8_NS) {
-                const uint32_t idesc = hi - row0 > 128 ? U8_IDESC_N256 : U8_IDESC_N128;
-                const PipeState b0 = bs;
+                const uint32_t nsel = hi - row0 > 128 ? (uint32_t)(256 >> 3) << 17 : (uint32_t)(128 >> 3) << 17;   // N = 256 (tail of a list: 128)
+                const uint32_t idesc = (2u << 4) | nsel | ((uint32_t)(U8_M >> 4) << 24);
+                const uint32_t b_addr = sB_u32 + (uint32_t)bs.stage * U8_SLOT_BYTES;
                 for (int t = 0; t < ntile; ++t, ++m) {
                     const uint32_t acc = m & 1u;
                     mbar_wait(&t_empty[acc], ((m >> 1) & 1) ^ 1u);
                     tc_fence_after();
+                    if (t == 0) { mbar_wait(&b_full[bs.stage], bs.phase); tc_fence_after(); }
                     const uint32_t d_tmem = tmem_base + acc * U8_NS;
-                    const uint32_t x = (gm + t) % (uint32_t)abuf;
-                    PipeState s = b0;
-                    for (int kb = 0; kb < nk; ++kb) {
-                        if (t == 0) { mbar_wait(&b_full[s.stage], s.phase); tc_fence_after(); }
-                        const uint32_t a_addr = sA_u32 + (uint32_t)(x * nk + kb) * U8_KBLK_BYTES;
-                        const uint32_t b_addr = sB_u32 + (uint32_t)s.stage * U8_SLOT_BYTES;
-                        const int ksteps = min(4, (p.d8 - kb * U8_KB + 31) / 32);
-                        if (elect_one() && !(p.exp & 4)) {
-                            for (int j = 0; j < ksteps; ++j)   // K = 32 bytes inside the 128-byte swizzle row
-                                tc_mma_i8(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), idesc, (kb || j) ? 1u : 0u);
+                    const uint32_t a_addr = sA_u32 + (uint32_t)((gm + t) % (uint32_t)U8_NT) * U8_KBLK_BYTES;
+                    if (elect_one() && !(p.exp & 4)) {
+                        if (!IP) {   // a = -floor(|v|^2 / 2) ...
+                            tc_mma_i8(d_tmem, tc_smem_desc_sw64(sGA_u32), tc_smem_desc_sw64(b_addr + 2 * U8_KBLK_BYTES), idesc | U8_IDESC_AUG, 0u);
+                            tc_mma_i8(d_tmem, tc_smem_desc_sw64(sGA_u32 + 32), tc_smem_desc_sw64(b_addr + 2 * U8_KBLK_BYTES + 32), idesc | U8_IDESC_AUG, 1u);
                         }
-                        __syncwarp();
-                        s.advance(NSLOT);
+                        for (int j = 0; j < ksteps; ++j)   // ... + q.v, K = 32 bytes inside the 128-byte swizzle row
+                            tc_mma_i8(d_tmem, tc_smem_desc(a_addr + j * 32), tc_smem_desc(b_addr + j * 32), idesc, (!IP || j) ? 1u : 0u);
                     }
+                    __syncwarp();
                     if (elect_one()) tc_commit(&t_full[acc]);
                     __syncwarp();
                 }
-                for (int kb = 0; kb < nk; ++kb) {   // the chunk's slots are free once every MMA above has read them
-                    if (elect_one()) tc_commit(&b_empty[bs.stage]);
-                    __syncwarp();
-                    bs.advance(NSLOT);
-                }
+                if (elect_one()) tc_commit(&b_empty[bs.stage]);   // the chunk's slot is free once every MMA above has read it
+                __syncwarp();
+                bs.advance(NSLOT);
             }
             for (int t = 0; t < ntile; ++t, ++gm) {   // ... and so are the item's query tiles
-                if (elect_one()) tc_commit(&a_empty[gm % (uint32_t)abuf]);
+                if (elect_one()) tc_commit(&a_empty[gm % (uint32_t)U8_NT]);
                 __syncwarp();
             }
         }
@@ -376,7 +382,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int part = warp >> 2;                // which 32 columns of each 128-column half
         const int cap = p.cap;
         const uint32_t t_full_u32 = smem_u32(t_full), t_empty_u32 = smem_u32(t_empty);
-        uint32_t m = 0, cn = 0;
+        uint32_t m = 0;
         for (int n = 0;; ++n) {
             const int qs = n % U8_NQ;
             mbar_wait(&i_full[qs], (n / U8_NQ) & 1);
@@ -396,11 +402,8 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             uint32_t ebase = (uint32_t)it.lo + part * 32;
             int left = n_rows - part * 32;
-            for (int rows_left = n_rows; rows_left > 0; rows_left -= U8_NS, ebase += U8_NS, left -= U8_NS, ++cn) {
+            for (int rows_left = n_rows; rows_left > 0; rows_left -= U8_NS, ebase += U8_NS, left -= U8_NS) {
                 const int nh = rows_left > 128 ? 2 : 1;
-                const int ns = cn % U8_NNORM;
-                mbar_wait(&n_full[ns], (cn / U8_NNORM) & 1);
-                const int* nvc = s_nv + ns * U8_NS + part * 32;
                 const bool fine = SEED && rows_left == n_rows && n_rows <= 1024;   // first chunk of a short list: 4-column blocks
 #pragma unroll 1
                 for (int t = 0; t < ntile; ++t, ++m) {
@@ -415,37 +418,33 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     }
                     tc_fence_after();
                     const int row = t * U8_M + trow;
+                    // the accumulator value a relates to u by  u = 2 a - parity  (L2) or u = a (IP): a passes (conservatively) iff
+                    // 2 a >= lim  <=>  a >= ceil(lim / 2)
                     const int lim = SEED ? 0 : iq_lim[row];
+                    const int lima = IP ? lim : (lim >> 1) + (lim & 1);   // ceil(lim / 2) for either sign (arithmetic shift = floor)
                     int a[4];
                     if (SEED) { const int4 v = s_x[part * U8_ITEM_Q + row]; a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * U8_NS + part * 32;
-                    auto process = [&](uint32_t (&ru)[32], const int h) {
-                        int r[32];
-                        if (IP) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) r[i] = (int)ru[i];
-                        } else {
-                            // u = 2 acc - |v|^2 as ONE integer multiply-add per column: the factor comes from the parameter block (so that
-                            // it stays an IMAD, which issues on the FMA pipe) and the staged norms are stored negated; as IADD3 the
-                            // subtraction shares the half-rate ALU pipe with the max tree, which is what bounds this epilogue (ncu: ALU
-                            // pipe 70 % active, tensor pipe 29 %)
-                            const int mul = p.mul;
-                            const int4* nv4 = reinterpret_cast<const int4*>(nvc + h * 128);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int4 nv = nv4[i];
-                                r[4 * i + 0] = (int)ru[4 * i + 0] * mul + nv.x;
-                                r[4 * i + 1] = (int)ru[4 * i + 1] * mul + nv.y;
-                                r[4 * i + 2] = (int)ru[4 * i + 2] * mul + nv.z;
-                                r[4 * i + 3] = (int)ru[4 * i + 3] * mul + nv.w;
-                            }
+#pragma unroll 1
+                    for (int h = 0; h < nh; ++h) {   // the two 128-column halves of the accumulator, one after the other
+                        uint32_t ru[32];
+                        tc_ld32_async(taddr + h * 128, ru);
+                        tc_ld_wait(ru);
+                        if (h == nh - 1) {   // the thread's last columns of this unit are in registers: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
                         }
+                        if (p.exp & 2) continue;
+                        int r[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = (int)ru[i];
                         // columns past the end of the segment hold other rows
                         const int n_valid = left - h * 128;
                         if (n_valid < 32) {
 #pragma unroll
                             for (int c = 0; c < 32; ++c)
-                                if (c >= n_valid) r[c] = INT_MIN;
+                                if (c >= n_valid) r[c] = U8_MASKED;
                         }
                         int m4[8];
 #pragma unroll
@@ -460,17 +459,18 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         } else {
                             const int mx = max(m16a, m16b);
                             if ((p.exp & 64) && lane == 0) atomicAdd(p.dbg + 1, 1);
-                            if (__any_sync(0xffffffffu, mx >= lim) && !(p.exp & 1)) {
+                            if (__any_sync(0xffffffffu, mx >= lima) && !(p.exp & 1)) {
                                 if ((p.exp & 64) && lane == 0) atomicAdd(p.dbg, 1);
                                 const size_t slot = (size_t)(it.q_begin + row);
                                 const uint32_t eb = ebase + h * 128;
+                                const int* nvb = IP ? nullptr : p.nv + eb;
                                 const int qn = iq_qn[row];
                                 bool over = false;
                                 // which blocks of 4 columns hold a passing entry in SOME lane: one warp reduction, then warp-uniform
                                 // branches (a vote per block would put eight dependent round trips on the warp's critical path)
                                 uint32_t qm = 0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) qm |= (m4[j] >= lim) ? (1u << j) : 0u;
+                                for (int j = 0; j < 8; ++j) qm |= (m4[j] >= lima) ? (1u << j) : 0u;
                                 const uint32_t um = __reduce_or_sync(0xffffffffu, qm);
                                 if (p.private_regions) {
                                     unsigned long long* cand = p.cand_key + (slot * U8_PARTS + part) * cap;
@@ -478,7 +478,8 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         if (um & (1u << j))
-                                            cnt = u8_append4_private(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt, cap);
+                                            cnt = u8_append4_private(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], IP ? nullptr : nvb + 4 * j, lim, qn,
+                                                                     eb + 4 * j, cand, cnt, cap);
                                     }
                                     s_cnt[part * U8_ITEM_Q + row] = cnt;
                                     over = cnt > cap;
@@ -488,46 +489,34 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         if (um & (1u << j))
-                                            over |= u8_append4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], lim, qn, eb + 4 * j, cand, cnt_ptr, cap);
+                                            over |= u8_append4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], IP ? nullptr : nvb + 4 * j, lim, qn,
+                                                               eb + 4 * j, cand, cnt_ptr, cap);
                                     }
                                 }
                                 if (over) iq_lim[row] = 0x7FFFFFFF;   // the region overflowed (the query is redone exactly): stop collecting
                             }
                         }
-                    };
-#pragma unroll 1
-                    for (int h = 0; h < nh; ++h) {   // the two 128-column halves of the accumulator, one after the other
-                        uint32_t ra[32];
-                        tc_ld32_async(taddr + h * 128, ra);
-                        tc_ld_wait(ra);
-                        if (h == nh - 1) {   // the thread's last columns of this unit are in registers: hand the accumulator back
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
-                        }
-                        if (!(p.exp & 2)) process(ra, h);
                     }
                     if (SEED) s_x[part * U8_ITEM_Q + row] = make_int4(a[0], a[1], a[2], a[3]);
                 }
-                // this warp is done with the chunk's norms
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&n_empty[ns]);
             }
             if (SEED) {
-                // a row's four column parts kept 4 values each: 16 distinct entries of this list segment. Their k-th largest has
-                // k entries at or above it  =>  T = |q|^2 - that value bounds the query's final k-th best score (k <= 16).
-                // Exhaustive probe sets (p.seed_out): the 16 scores go to global memory and are pooled over the query's lists.
+                // a row's four column parts kept 4 accumulator values each: 16 distinct entries of this list segment, each with
+                // u >= 2 a - 1. The k-th largest of these lower bounds has k entries at or above it  =>  T = |q|^2 - that value
+                // bounds the query's final k-th best score (k <= 16).
+                // Exhaustive probe sets (p.seed_out): the 16 score bounds go to global memory and are pooled over the query's lists.
                 named_bar_sync(1, U8_EPI_WARPS * 32);
-                const int row = warp * 32 + lane;   // 512 epilogue threads, one row each
+                const int row = warp * 32 + lane;   // 512 epilogue threads, one row each (384 rows at most)
                 if (row < it.q_count) {
                     const int qn = iq_qn[row];
+                    auto lower_u = [&](int av) { return av > U8_MASKED ? (IP ? av : 2 * av - 1) : INT_MIN; };
                     if (p.seed_out) {
 #pragma unroll
                         for (int pp = 0; pp < U8_PARTS; ++pp) {
                             const int4 x = s_x[pp * U8_ITEM_Q + row];
                             int4 o;
-                            o.x = x.x > INT_MIN ? qn - x.x : INT_MAX; o.y = x.y > INT_MIN ? qn - x.y : INT_MAX;
-                            o.z = x.z > INT_MIN ? qn - x.z : INT_MAX; o.w = x.w > INT_MIN ? qn - x.w : INT_MAX;
+                            o.x = x.x > U8_MASKED ? qn - lower_u(x.x) : INT_MAX; o.y = x.y > U8_MASKED ? qn - lower_u(x.y) : INT_MAX;
+                            o.z = x.z > U8_MASKED ? qn - lower_u(x.z) : INT_MAX; o.w = x.w > U8_MASKED ? qn - lower_u(x.w) : INT_MAX;
                             *reinterpret_cast<int4*>(p.seed_out + ((size_t)(it.q_begin + row) * U8_PARTS + pp) * 4) = o;
                         }
                     } else {
@@ -535,10 +524,11 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
                         for (int pp = 0; pp < U8_PARTS; ++pp) {
                             const int4 x = s_x[pp * U8_ITEM_Q + row];
-                            v[4 * pp + 0] = -(float)x.x; v[4 * pp + 1] = -(float)x.y; v[4 * pp + 2] = -(float)x.z; v[4 * pp + 3] = -(float)x.w;
+                            v[4 * pp + 0] = -(float)lower_u(x.x); v[4 * pp + 1] = -(float)lower_u(x.y);
+                            v[4 * pp + 2] = -(float)lower_u(x.z); v[4 * pp + 3] = -(float)lower_u(x.w);
                         }
                         tc_sort16(v);
-                        const float tk = tc_pick16(v, p.k - 1);   // = -(k-th largest u); 2^31 when fewer than k entries were seen
+                        const float tk = tc_pick16(v, p.k - 1);   // = -(k-th largest bound); 2^31 when fewer than k entries were seen
                         if (tk < 1073741824.f) atomicMin(p.thr + iq_q[row], f32_to_ordered((float)qn + tk));
                     }
                 }
@@ -611,6 +601,27 @@ __global__ void u8_seed_items_kernel(const ScanItem* __restrict__ items, const i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ScanItem it = items[i];
         if (it.list < S) out[atomicAdd(n_out, 1)] = it;
+    }
+}
+
+// the norm digits of the list rows (L2): aug[n, 64] unsigned bytes with  128 (d_0 + .. + d_62) + d_63 = floor(|x|^2 / 2)
+// (greedy: leading digits 255), the B side of the two augmented MMAs whose A side is the constant row (-128 x 63, -1)
+__global__ void shadow_digits_u8_kernel(const float* __restrict__ norm, long long n, uint8_t* __restrict__ aug) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * 16; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i >> 4;
+        const int g = (int)(i & 15);          // which 4 digits of the row
+        const int nv2 = (int)norm[row] >> 1;  // floor(|x|^2 / 2)
+        const int H = nv2 >> 7, L = nv2 & 127;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = 4 * g + c;
+            int dj;
+            if (j == 63) dj = L;
+            else { const int rem = H - 255 * j; dj = rem <= 0 ? 0 : (rem >= 255 ? 255 : rem); }
+            pk |= (uint32_t)dj << (8 * c);
+        }
+        *reinterpret_cast<uint32_t*>(aug + row * 64 + 4 * g) = pk;
     }
 }
 
