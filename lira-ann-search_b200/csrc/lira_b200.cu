@@ -803,6 +803,7 @@ static U8Params u8_params(const lira_index* h, Workspace& ws, const TcStage& sg)
     up.q_mod = sg.q_mod;
     up.nv = h->nv_i;
     up.dbg = ws.n_items.as<int>() + 10;
+    up.trace = nullptr;
     up.qnorm = ws.qnorm.as<float>();
     up.thr = ws.thr.as<uint32_t>();
     up.cand_key = nullptr;
@@ -915,6 +916,11 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
         up.cand_count = tp.cand_count;
         up.cap = cap;
         up.exp = tp.exp;
+        if (getenv("LIRA_U8_TRACE")) {   // debug: clock stamps of CTA 0's first 512 units -> CSV (tools/u8_trace_summary.py)
+            if (int rc = ws.trace.ensure(6 * 512 * 8)) return rc;
+            LIRA_CUDA_OK(cudaMemsetAsync(ws.trace.p, 0, 6 * 512 * 8, st));
+            up.trace = ws.trace.as<long long>();
+        }
         if (up.is_ip) u8_scan_kernel<false, true><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
         else u8_scan_kernel<false, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
     } else
@@ -1173,6 +1179,16 @@ static int tc_search(lira_index* h, const float* d_q, long long ldq, long long Q
         return 0;
     }
     if (trace_path) tc_dump_trace(h, ws, trace_path);
+    if (getenv("LIRA_U8_TRACE") && use_u8) {
+        std::vector<long long> tr(6 * 512);
+        cudaMemcpy(tr.data(), ws.trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(getenv("LIRA_U8_TRACE"), "w")) {
+            fprintf(f, "unit,mma_acc_free,mma_b_ready,mma_issued,epi_ready,epi_loaded,epi_done\n");
+            for (int u = 0; u < 512; ++u)
+                fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", u, tr[u], tr[512 + u], tr[1024 + u], tr[1536 + u], tr[2048 + u], tr[2560 + u]);
+            fclose(f);
+        }
+    }
     if (getenv("LIRA_DEBUG")) tc_debug_stats(h, ws, Q, P, *n_redo);
     h->last_path = 1;
     h->last_redo = *n_redo;

@@ -99,6 +99,8 @@ struct U8Params {
     int cap;
     int k;
     int is_ip;
+    long long* trace;                // LIRA_U8_TRACE: [6][512] SM clock stamps of CTA 0's units (MMA: accumulator free, operands ready, issued;
+                                     //   epilogue warp 0: accumulator ready, loaded, done), or null
     int* dbg;                        // LIRA_TC_EXP bit 6: {groups with a survivor, groups, items, tiles, chunks, units} counters
     int exp;                         // experiments (LIRA_TC_EXP, wrong results, timing only): bit 0 = skip the survivor path,
                                      //   bit 1 = skip the whole epilogue arithmetic, bit 2 = skip the MMAs
@@ -349,7 +351,9 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const uint32_t acc = m & 1u;
                     mbar_wait(&t_empty[acc], ((m >> 1) & 1) ^ 1u);
                     tc_fence_after();
+                    if (p.trace && blockIdx.x == 0 && m < 512 && lane == 0) p.trace[0 * 512 + m] = clock64();
                     if (t == 0) { mbar_wait(&b_full[bs.stage], bs.phase); tc_fence_after(); }
+                    if (p.trace && blockIdx.x == 0 && m < 512 && lane == 0) p.trace[1 * 512 + m] = clock64();
                     const uint32_t d_tmem = tmem_base + acc * U8_NS;
                     const uint32_t a_addr = sA_u32 + (uint32_t)((gm + t) % (uint32_t)U8_NT) * U8_KBLK_BYTES;
                     if (elect_one() && !(p.exp & 4)) {
@@ -363,6 +367,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     __syncwarp();
                     if (elect_one()) tc_commit(&t_full[acc]);
                     __syncwarp();
+                    if (p.trace && blockIdx.x == 0 && m < 512 && lane == 0) p.trace[2 * 512 + m] = clock64();
                 }
                 if (elect_one()) tc_commit(&b_empty[bs.stage]);   // the chunk's slot is free once every MMA above has read it
                 __syncwarp();
@@ -410,6 +415,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     const uint32_t acc = m & 1u;
                     const uint32_t par = (m >> 1) & 1u;
                     mbar_wait_addr(t_full_u32 + acc * 8, par);
+                    if (p.trace && blockIdx.x == 0 && m < 512 && threadIdx.x == 0) p.trace[3 * 512 + m] = clock64();
                     // a warp whose 32 rows of this tile are all padding only keeps the accumulator handshake going
                     if (t * U8_M + quad * 32 >= it.q_count) {
                         if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
@@ -434,6 +440,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_addr(t_empty_u32 + acc * 8);
+                            if (p.trace && blockIdx.x == 0 && m < 512 && threadIdx.x == 0) p.trace[4 * 512 + m] = clock64();
                         }
                         if (p.exp & 2) continue;
                         int r[32];
@@ -498,6 +505,7 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         }
                     }
                     if (SEED) s_x[part * U8_ITEM_Q + row] = make_int4(a[0], a[1], a[2], a[3]);
+                    if (p.trace && blockIdx.x == 0 && m < 512 && threadIdx.x == 0) p.trace[5 * 512 + m] = clock64();
                 }
             }
             if (SEED) {
