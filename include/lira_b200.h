@@ -247,7 +247,7 @@ int lira_index_last_redo(const lira_index_t* h); /* queries of the last tensor-c
                                                     overflowed and that were answered by the CUDA-core scan */
 int lira_index_tensor_core_eligible(const lira_index_t* h);
 int lira_index_tensor_core_mode(const lira_index_t* h);
-/* Byte-valued data (mode 1 with every value an integer in [0, 255], d <= 256) additionally qualifies for the integer
+/* Byte-valued data (mode 1 with every value an integer in [0, 255], d <= 128) additionally qualifies for the integer
  * tensor-core scan (tcgen05.mma kind::i8 over a one-byte-per-component copy of the rows, int32 accumulators: exact).
  * It is what exhaustive probe sets (lira_knn*, compute_knn.cpp:208-259) run by default; threshold / top-n / explicit probe
  * sets use it when LIRA_U8_SEARCH=1 is set in the environment. last_scan_kind: 0 CUDA cores, 1 fp16 tensor-core scan,
