@@ -189,6 +189,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (its
+// CTAs become resident and run their own prologue) while the previous kernel of the stream is still draining. pdl_wait()
+// returns once that kernel has completed and its writes are visible: EVERY thread of such a kernel executes it before the
+// first access to anything another kernel produces or still reads, and before it can exit (completion of this grid then
+// implies completion of every earlier one). pdl_launch() lets the NEXT kernel of the stream be scheduled as soon as every
+// CTA of this one has issued it. Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #endif  // __CUDACC__
 
 }  // namespace lira

@@ -75,28 +75,36 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const PrepParams p) {
 }
 
 // block-wide exclusive scan of int counts into long long offsets (n + 1 entries); every thread of the 1024-thread CTA calls it
-template <class Load>
-__device__ __forceinline__ void block_exclusive_scan_1024(Load in, long long* out, int n, long long* warp_sum, long long* carry_s) {
+// `raw` is a plain load (all of a thread's loads are issued together), `in` turns the loaded value into the count (it may have
+// side effects: stores and atomics, which would otherwise serialise the loads into one global round trip per element).
+// Element layout: a warp owns 256 consecutive elements of a pass and lane l takes elements l, l + 32, ..: every load and store
+// instruction of a warp touches ONE contiguous run (8 consecutive elements per THREAD made each instruction touch 32 sectors
+// in 8-16 cache lines, and the single CTA spent its time queueing in the load/store unit). Counts per warp pass stay below 2^31.
+template <class Raw, class Load>
+__device__ __forceinline__ void block_exclusive_scan_1024(Raw raw, Load in, long long* out, int n, long long* warp_sum, long long* carry_s) {
     constexpr int PER = 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) *carry_s = 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024 * PER) {
-        const int i0 = base + threadIdx.x * PER;
-        int v[PER];
-        long long tsum = 0;
+        const int i0 = base + warp * (32 * PER) + lane;   // element j of this thread: i0 + 32 j
+        int v[PER], inc[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] = (i0 + 32 * j < n) ? raw(i0 + 32 * j) : 0;
+        int run = 0;   // elements of this warp before row j
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            v[j] = (i0 + j < n) ? in(i0 + j) : 0;
-            tsum += v[j];
-        }
-        long long x = tsum;
+            v[j] = (i0 + 32 * j < n) ? in(i0 + 32 * j, v[j]) : 0;
+            int x = v[j];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            inc[j] = run + x;   // inclusive prefix inside the warp's 256 elements
+            run += __shfl_sync(0xffffffffu, x, 31);
         }
-        if (lane == 31) warp_sum[warp] = x;
+        if (lane == 31) warp_sum[warp] = run;
         __syncthreads();
         if (warp == 0) {
             long long w = warp_sum[lane];
@@ -109,12 +117,10 @@ __device__ __forceinline__ void block_exclusive_scan_1024(Load in, long long* ou
         }
         __syncthreads();
         const long long carry = *carry_s;
-        long long before = carry + (warp ? warp_sum[warp - 1] : 0) + (x - tsum);
+        const long long before = carry + (warp ? warp_sum[warp - 1] : 0);
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            if (i0 + j < n) out[i0 + j] = before;
-            before += v[j];
-        }
+        for (int j = 0; j < PER; ++j)
+            if (i0 + 32 * j < n) out[i0 + 32 * j] = before + (inc[j] - v[j]);
         __syncthreads();
         if (threadIdx.x == 1023) *carry_s = carry + warp_sum[31];
         __syncthreads();
@@ -144,14 +150,16 @@ struct FinishSelectParams {
 };
 
 __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectParams p) {
+    pdl_wait();
+    pdl_launch();
     __shared__ long long warp_sum[32];
     __shared__ long long carry_s;
     __shared__ int iwarp_sum[32];
     __shared__ int icarry_s;
+    __shared__ unsigned long long stats_s[2];
     // probe offsets over the queries; the loader clamps a query's count to the cap (flagging the truncation) and gives a query
     // without any selection its argmax (mode 1, search.cpp:456-466), which also enters the partition histogram
-    block_exclusive_scan_1024([&](int q) {
-        int n = p.nsel[q];
+    block_exclusive_scan_1024([&](int q) { return __ldcg(p.nsel + q); }, [&](int q, int n) {
         if (n > p.cap) { atomicMax(p.trunc_flag + 1, n); n = p.cap; *p.trunc_flag = 1; }
         if (n == 0 && p.mode == 1) {
             const int b = (int)(0xFFFFFFFFu - (uint32_t)(p.rowbest[q] & 0xFFFFFFFFull));
@@ -162,25 +170,31 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
         p.nsel[q] = n;
         return n;
     }, p.probe_offsets, p.Q, warp_sum, &carry_s);
-    block_exclusive_scan_1024([&](int b) { return p.list_count[b]; }, p.group_offsets, p.B, warp_sum, &carry_s);
+    block_exclusive_scan_1024([&](int b) { return p.list_count[b]; }, [&](int, int c) { return c; }, p.group_offsets, p.B, warp_sum, &carry_s);
     // work items: lists in size order, each list's group cut into tiles of `tile` queries (build_items_kernel's arithmetic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) icarry_s = 0;
+    if (threadIdx.x == 0) { icarry_s = 0; stats_s[0] = 0; stats_s[1] = 0; }
     __syncthreads();
     for (int base = 0; base < p.B; base += 1024) {
         const int i = base + threadIdx.x;
         int b = 0, g = 0, cnt = 0, nseg = 1;
+        unsigned long long st_rows = 0, st_pairs = 0;
         if (i < p.B) {
             b = p.list_order[i];
-            g = (int)(p.group_offsets[b + 1] - p.group_offsets[b]);
+            g = p.list_count[b];   // (= group_offsets[b + 1] - group_offsets[b]: one 4-byte gather instead of two 8-byte ones)
             cnt = (g + p.tile - 1) / p.tile;
             const unsigned long long nb = (unsigned long long)(p.list_offsets[b + 1] - p.list_offsets[b]);
-            if (g > 0 && p.stats) {
-                atomicAdd(p.stats + 0, nb);
-                atomicAdd(p.stats + 1, nb * (unsigned long long)g);
-            }
+            if (g > 0) { st_rows = nb; st_pairs = nb * (unsigned long long)g; }
             if (p.seg_rows > 0) { nseg = (int)((nb + p.seg_rows - 1) / p.seg_rows); if (nseg < 1) nseg = 1; cnt *= nseg; }
         }
+        // {E_p, pairs}: one shared-memory atomic per warp (1024 threads adding to ONE global address are 2048 serialised L2
+        // operations: they were most of this kernel's time)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_rows += shfl_u64(st_rows, lane ^ o);
+            st_pairs += shfl_u64(st_pairs, lane ^ o);
+        }
+        if (lane == 0 && (st_rows | st_pairs)) { atomicAdd(&stats_s[0], st_rows); atomicAdd(&stats_s[1], st_pairs); }
         int x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -218,7 +232,10 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
         if (threadIdx.x == 1023) icarry_s = carry + iwarp_sum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *p.n_items = icarry_s;
+    if (threadIdx.x == 0) {
+        *p.n_items = icarry_s;
+        if (p.stats) { atomicAdd(p.stats + 0, stats_s[0]); atomicAdd(p.stats + 1, stats_s[1]); }
+    }
 }
 
 struct ScatterQueriesParams {
@@ -247,10 +264,15 @@ struct ScatterQueriesParams {
     int Q;
 };
 
-__global__ void __launch_bounds__(256) scatter_queries_kernel(const ScatterQueriesParams p) {
+__global__ void __launch_bounds__(256, 8) scatter_queries_kernel(const ScatterQueriesParams p) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= p.Q) return;
+    // (the first 32 probe slots of the row are requested together with the count: one global round trip less on the
+    //  chain count -> list id -> returning atomic -> stores that a warp is waiting on most of the time)
+    const int sel_first = lane < p.cap ? p.sel[(size_t)q * p.cap + lane] : 0;
     const int n = p.nsel[q];
     const long long po = p.probe_offsets[q];
     // this lane's part of the fp16 row: 4 values per lane and 128-column block (d <= 128: one block, kept in registers)
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(256) scatter_queries_kernel(const ScatterQueri
         const int j = j0 + lane;
         int pos = 0;
         if (j < n) {
-            const int b = p.sel[(size_t)q * p.cap + j];
+            const int b = j0 == 0 ? sel_first : p.sel[(size_t)q * p.cap + j];
             pos = (int)p.group_offsets[b] + atomicAdd(p.cursor + b, 1);
             p.group_queries[pos] = q;
             if (p.cand_count) p.cand_count[pos] = 0;

@@ -35,6 +35,28 @@ static std::atomic<long long> g_launches{0};
         LIRA_CUDA_OK(cudaGetLastError());                                                      \
     } while (0)
 
+// Kernel launch with programmatic dependent launch (see pdl_wait in common.cuh): the kernel may be scheduled while the
+// previous kernel of the stream drains; it calls pdl_wait() before it touches anything that kernel produces. Only used for
+// kernels that do so on every thread. LIRA_NO_PDL=1 launches them fully serialised (A/B timing).
+static bool pdl_enabled() {
+    static const bool on = getenv("LIRA_NO_PDL") == nullptr;
+    return on;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int grid_for(long long n, int block, int cap = 148 * 8) {
     long long g = (n + block - 1) / block;
@@ -423,7 +445,7 @@ static int launch_tc_dense(const float* a_h, const float* a_l, long long M, int 
     if (int rc = make_tmap(&tm_al, a_l, M, K, lda)) return rc;
     const long long tiles = ((M + TC_M - 1) / TC_M) * ((N + TC_N - 1) / TC_N);
     const int grid = (int)std::min<long long>(tiles, num_sms);
-    tc_dense_kernel<EPI><<<grid, TD_THREADS, TD_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_bh, tm_bl, tp);
+    LIRA_CUDA_OK(launch_pdl(tc_dense_kernel<EPI>, dim3(grid), dim3(TD_THREADS), TD_SMEM_BYTES, st, tm_ah, tm_al, tm_bh, tm_bl, tp));
     LIRA_LAUNCH_CHECK();
     return 0;
 }
@@ -863,7 +885,8 @@ static int tc_seed_main(lira_index* h, Workspace& ws, const TcStage& sg, cudaStr
         LIRA_LAUNCH_CHECK();
         return 0;
     }
-    tc_scan_kernel<true, false><<<h->num_sms, tc_threads(true), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, sp);
+    LIRA_CUDA_OK(launch_pdl(tc_scan_kernel<true, false>, dim3(h->num_sms), dim3(tc_threads(true)), TC_SMEM_BYTES, st, *sg.tmap_q, h->tmap16,
+                            h->tmap_vaug, h->tmap_aaug, sp));
     LIRA_LAUNCH_CHECK();
     return 0;
 }
@@ -925,7 +948,8 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
         else u8_scan_kernel<false, false><<<h->num_sms, U8_THREADS, u8_smem_bytes(false), st>>>(*sg.tmap_q, h->tmap8, h->tmap_vaug8, h->tmap_aaug8, up);
     } else
     if (tp.trace) tc_scan_kernel<false, true><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
-    else tc_scan_kernel<false, false><<<h->num_sms, tc_threads(false), TC_SMEM_BYTES, st>>>(*sg.tmap_q, h->tmap16, h->tmap_vaug, h->tmap_aaug, tp);
+    else LIRA_CUDA_OK(launch_pdl(tc_scan_kernel<false, false>, dim3(h->num_sms), dim3(tc_threads(false)), TC_SMEM_BYTES, st, *sg.tmap_q, h->tmap16,
+                                 h->tmap_vaug, h->tmap_aaug, tp));
     LIRA_LAUNCH_CHECK();
     if (h->timing) LIRA_CUDA_OK(cudaEventRecord(h->ev[1], st));
     // ---- refine ----
@@ -934,11 +958,11 @@ static int tc_filter_refine(lira_index* h, Workspace& ws, const TcStage& sg, cud
                     h->vecs, (long long)h->ds, sg.d_q, sg.ldq, h->d, ws.qnorm.as<float>(), h->tc_sigma * h->tc_sigma, sg.margin_c, sg.margin_abs,
                     1.0f / (h->tc_sigma * h->tc_sigma)};
     const int warps = 8;
-    if (parts == 1 && k <= 32) refine_topk_kernel<1, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else if (parts == 1) refine_topk_kernel<4, false, 1><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else if (approx) refine_topk_kernel<1, true><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else if (k <= 32) refine_topk_kernel<1, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
-    else refine_topk_kernel<4, false><<<(int)((Q + warps - 1) / warps), warps * 32, 0, st>>>(rp);
+    if (parts == 1 && k <= 32) LIRA_CUDA_OK(launch_pdl(refine_topk_kernel<1, false, 1>, dim3((unsigned)((Q + warps - 1) / warps)), dim3(warps * 32), 0, st, rp));
+    else if (parts == 1) LIRA_CUDA_OK(launch_pdl(refine_topk_kernel<4, false, 1>, dim3((unsigned)((Q + warps - 1) / warps)), dim3(warps * 32), 0, st, rp));
+    else if (approx) LIRA_CUDA_OK(launch_pdl(refine_topk_kernel<1, true>, dim3((unsigned)((Q + warps - 1) / warps)), dim3(warps * 32), 0, st, rp));
+    else if (k <= 32) LIRA_CUDA_OK(launch_pdl(refine_topk_kernel<1, false>, dim3((unsigned)((Q + warps - 1) / warps)), dim3(warps * 32), 0, st, rp));
+    else LIRA_CUDA_OK(launch_pdl(refine_topk_kernel<4, false>, dim3((unsigned)((Q + warps - 1) / warps)), dim3(warps * 32), 0, st, rp));
     LIRA_LAUNCH_CHECK();
     if (h->timing) { LIRA_CUDA_OK(cudaEventRecord(h->ev[5], st)); h->scan_total_valid = true; }
     return 0;
@@ -1382,7 +1406,7 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     FinishSelectParams fp{ws.nsel.as<int>(), ws.sel.as<int>(), cap, fs.mode, ws.top1.as<unsigned long long>(), ws.list_count.as<int>(),
                           (int)Q, B, ws.probe_offsets.as<long long>(), ws.group_offsets.as<long long>(), fl_dev + 2, h->d_list_order,
                           h->d_offsets, u8 ? h->u8_item_q() : TC_M, u8 ? U8_SEG_ROWS : 0, ws.items.as<ScanItem>(), ctl, (unsigned long long*)((char*)ws.n_items.p + 64)};
-    finish_select_kernel<<<1, 1024, 0, st>>>(fp);
+    LIRA_CUDA_OK(launch_pdl(finish_select_kernel, dim3(1), dim3(1024), 0, st, fp));
     LIRA_LAUNCH_CHECK();
     if (int rc = save_stats(h, ws, st)) return rc;
     const bool is_ip = h->metric == LIRA_METRIC_IP;
@@ -1392,7 +1416,7 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
                             ws.probe_slot.as<int>(), ws.probe_ids.as<int>(), ws.gq.as<__half>(), h->d16, qscale, u8 ? ws.cand_count.as<int>() : nullptr, u8 ? ws.gq.as<uint8_t>() : nullptr, h->d8,
                             (approx || u8) ? fl_dev : nullptr,
                             d_nprobe, d_cmp, (int)Q};
-    scatter_queries_kernel<<<qgrid, warps * 32, 0, st>>>(sc);
+    LIRA_CUDA_OK(launch_pdl(scatter_queries_kernel, dim3(qgrid), dim3(warps * 32), 0, st, sc));
     LIRA_LAUNCH_CHECK();
     CUtensorMap tmap_q;
     if (u8) { if (int rc = make_tmap_u8(&tmap_q, ws.gq.p, P, h->d8, h->d8)) return rc; }

@@ -90,6 +90,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // (the prologue above touches nothing another kernel produces)
+    pdl_launch();
 
     const int tiles_n = (p.N + TC_N - 1) / TC_N;
     const int tiles_m = (p.M + TC_M - 1) / TC_M;

@@ -264,6 +264,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // (the prologue above touches nothing another kernel produces)
+    pdl_launch();
     const int n_items = *p.n_items;
     const int nk = p.nk;
     // A tiles: with d <= 128 (nk <= 2) two query tiles fit, so the next work item's queries load while this item's MMAs run
@@ -868,6 +870,8 @@ struct RefineParams {
 
 template <int S, bool EXACT, int PARTS = TC_PARTS>
 __global__ void __launch_bounds__(256) refine_topk_kernel(const RefineParams p) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= p.Q) return;

@@ -190,6 +190,8 @@ u8_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // (the prologue above touches nothing another kernel produces)
+    pdl_launch();
     const int n_items = *p.n_items;
 
     if (warp == W_ALLOC) {
