@@ -824,6 +824,7 @@ def run_sift1m(args, rank, world, local, dist, log):
         "data": "synthetic", "config": config_sift1m(wl, op, k, world, args.shard), "recall_at_10": rec,
         "e2e": {"value": jobs * Q / e2e["pinned_s"], "unit": "queries/s", "h2d_bytes_per_step": int(Q * d * 4),
                 "d2h_bytes_per_step": int(Q * k * 12 + Q * 12), "pageable_value": jobs * Q / e2e["pageable_s"],
+                "steps_timed": e2e["pinned_s_steps"], "median_step_value": jobs * Q / e2e["pinned_s_median"],
                 "api": e2e["api"]},
         "gpu_launches": int(launches), "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -916,6 +917,8 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             s = float(t.item())
         res[name] = s
+        res[name + "_median"] = float(np.median(ts[3:]))
+        res[name + "_steps"] = len(ts) - 3
         res["ids"] = ids
     return res
 

@@ -157,8 +157,12 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
     __shared__ int iwarp_sum[32];
     __shared__ int icarry_s;
     __shared__ unsigned long long stats_s[2];
+    // The prefix over the queries and the partition side (prefix over the partitions + work items) are independent as long as
+    // no query needs the argmax fix-up (mode 0): the launch then has TWO CTAs, one per half; mode 1 runs both in one CTA.
+    const bool do_queries = gridDim.x == 1 || blockIdx.x == 0, do_lists = gridDim.x == 1 || blockIdx.x == 1;
     // probe offsets over the queries; the loader clamps a query's count to the cap (flagging the truncation) and gives a query
     // without any selection its argmax (mode 1, search.cpp:456-466), which also enters the partition histogram
+    if (do_queries)
     block_exclusive_scan_1024([&](int q) { return __ldcg(p.nsel + q); }, [&](int q, int n) {
         if (n > p.cap) { atomicMax(p.trunc_flag + 1, n); n = p.cap; *p.trunc_flag = 1; }
         if (n == 0 && p.mode == 1) {
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(1024) finish_select_kernel(const FinishSelectP
         p.nsel[q] = n;
         return n;
     }, p.probe_offsets, p.Q, warp_sum, &carry_s);
+    if (!do_lists) return;
     block_exclusive_scan_1024([&](int b) { return p.list_count[b]; }, [&](int, int c) { return c; }, p.group_offsets, p.B, warp_sum, &carry_s);
     // work items: lists in size order, each list's group cut into tiles of `tile` queries (build_items_kernel's arithmetic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -1406,7 +1406,7 @@ static int fused_enqueue(lira_index* h, lira_model* m, const float* d_q, long lo
     FinishSelectParams fp{ws.nsel.as<int>(), ws.sel.as<int>(), cap, fs.mode, ws.top1.as<unsigned long long>(), ws.list_count.as<int>(),
                           (int)Q, B, ws.probe_offsets.as<long long>(), ws.group_offsets.as<long long>(), fl_dev + 2, h->d_list_order,
                           h->d_offsets, u8 ? h->u8_item_q() : TC_M, u8 ? U8_SEG_ROWS : 0, ws.items.as<ScanItem>(), ctl, (unsigned long long*)((char*)ws.n_items.p + 64)};
-    LIRA_CUDA_OK(launch_pdl(finish_select_kernel, dim3(1), dim3(1024), 0, st, fp));
+    LIRA_CUDA_OK(launch_pdl(finish_select_kernel, dim3(fs.mode == 0 ? 2 : 1), dim3(1024), 0, st, fp));
     LIRA_LAUNCH_CHECK();
     if (int rc = save_stats(h, ws, st)) return rc;
     const bool is_ip = h->metric == LIRA_METRIC_IP;

@@ -780,3 +780,56 @@ def test_byte_scan_without_seed_overflows_to_the_exact_path(L, monkeypatch):
     assert index.last_scan_kind == "u8" and index.last_redo == len(x_q)
     I_ref, D_ref, cmp_ref = O.search(off, ids, vecs, x_q, poff, pids, 10, O.L2, O.F64, 1)
     assert np.array_equal(I, I_ref) and np.array_equal(D, D_ref) and np.array_equal(cmp_, cmp_ref)
+
+
+_PDL_CHILD = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import lira_ann_search_b200 as L
+z = np.load(sys.argv[2])
+index = L.LiraIndex.from_csr(z["x_d"], z["off"], z["ids"], int(z["metric"]))
+model = L.LiraModel.from_arrays(z["cent"], z["mean"], z["scale"], [z[f"w{i}"] for i in range(12)])
+out = {}
+for j, (mode, value) in enumerate(zip(z["modes"], z["values"])):
+    D, I, n, c = index.probe_search(model, z["x_q"], int(mode), float(value), 10)
+    assert index.last_path == "tensor-core"
+    out[f"D{j}"], out[f"I{j}"], out[f"n{j}"], out[f"c{j}"] = D, I, n, c
+np.savez(sys.argv[3], **out)
+'''
+
+
+def test_programmatic_launch_chain_changes_nothing(L, tmp_path):
+    """The batch's kernels are chained by programmatic dependent launch (each kernel's CTAs start while the previous one
+    drains and wait in griddepcontrol.wait): a process with LIRA_NO_PDL=1 (every launch fully serialised) must produce the
+    same bytes -- ids, distances, nprobe, cmp -- for both selection modes."""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.RandomState(31)
+    B, d, k = 100, 64, 10
+    x_d, x_q = synth(30000, d, 700, seed=17, integer=True)
+    cl = random_lists(len(x_d), B, rng, redundancy=0.3)
+    off, ids, vecs = lists_csr(x_d, cl)
+    shapes = [(128, B), (128,), (64, 128), (64,), (128, d), (128,), (64, 128), (64,), (128, 128), (128,), (B, 128), (B,)]
+    w = [(rng.randn(*s) * (0.5 / np.sqrt(s[-1]) if len(s) == 2 else 0.1)).astype(np.float32) for s in shapes]
+    w[4] = (w[4] / 128.0).astype(np.float32)
+    cent = x_d[rng.choice(len(x_d), B, replace=False)]
+    f = O.features_cpp(x_d[:2000], cent, None, None)
+    mean, scale = f.mean(0).astype(np.float32), f.std(0).astype(np.float32)
+    model = L.LiraModel.from_arrays(cent, mean, scale, w)
+    s = model.scores(x_q)
+    modes = [L.SELECT_GT, L.SELECT_GE_ARGMAX]
+    values = [float(np.quantile(s, 0.9)), float(np.quantile(s.max(1), 0.5))]
+    inp, outp = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, x_d=x_d, x_q=x_q, off=off, ids=ids, metric=O.L2, cent=cent, mean=mean, scale=scale, modes=np.array(modes),
+             values=np.array(values), **{f"w{i}": w[i] for i in range(12)})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LIRA_NO_PDL="1")
+    subprocess.run([sys.executable, "-c", _PDL_CHILD, root, inp, outp], check=True, env=env, timeout=600)
+    z = np.load(outp)
+    index = L.LiraIndex.from_csr(x_d, off, ids, O.L2)
+    for j, (mode, value) in enumerate(zip(modes, values)):
+        D, I, n, c = index.probe_search(model, x_q, mode, value, k)
+        assert index.last_path == "tensor-core"
+        assert np.array_equal(I, z[f"I{j}"]) and np.array_equal(D, z[f"D{j}"])
+        assert np.array_equal(n, z[f"n{j}"]) and np.array_equal(c, z[f"c{j}"])
