@@ -134,7 +134,9 @@ int lira_probe_search_dev(lira_index_t* h, lira_model_t* m, const float* d_q, in
  * Host-buffer form with four staging slots (slot in [0, 4)): submit(slot) copies the queries in (pinned or pageable source) on a copy
  * stream, enqueues the batch and the copy of its results into pinned memory on a second copy stream; wait(slot) returns
  * the results in the caller's arrays. With submit(i+1) issued before wait(i), the copies of one batch overlap the
- * kernels of the other. */
+ * kernels of the other. A pageable query array is staged through a pinned buffer of the handle; a pinned one is uploaded
+ * from directly unless the first timed batches show its upload taking more than 0.7 of the time of the batch's kernels (pages pinned by
+ * another allocator can upload at half the rate), in which case it is staged too (LIRA_STAGE_PINNED=0 / 1 fixes the choice). */
 int lira_probe_search_enqueue_dev(lira_index_t* h, lira_model_t* m, const float* d_q, int64_t ldq, int64_t Q,
                                   int mode, double value, int k, int dedup, float* d_D, int64_t* d_I,
                                   int32_t* d_nprobe, int64_t* d_cmp, void* stream);
