@@ -852,6 +852,7 @@ def measure_e2e(args, index, model, x_q, thr, k, gather_merge, flush, dist, dev)
     import torch
     import lira_ann_search_b200 as L
     Q, d = x_q.shape
+    index.set_timing(False)   # (a caller does not ask for the per-kernel events: they sit between the launches of a batch)
     pin_q = torch.empty((Q, d), dtype=torch.float32).pin_memory()
     pin_q.copy_(torch.as_tensor(x_q))
     res = {}
