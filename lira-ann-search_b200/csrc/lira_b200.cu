@@ -2451,6 +2451,16 @@ int lira_probe_search_wait(lira_index_t* h, int slot, float* D, int64_t* I, int3
                     // (staged as soon as the upload comes within 30 % of the kernels' time: measured on a host whose direct upload
                     //  took 0.41 ms against 0.49 ms of kernels, staging was the faster pipeline, 21.2 M against 20.2 M queries/s)
                     h->stage_pinned = h->direct_h2d_ms > 0.7f * h->direct_compute_ms ? 1 : 0;
+                    if (h->stage_pinned == 1) {   // every slot's staging buffer now, not in the middle of the caller's steady state
+                        const size_t bq = (size_t)s.pb.Q * h->d * 4;
+                        for (auto& sl : h->slots)
+                            if (bq > sl.pin_in_cap && !sl.busy) {
+                                if (sl.pin_in) cudaFreeHost(sl.pin_in);
+                                sl.pin_in = nullptr; sl.pin_in_cap = 0;
+                                if (cudaHostAlloc(&sl.pin_in, bq + bq / 4, cudaHostAllocDefault) == cudaSuccess) sl.pin_in_cap = bq + bq / 4;
+                                else { sl.pin_in = nullptr; cudaGetLastError(); }
+                            }
+                    }
                     if (getenv("LIRA_DEBUG_STAGE"))
                         fprintf(stderr, "[lira] pinned query arrays: upload %.3f ms vs kernels %.3f ms per batch -> %s\n", h->direct_h2d_ms / 3,
                                 h->direct_compute_ms / 3, h->stage_pinned ? "staged through the handle's own pinned buffer" : "uploaded directly");

@@ -56,7 +56,7 @@ with open(os.path.join(P, f"{rnd}_scan_ncu_metrics.txt"), "w") as f:
             hsh = hashlib.sha256()
             cs = os.path.join(ROOT, "lira-ann-search_b200", "csrc")
             for fn in sorted(os.listdir(cs)):
-                if fn.endswith((".cu", ".cuh")):
+                if fn.endswith(".cuh"):   # (the kernels live in the .cuh files; lira_b200.cu is host code)
                     hsh.update(open(os.path.join(cs, fn), "rb").read())
             traffic = {"kernel": "tc_scan_kernel<false, false>", "workload": "sift1m-shape", "source_hash": hsh.hexdigest()[:16],
                        "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
